@@ -1,0 +1,56 @@
+"""Shared helpers for the test-suite (synthetic generators of SURVEY.md s.8d, tolerances)."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASE_NAMES = ["DoubleIntegrator", "Cartpole_SwingUp", "Quadrotor", "Segway_Balance"]
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def s2_instance(seed, d, m, N):
+    """Synthetic HOP-LQR instance S2: draw order all A, all B, all Q, R, z0, w."""
+    r = np.random.default_rng(seed)
+    A = np.eye(d)[None] + 0.05 * r.standard_normal((N, d, d)) / np.sqrt(d)
+    B = 0.05 * r.standard_normal((N, d, m))
+    Q = np.stack([np.diag(r.uniform(0.5, 2.0, d)) for _ in range(N)])
+    R = np.diag(r.uniform(0.05, 0.5, m))
+    z0 = r.standard_normal(d)
+    w = r.uniform(0.01, 0.1)
+    QT = np.tile(50.0 * np.eye(d), (N, 1, 1))
+    return A, B, Q, R, z0, w, QT
+
+
+def s2_batch(seeds, d, m, N):
+    inst = [s2_instance(s, d, m, N) for s in seeds]
+    A = np.stack([i[0] for i in inst]); B = np.stack([i[1] for i in inst]); Q = np.stack([i[2] for i in inst])
+    R = np.stack([i[3] for i in inst]); z0 = np.stack([i[4] for i in inst]); w = np.array([i[5] for i in inst])
+    QT = np.stack([i[6] for i in inst])
+    return A, B, Q, R, z0, w, QT
+
+
+def s1_x0(B, seed=0):
+    """S1 workload: quadrotor x0_b = x0 + sigma * xi_b (run_suite.py:72 sigma)."""
+    x0 = np.zeros(12); x0[:3] = 2.0
+    sigma = np.array([0.4, 0.4, 0.4] + [0.0] * 9)
+    xi = np.random.default_rng(seed).standard_normal((B, 12))
+    return x0[None] + sigma[None] * xi
+
+
+# Per-case tolerance of the selection curve J(T) against the reference's own output.
+# The reference curve is reproducible only to this level across BLAS builds:
+# (window rel tol, rel tol at T*, allowed |T - T_ref|)
+J_TOL = {
+    "DoubleIntegrator": (1e-5, 1e-7, 0),
+    "Quadrotor": (1e-6, 1e-8, 0),
+    "Segway_Balance": (None, 1e-6, 0),      # uncontrolled diverging tail beyond T*: window is O(0.1) noise
+    "Cartpole_SwingUp": (None, 1e-3, 1),    # argmin gap 1.3e-5 < reference noise 3e-5: T* ill-posed
+}
