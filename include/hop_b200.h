@@ -1,0 +1,120 @@
+/* hop_b200.h -- C-ABI of libhop_b200.so: the B200-native HOP horizon-selection hot path.
+ *
+ * The reference (dmmsjtu-umich/time-opt-ilqr) is pure Python and has no FFI; its boundary for this
+ * path is the Python function API.  Each entry point below names the reference function(s) it
+ * replaces (file:line).  The host-side mirror of those Python signatures lives in
+ * time-opt-ilqr_b200/dropin/ and calls these symbols through ctypes.
+ *
+ * Conventions
+ *   - fp64, row-major, batch-major: [B][N][rows][cols].  Unless an entry point says "host", every
+ *     pointer is a DEVICE pointer owned by the caller; nothing is retained after the call returns.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous
+ *     with respect to the host except the *_host_* variants, which synchronise before returning.
+ *   - Return value: 0 on success, otherwise a cudaError_t value or HOP_E_* (< 0); the message is
+ *     available from hop_last_error_string().  Kernels never trap: per-instance numerical outcomes
+ *     are reported in `status[b]`:
+ *         low byte  0 = ok, 1 = non-finite input to a chol_inv (reference: FloatingPointError,
+ *                   utils.py:40-42,75), 2 = singular LU fallback (reference: LinAlgError, utils.py:93)
+ *         bit 8     some Cholesky attempt failed and the jitter ladder was climbed (utils.py:81-88)
+ *         bit 9     the LU fallback of utils.py:90-93 was taken
+ *   - wrap_mask bit i  <=>  state index i is in the reference's wrap_idx list (utils.py:131-137).
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef HOP_B200_H
+#define HOP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOP_ABI_VERSION 1
+
+enum { HOP_E_BADARG = -1, HOP_E_UNSUPPORTED_DIMS = -2, HOP_E_NO_DEVICE = -3, HOP_E_WORKSPACE = -4 };
+
+/* status word */
+enum { HOP_ST_OK = 0, HOP_ST_NONFINITE = 1, HOP_ST_LINALG = 2, HOP_ST_ERRMASK = 0xff,
+       HOP_ST_FLAG_RETRY = 0x100, HOP_ST_FLAG_LU = 0x200 };
+
+/* selection variants */
+enum { HOP_MODE_EXACT = 0 /* sequential sweep in the reference's operation order */ };
+
+/* device dynamics registry (systems.py closures cannot run on the GPU) */
+enum { HOP_SYS_DOUBLE_INTEGRATOR = 0, /* systems.py:28-50   params [dt]                               */
+       HOP_SYS_CARTPOLE = 1,          /* systems.py:57-112  params [dt,g,m_pole,length,total_mass,pml] */
+       HOP_SYS_QUADROTOR = 2,         /* systems.py:119-230 params [dt,m,g,Ix,Iy,Iz,1/Ix,1/Iy,1/Iz,kv,kw,cos_min,omg_max,norm_max] */
+       HOP_SYS_SEGWAY = 3 };          /* systems.py:303-349 params [dt,A_tau,A_th,B_tau,B_th]           */
+#define HOP_NPARAMS 16
+
+int hop_abi_version(void);
+const char *hop_version(void);
+const char *hop_last_error_string(void);
+/* number of visible CUDA devices (0 => every compute call returns HOP_E_NO_DEVICE) */
+int hop_device_count(void);
+/* 1 if (d, m) is an instantiated augmented-dimension / control-dimension pair */
+int hop_select_supported(int d, int m);
+
+/* horizon_selection.py:36-86 propagator_all_Jt_aug (+ solver.py:522,590 argmin), batched.
+ *   A_aug [B][N][d][d], B_aug [B][N][d][m], Q_aug [B][N][d][d], QT [B][N][d][d] (QT[t-1] = terminal block
+ *   of horizon t), R_inv [B][m][m] (the R_inv_cached argument), z0 [B][d].
+ *   w_explicit: NULL, or [B] -- argmin is then taken over J(t) + w*t (SURVEY.md s.8d "S2"); J_out is
+ *   always the raw curve the reference returns.
+ *   Outputs: J_out [B][T_max] (index t-1), Tstar_out [B] = argmin over t in [T_min, T_max] (first
+ *   minimum, NaN wins, as np.argmin), Jstar_out [B], status [B]. */
+int hop_select_f64(int B, int N, int d, int m, int T_min, int T_max,
+                   const double *A_aug, const double *B_aug, const double *Q_aug, const double *R_inv,
+                   const double *z0, const double *QT, const double *w_explicit, int mode,
+                   double *J_out, int *Tstar_out, double *Jstar_out, int *status, void *stream);
+
+/* Fused form: augmented.py:10-60 build_augmented_sequence_QR + augmented.py:63-87
+ * build_terminal_aug_list + horizon_selection.py:36-86 + argmin in one kernel; the (n+1)^2 blocks are
+ * built in shared memory and never written to HBM.
+ *   A [B][N][n][n], Bm [B][N][n][m] (linearisation), a_resid [B][N][n] or NULL (= 0, which is what
+ *   linearization.py:269-270 yields on a consistent rollout), X [B][N+1][n], U [B][N][m]
+ *   (u_batch_stride = N*m) or one shared U [N][m] (u_batch_stride = 0), xg [B][n], w [B]; shared case constants u_ref [m], Q [n][n], R [m][m], Qf [n][n] (=
+ *   as_terminal_weight(alpha), utils.py:49-62). */
+int hop_select_fused_f64(int B, int N, int n, int m, int T_min, int T_max,
+                         const double *A, const double *Bm, const double *a_resid, const double *X,
+                         const double *U, long u_batch_stride, const double *xg, const double *w, const double *u_ref,
+                         const double *Q, const double *R, const double *Qf, unsigned wrap_mask,
+                         double q_reg, double rho_reg, int mode,
+                         double *J_out, int *Tstar_out, double *Jstar_out, int *status, void *stream);
+
+/* solver.py:42-62 rollout, batched: X [B][N+1][n] from x0 [B][n], U [B][N][m]
+ * (u_batch_stride = N*m for per-instance controls, 0 when all instances share one U [N][m]).
+ * params: HOP_NPARAMS doubles on the HOST. */
+int hop_rollout_f64(int B, int sys, const double *params_host, int N, const double *x0, const double *U,
+                    long u_batch_stride, double max_state_norm, double *X, void *stream);
+
+/* linearization.py:216-262 (central = 0) / :177-211 (central = 1), batched: A [B][N][n][n], Bm [B][N][n][m]. */
+int hop_linearize_f64(int B, int sys, const double *params_host, int N, const double *X, const double *U,
+                      long u_batch_stride, int central, double epsx, double epsu, double relx, double relu,
+                      double *A, double *Bm, void *stream);
+
+/* Whole selection from initial states (SURVEY.md s.8d workload "S1"): rollout -> forward/central FD
+ * linearisation -> fused selection.  `workspace` must hold hop_select_from_x0_workspace_bytes(...). */
+unsigned long long hop_select_from_x0_workspace_bytes(int B, int N, int n, int m);
+int hop_select_from_x0_f64(int B, int sys, const double *params_host, int N, int T_min, int T_max,
+                           const double *x0, const double *U, long u_batch_stride, const double *xg,
+                           const double *w, const double *u_ref, const double *Q, const double *R,
+                           const double *Qf, unsigned wrap_mask, int central, int mode,
+                           void *workspace, unsigned long long workspace_bytes,
+                           double *J_out, int *Tstar_out, double *Jstar_out, int *status, void *stream);
+
+/* Same, HOST buffers in and out (x0, U, xg, w and the outputs live in host memory; the case
+ * constants too).  Copies, kernels and the final device->host read are issued on one internal
+ * stream and the call returns after they complete.  J_out may be NULL (only T*, J* wanted). */
+int hop_select_from_x0_host_f64(int B, int sys, const double *params_host, int N, int T_min, int T_max,
+                                const double *x0, const double *U, long u_batch_stride, const double *xg,
+                                const double *w, const double *u_ref, const double *Q, const double *R,
+                                const double *Qf, unsigned wrap_mask, int central, int mode,
+                                double *J_out, int *Tstar_out, double *Jstar_out, int *status);
+
+/* Measures the FP64 FMA throughput of the current device with a register-resident DFMA chain
+ * (8 independent accumulators per thread, 2048 threads per SM), timed with CUDA events.  This is
+ * the roofline denominator bench.py reports against (MEASURED_PEAKS.json holds no FP64 figure). */
+int hop_probe_fp64_tflops(int iters, double *tflops_out, double *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,64 @@
+// emul_select.cpp -- host entry points that run the HOP select kernel bodies under the SIMT
+// emulator (test infrastructure; mirrors the grid/slab arithmetic of hop_select.cu).
+#include <cstdlib>
+#include <vector>
+
+#include "hop_select_body.cuh"
+
+namespace {
+template <int D, int M, int G>
+struct GenericJob { const hop::SelectArgs* p; int b0; double* smem; };
+template <int D, int M, int G>
+void generic_lane(void* a) {
+    auto* j = (GenericJob<D, M, G>*)a;
+    const int lane = hop::simt::lane_id();
+    const int slot = lane / G;
+    hop::select_generic_body<D, M, G>(*j->p, j->b0 + slot, j->smem + (size_t)slot * hop::Geo<D, M, G>::SLAB);
+}
+template <int D, int M, int G>
+int run_generic(const hop::SelectArgs& p) {
+    constexpr int GPW = 32 / G;
+    std::vector<double> smem((size_t)GPW * hop::Geo<D, M, G>::SLAB, -7.0);
+    for (int b0 = 0; b0 < p.B; b0 += GPW) {
+        GenericJob<D, M, G> j{&p, b0, smem.data()};
+        if (hop::simt::run_warp(generic_lane<D, M, G>, &j)) return -1;
+    }
+    return 0;
+}
+template <int D, int M, int G>
+struct FusedJob { const hop::FusedArgs* p; int b0; double* smem; const double* cst; };
+template <int D, int M, int G>
+void fused_lane(void* a) {
+    auto* j = (FusedJob<D, M, G>*)a;
+    const int lane = hop::simt::lane_id();
+    const int slot = lane / G;
+    hop::select_fused_body<D, M, G>(*j->p, j->b0 + slot, j->smem + (size_t)slot * hop::Geo<D, M, G>::SLAB, j->cst);
+}
+template <int D, int M, int G>
+int run_fused(const hop::FusedArgs& p) {
+    constexpr int GPW = 32 / G;
+    std::vector<double> smem((size_t)GPW * hop::Geo<D, M, G>::SLAB, -7.0);
+    std::vector<double> cst(hop::FusedConst<D, M>::SIZE, 0.0);
+    hop::fused_const_fill<D, M>(p, cst.data(), 0, 1);
+    for (int b0 = 0; b0 < p.B; b0 += GPW) {
+        FusedJob<D, M, G> j{&p, b0, smem.data(), cst.data()};
+        if (hop::simt::run_warp(fused_lane<D, M, G>, &j)) return -1;
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" int emul_select_generic(int d, int m, const hop::SelectArgs* p) {
+    if (d == 3 && m == 1) return run_generic<3, 1, 4>(*p);
+    if (d == 4 && m == 2) return run_generic<4, 2, 4>(*p);
+    if (d == 5 && m == 1) return run_generic<5, 1, 8>(*p);
+    if (d == 12 && m == 4) return run_generic<12, 4, 16>(*p);
+    if (d == 13 && m == 4) return run_generic<13, 4, 16>(*p);
+    return -2;
+}
+extern "C" int emul_select_fused(int n, int m, const hop::FusedArgs* p) {
+    if (n == 2 && m == 1) return run_fused<3, 1, 4>(*p);
+    if (n == 4 && m == 1) return run_fused<5, 1, 8>(*p);
+    if (n == 12 && m == 4) return run_fused<13, 4, 16>(*p);
+    return -2;
+}

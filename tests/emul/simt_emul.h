@@ -1,0 +1,27 @@
+// simt_emul.h -- TEST INFRASTRUCTURE: run the HOP kernel bodies on the host.
+//
+// The 32 lanes of a warp are cooperative fibers (ucontext); sync()/shfl()/ballot() are barriers
+// among them.  This lets `pytest -m "not gpu"` execute the very same kernel source
+// (time-opt-ilqr_b200/csrc/hop_select_body.cuh, compiled with -DHOP_HOST_EMUL by g++) in a container
+// without a GPU.  It is never linked into the product library and is not a CPU fallback: the
+// product's loader refuses to run without CUDA.
+#pragma once
+#include <cmath>
+#include <cstddef>
+
+#define HOP_DEVICE inline
+#define HOP_DEVICE_NOINLINE
+
+using std::isfinite;
+
+namespace hop { namespace simt {
+int lane_id();
+void sync();
+double shfl(double v, int src_in_group, int width);
+double shfl_xor(double v, int mask, int width);
+unsigned ballot(bool p);
+bool all(bool p);
+// Run fn(arg) once per lane of one emulated warp.  Returns 0, or -1 if lanes exited non-uniformly
+// (some lane still waiting at a barrier when another finished), which on a GPU would be a hang.
+int run_warp(void (*fn)(void*), void* arg);
+}}  // namespace hop::simt

@@ -1,0 +1,61 @@
+"""Runs the CUDA kernel *source* (hop_select_body.cuh) on the host through the fiber-based SIMT
+emulator of tests/emul and checks it against the oracle / reference goldens.  CPU only; this is how
+the kernel logic is exercised in a container without a GPU.  The GPU run of the same checks is in
+tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import emul
+import oracle as O
+from _common import CASE_NAMES, J_TOL, golden, rel, s2_batch
+from hop import cases
+
+
+@pytest.mark.parametrize("d,m,N", [(3, 1, 32), (4, 2, 64), (5, 1, 64), (12, 4, 32), (13, 4, 48)])
+def test_emulated_generic_kernel_matches_oracle_on_s2(d, m, N):
+    A, B, Q, R, z0, w, QT = s2_batch(range(5), d, m, N)      # 5 instances: ragged last warp on every G
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    J, T, Js, st = emul.select_generic(A, B, Q, Rinv, z0, QT, 1, N, w_explicit=w)
+    Jo, sto = O.propagator_batch(A, B, Q, Rinv, z0, QT)
+    assert not st.any() and not sto.any()
+    assert rel(J, Jo) <= 1e-12
+    tot = Jo + w[:, None] * np.arange(1, N + 1)
+    assert np.array_equal(T, np.argmin(tot, axis=1) + 1)
+    assert np.allclose(Js, tot.min(axis=1), rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["DoubleIntegrator", "Segway_Balance", "Quadrotor"])
+def test_emulated_fused_kernel_matches_reference_goldens(name):
+    g = golden("case_" + name)
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case(name, N=int(g["N"]))
+    if name == "Quadrotor":
+        T_max = 64                    # keep the emulation fast; the curve prefix does not depend on T_max
+    n = x0.size
+    J, T, Js, st = emul.select_fused(g["A_fwd"][None], g["B_fwd"][None], g["a_resid"][None], g["X"][None], g["U"][None],
+                                     xg[None], np.array([w]), u_ref, Q, R, O.as_terminal_weight(alpha, n),
+                                     O.wrap_mask(wrap_idx), T_min, T_max)
+    Jr, Tr = g["J_curve0"], int(g["T0"])
+    tol_win, tol_star, dT = J_TOL[name]
+    assert (st[0] & 0xFF) == 0
+    assert abs(int(T[0]) - Tr) <= dT
+    assert abs(J[0, Tr - 1] - Jr[Tr - 1]) <= tol_star * abs(Jr[Tr - 1])
+    if tol_win is not None:
+        assert rel(J[0, T_min - 1:T_max], Jr[T_min - 1:T_max]) <= tol_win
+
+
+def test_emulated_kernel_ladder_fallback_and_nonfinite_status():
+    """Edge cases the reference handles by exceptions / the jitter ladder (utils.py:75,81-93)."""
+    d, m, N = 4, 2, 8
+    A, B, Q, R, z0, w, QT = s2_batch(range(3), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    Q[1, 3] = np.diag([1.0, 1.0, 1.0, -1e-4])        # needs the ladder (PD again once eps >= 1e-3)
+    QT[2, 5] = -np.eye(d)                             # never PD -> LU fallback on (A + 0.1 I)
+    J, T, Js, st = emul.select_generic(A, B, Q, Rinv, z0, QT, 1, N)
+    Jo, sto = O.propagator_batch(A, B, Q, Rinv, z0, QT)
+    assert st[0] == 0 and st[1] == 0x100 and st[2] == 0x300 and not sto.any()
+    assert rel(J, Jo) <= 1e-9
+    A[0, 2, 1, 1] = np.nan
+    J, T, Js, st = emul.select_generic(A, B, Q, Rinv, z0, QT, 1, N)
+    _, sto = O.propagator_batch(A, B, Q, Rinv, z0, QT)
+    assert (st[0] & 0xFF) == 1 and sto[0] == 1        # FloatingPointError in the reference
+    assert (st[1] & 0xFF) == 0 and (st[2] & 0xFF) == 0

@@ -1,0 +1,174 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the reference
+goldens.  Tolerances: T* exact; J within 1e-9 relative on the well-conditioned synthetic family
+(north star), and within the reference's own reproducibility on the augmented cases (J_TOL)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from _common import CASE_NAMES, J_TOL, golden, rel, s1_x0, s2_batch
+from hop import api, cases
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device=DEV)
+
+
+@pytest.mark.parametrize("d,m,N,B", [(3, 1, 32, 9), (4, 2, 64, 33), (5, 1, 64, 7), (12, 4, 128, 5), (13, 4, 128, 6),
+                                     (13, 4, 256, 3), (4, 2, 256, 2)])
+def test_select_generic_matches_oracle_on_s2(d, m, N, B):
+    A, Bm, Q, R, z0, w, QT = s2_batch(range(B), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    sel = api.propagator_all_Jt_aug_batched(_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, N, w_explicit=_t(w))
+    Jo, sto = O.propagator_batch(A, Bm, Q, Rinv, z0, QT, nthreads=4)
+    J = sel.J.cpu().numpy()
+    assert not sel.status.cpu().numpy().any() and not sto.any()
+    assert rel(J, Jo) <= 1e-9                                      # north-star tolerance
+    tot = Jo + w[:, None] * np.arange(1, N + 1)
+    assert np.array_equal(sel.T_star.cpu().numpy(), np.argmin(tot, axis=1) + 1)
+    assert np.allclose(sel.J_star.cpu().numpy(), tot.min(axis=1), rtol=1e-9)
+
+
+def test_select_generic_matches_reference_golden_s2():
+    g = golden("s2_synthetic")
+    from _common import s2_instance
+    for key in g.files:
+        if not key.startswith("J_"):
+            continue
+        d, m, N, s = (int(tok[1:]) for tok in key.split("_")[1:])
+        A, Bm, Q, R, z0, w, QT = s2_instance(s, d, m, N)
+        sel = api.propagator_all_Jt_aug_batched(_t(A[None]), _t(Bm[None]), _t(Q[None]), _t(O.chol_inv(R)), _t(z0),
+                                                _t(QT[None]), 1, N)
+        assert rel(sel.J.cpu().numpy()[0], g[key]) <= 1e-9
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+@pytest.mark.parametrize("traj", ["nominal", "converged"])
+def test_select_fused_matches_reference_golden(name, traj):
+    g = golden("case_" + name)
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case(name, N=int(g["N"]))
+    if traj == "nominal":
+        X, U, A, Bm, Jr, Tr = g["X"], g["U"], g["A_fwd"], g["B_fwd"], g["J_curve0"], int(g["T0"])
+    else:
+        X, U = g["sol_X"], g["sol_U"]
+        A, Bm = O.linearize(F.hop_sys, F.hop_params, X, U)
+        Jr, Tr = g["conv_J_curve"], int(g["conv_T"])
+    sel = api.select_fused_batched(_t(A[None]), _t(Bm[None]), _t(X[None]), _t(U[None]), xg, w, u_ref, Q, R, alpha,
+                                   T_min, T_max, wrap_idx)
+    J = sel.J.cpu().numpy()[0]
+    tol_win, tol_star, dT = J_TOL[name]
+    assert (int(sel.status[0]) & 0xFF) == 0
+    assert abs(int(sel.T_star[0]) - Tr) <= dT
+    assert abs(J[Tr - 1] - Jr[Tr - 1]) <= max(tol_star, 3e-5 if name == "Cartpole_SwingUp" else 0) * abs(Jr[Tr - 1])
+    if tol_win is not None:
+        assert rel(J[T_min - 1:T_max], Jr[T_min - 1:T_max]) <= tol_win
+
+
+def test_generic_and_fused_agree_bitwise_in_T_and_closely_in_J():
+    """The fused kernel builds the augmented blocks itself; feeding the oracle-built blocks to the
+    generic kernel must give the same selection."""
+    g = golden("case_Quadrotor")
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case("Quadrotor", N=128)
+    A_aug, B_aug, Q_aug, z0, R_inv = O.build_augmented(g["A_fwd"], g["B_fwd"], g["a_resid"], g["X"], g["U"], xg, u_ref, Q,
+                                                       R, w, wrap_idx)
+    QT = O.build_terminal(g["X"], xg, alpha, wrap_idx)
+    s1 = api.propagator_all_Jt_aug_batched(_t(A_aug[None]), _t(B_aug[None]), _t(Q_aug[None]), _t(R_inv), _t(z0),
+                                           _t(QT[None]), T_min, T_max)
+    s2 = api.select_fused_batched(_t(g["A_fwd"][None]), _t(g["B_fwd"][None]), _t(g["X"][None]), _t(g["U"][None]), xg, w,
+                                  u_ref, Q, R, alpha, T_min, T_max, wrap_idx, a_resid=_t(g["a_resid"][None]))
+    assert int(s1.T_star[0]) == int(s2.T_star[0]) == int(g["T0"])
+    assert rel(s1.J.cpu().numpy()[0, T_min - 1:], s2.J.cpu().numpy()[0, T_min - 1:]) <= 1e-6
+
+
+def test_ladder_fallback_and_nonfinite_status_on_gpu():
+    d, m, N = 4, 2, 8
+    A, Bm, Q, R, z0, w, QT = s2_batch(range(11), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    Q[1, 3] = np.diag([1.0, 1.0, 1.0, -1e-4])
+    QT[2, 5] = -np.eye(d)
+    A[9, 2, 1, 1] = np.nan
+    sel = api.propagator_all_Jt_aug_batched(_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, N)
+    Jo, sto = O.propagator_batch(A, Bm, Q, Rinv, z0, QT)
+    st = sel.status.cpu().numpy()
+    assert st[0] == 0 and st[1] == 0x100 and st[2] == 0x300 and (st[9] & 0xFF) == 1 and sto[9] == 1
+    ok = [i for i in range(11) if i != 9]
+    assert rel(sel.J.cpu().numpy()[ok], Jo[ok]) <= 1e-9
+    with pytest.raises(FloatingPointError):
+        sel.raise_for_status()
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_rollout_and_linearize_match_oracle(name):
+    g = golden("case_" + name)
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case(name, N=int(g["N"]))
+    rng = np.random.default_rng(3)
+    B = 5
+    x0s = x0[None] + 0.05 * rng.standard_normal((B, x0.size))
+    x0s[0] = x0
+    U = g["U"]
+    X = api.rollout_batched(F, _t(x0s), _t(U)).cpu().numpy()
+    Xo = np.stack([O.rollout(F.hop_sys, F.hop_params, x, U) for x in x0s])
+    assert np.abs(X - Xo).max() <= 1e-9 * max(1.0, np.abs(Xo).max())
+    assert np.abs(X[0] - g["X"]).max() <= 1e-9 * max(1.0, np.abs(g["X"]).max())      # vs the reference itself
+    for central, ka, kb in ((False, "A_fwd", "B_fwd"), (True, "A_cen", "B_cen")):
+        A, Bm = api.linearize_batched(F, _t(Xo), _t(U), central=central)
+        Ao, Bo = zip(*[O.linearize(F.hop_sys, F.hop_params, x, U, central=central) for x in Xo])
+        # forward differences amplify a last-bit difference in sin/cos by 1/h = 1e5
+        assert np.abs(A.cpu().numpy() - np.stack(Ao)).max() <= 2e-9 * max(1.0, np.abs(np.stack(Ao)).max())
+        assert np.abs(Bm.cpu().numpy() - np.stack(Bo)).max() <= 2e-9 * max(1.0, np.abs(np.stack(Bo)).max())
+        assert np.abs(A.cpu().numpy()[0] - g[ka]).max() <= 2e-9 * max(1.0, np.abs(g[ka]).max())
+        assert np.abs(Bm.cpu().numpy()[0] - g[kb]).max() <= 2e-9 * max(1.0, np.abs(g[kb]).max())
+
+
+def test_rollout_divergence_guard_nan_fills_like_the_reference():
+    F = cases.make_case("Quadrotor", N=128)[0]
+    x0 = np.zeros((2, 12)); x0[1, 7] = np.pi / 2          # Euler singularity -> F returns NaN (systems.py:179-181)
+    U = np.tile(np.array([9.81, 0, 0, 0.0]), (16, 1))
+    X = api.rollout_batched(F, _t(x0), _t(U)).cpu().numpy()
+    assert np.isfinite(X[0]).all() and np.isfinite(X[1, 0]).all() and np.isnan(X[1, 1:]).all()
+
+
+def test_s1_from_x0_device_and_host_paths_match_reference_and_oracle():
+    """Headline workload S1: quadrotor n=12, N=128, x0 ~ x0 + sigma xi (first 16 = reference golden)."""
+    g = golden("s1_quadrotor_batch")
+    case = cases.make_case("Quadrotor", N=128)
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = case
+    B = 300
+    x0s = s1_x0(B)
+    sel = api.select_horizon_batched(case, _t(x0s))
+    T = sel.T_star.cpu().numpy(); J = sel.J.cpu().numpy()
+    assert not (sel.status.cpu().numpy() & 0xFF).any()
+    assert np.array_equal(T[:16], g["T"])                                          # vs the reference
+    assert rel(J[:16, T_min - 1:], g["J"][:16, T_min - 1:]) <= 1e-6
+    U = np.tile(u_ref, (N, 1))
+    Jo, To, sto = O.select_from_x0_batch(F.hop_sys, F.hop_params, N, T_min, T_max, x0s, U, xg, u_ref, Q, R, alpha, w,
+                                         wrap_idx, nthreads=8)
+    mism = np.nonzero(T != To)[0]
+    # any T* mismatch against the oracle must be a near-tie (gap below the fp64 noise floor)
+    for b in mism:
+        gap = abs(Jo[b, T[b] - 1] - Jo[b, To[b] - 1]) / abs(Jo[b, To[b] - 1])
+        assert gap < 1e-7, (b, T[b], To[b], gap)
+    assert len(mism) <= 3
+    Jh, Th, Jsh, sth = api.select_horizon_host(case, x0s)
+    assert np.array_equal(Th, T) and np.array_equal(Jh, J) and np.array_equal(sth, sel.status.cpu().numpy())
+
+
+def test_full_size_properties_without_oracle():
+    """At a size the oracle would not finish quickly: size-independent properties.
+    (1) determinism, (2) batch-permutation equivariance, (3) J(T) for T < T_min unaffected by window."""
+    case = cases.make_case("Quadrotor", N=128)
+    B = 4096
+    x0s = s1_x0(B, seed=7)
+    sel = api.HorizonSelector(case, B, device=DEV)
+    r1 = sel(_t(x0s)); T1 = r1.T_star.clone(); J1 = r1.J.clone()
+    r2 = sel(_t(x0s))
+    assert torch.equal(T1, r2.T_star) and torch.equal(J1, r2.J)
+    perm = np.random.default_rng(0).permutation(B)
+    r3 = sel(_t(x0s[perm]))
+    assert torch.equal(r3.T_star.cpu(), T1.cpu()[perm]) and torch.equal(r3.J.cpu(), J1.cpu()[perm])
+    assert int(T1.min()) >= 40 and int(T1.max()) <= 128 and torch.isfinite(J1).all()
+    Jw = J1[:, 39:]
+    assert torch.equal(Jw.argmin(dim=1).int() + 40, T1)

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Build libhop_b200.so (sm_100a) in-tree with nvcc.  Usage: python build.py [--force]"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "hop", "libhop_b200.so")
+SRCS = ["hop_select.cu", "hop_traj.cu", "hop_cabi.cu"]
+HDRS = ["hop_simt.cuh", "hop_select_core.cuh", "hop_select_body.cuh", "hop_dynamics.cuh", "hop_common.cuh",
+        os.path.join("..", "..", "include", "hop_b200.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+         "-Xptxas", "-v"]
+
+
+def stale(target, deps):
+    return not os.path.exists(target) or any(os.path.getmtime(d) > os.path.getmtime(target) for d in deps)
+
+
+def build(force=False, verbose=False):
+    deps = [os.path.join(HERE, f) for f in SRCS + HDRS]
+    if not (force or stale(OUT, deps)):
+        return OUT
+    objs = []
+
+    def compile_one(src):
+        obj = os.path.join(HERE, src.replace(".cu", ".o"))
+        r = subprocess.run([NVCC, *FLAGS, "-c", os.path.join(HERE, src), "-o", obj], capture_output=True, text=True)
+        with open(obj + ".ptxas.log", "w") as fh:
+            fh.write(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stderr}")
+        if verbose:
+            print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SRCS)) as ex:
+        objs = list(ex.map(compile_one, SRCS))
+    # static cudart (nvcc default): the library has no runtime dependency besides the driver
+    subprocess.check_call([NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

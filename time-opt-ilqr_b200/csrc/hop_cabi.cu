@@ -1,0 +1,261 @@
+// hop_cabi.cu -- extern "C" surface of libhop_b200.so (see include/hop_b200.h for the contract).
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "hop_common.cuh"
+#include "hop_select_body.cuh"
+#include "../../include/hop_b200.h"
+
+namespace hop {
+int dispatch_select_generic(int d, int m, const SelectArgs& p, cudaStream_t st);
+int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st);
+int dispatch_rollout(int B, int sys, const double* params_host, int N, const double* x0, const double* U, long ustride,
+                     double max_norm, double* X, cudaStream_t st);
+int dispatch_linearize(int B, int sys, const double* params_host, int N, const double* X, const double* U, long ustride,
+                       int central, double epsx, double epsu, double relx, double relu, double* A, double* Bm,
+                       cudaStream_t st);
+int sys_dims(int sys, int* n, int* m);
+
+static thread_local std::string g_err;
+void set_last_error(const char* msg) { g_err = msg ? msg : ""; }
+int report_cuda(cudaError_t e, const char* where) {
+    if (e == cudaSuccess) return 0;
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+static int need_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        set_last_error("no CUDA device visible: libhop_b200 has no CPU fallback");
+        return HOP_E_NO_DEVICE;
+    }
+    return 0;
+}
+static const double kJitter = 1e-9;   // utils.py:69 defaults
+static const int kMaxTries = 8;
+}  // namespace hop
+
+using namespace hop;
+
+extern "C" {
+
+int hop_abi_version(void) { return HOP_ABI_VERSION; }
+const char* hop_version(void) { return "hop_b200 0.1 (sm_100a, fp64)"; }
+const char* hop_last_error_string(void) { return g_err.c_str(); }
+int hop_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+int hop_select_supported(int d, int m) {
+    return (d == 3 && m == 1) || (d == 4 && m == 2) || (d == 5 && m == 1) || (d == 12 && m == 4) || (d == 13 && m == 4);
+}
+
+int hop_select_f64(int B, int N, int d, int m, int T_min, int T_max, const double* A_aug, const double* B_aug,
+                   const double* Q_aug, const double* R_inv, const double* z0, const double* QT,
+                   const double* w_explicit, int mode, double* J_out, int* Tstar_out, double* Jstar_out, int* status,
+                   void* stream) {
+    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || mode != HOP_MODE_EXACT) {
+        set_last_error("hop_select_f64: bad argument (need 1 <= T_min <= T_max <= N, mode = HOP_MODE_EXACT)");
+        return HOP_E_BADARG;
+    }
+    if (int rc = need_device()) return rc;
+    if (B == 0) return 0;
+    SelectArgs p{B, N, T_min, T_max, kJitter, kMaxTries, A_aug, B_aug, Q_aug, R_inv, z0, QT, w_explicit,
+                 J_out, Tstar_out, Jstar_out, status};
+    return dispatch_select_generic(d, m, p, (cudaStream_t)stream);
+}
+
+int hop_select_fused_f64(int B, int N, int n, int m, int T_min, int T_max, const double* A, const double* Bm,
+                         const double* a_resid, const double* X, const double* U, long u_batch_stride,
+                         const double* xg, const double* w,
+                         const double* u_ref, const double* Q, const double* R, const double* Qf, unsigned wrap_mask,
+                         double q_reg, double rho_reg, int mode, double* J_out, int* Tstar_out, double* Jstar_out,
+                         int* status, void* stream) {
+    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || mode != HOP_MODE_EXACT) {
+        set_last_error("hop_select_fused_f64: bad argument (need 1 <= T_min <= T_max <= N, mode = HOP_MODE_EXACT)");
+        return HOP_E_BADARG;
+    }
+    if (int rc = need_device()) return rc;
+    if (B == 0) return 0;
+    FusedArgs p{B, N, T_min, T_max, kJitter, kMaxTries, A, Bm, a_resid, X, U, u_batch_stride, xg, w, u_ref, Q, R, Qf,
+                wrap_mask, q_reg, rho_reg, J_out, Tstar_out, Jstar_out, status};
+    return dispatch_select_fused(n, m, p, (cudaStream_t)stream);
+}
+
+int hop_rollout_f64(int B, int sys, const double* params_host, int N, const double* x0, const double* U,
+                    long u_batch_stride, double max_state_norm, double* X, void* stream) {
+    if (B < 0 || N < 1 || !params_host) { set_last_error("hop_rollout_f64: bad argument"); return HOP_E_BADARG; }
+    if (int rc = need_device()) return rc;
+    if (B == 0) return 0;
+    return dispatch_rollout(B, sys, params_host, N, x0, U, u_batch_stride, max_state_norm, X, (cudaStream_t)stream);
+}
+
+int hop_linearize_f64(int B, int sys, const double* params_host, int N, const double* X, const double* U,
+                      long u_batch_stride, int central, double epsx, double epsu, double relx, double relu, double* A,
+                      double* Bm, void* stream) {
+    if (B < 0 || N < 1 || !params_host) { set_last_error("hop_linearize_f64: bad argument"); return HOP_E_BADARG; }
+    if (int rc = need_device()) return rc;
+    if (B == 0) return 0;
+    return dispatch_linearize(B, sys, params_host, N, X, U, u_batch_stride, central, epsx, epsu, relx, relu, A, Bm,
+                              (cudaStream_t)stream);
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+unsigned long long hop_select_from_x0_workspace_bytes(int B, int N, int n, int m) {
+    const size_t sX = align256(sizeof(double) * (size_t)B * (N + 1) * n);
+    const size_t sA = align256(sizeof(double) * (size_t)B * N * n * n);
+    const size_t sB = align256(sizeof(double) * (size_t)B * N * n * m);
+    return (unsigned long long)(sX + sA + sB);
+}
+
+int hop_select_from_x0_f64(int B, int sys, const double* params_host, int N, int T_min, int T_max, const double* x0,
+                           const double* U, long u_batch_stride, const double* xg, const double* w,
+                           const double* u_ref, const double* Q, const double* R, const double* Qf, unsigned wrap_mask,
+                           int central, int mode, void* workspace, unsigned long long workspace_bytes, double* J_out,
+                           int* Tstar_out, double* Jstar_out, int* status, void* stream) {
+    int n = 0, m = 0;
+    if (sys_dims(sys, &n, &m)) { set_last_error("hop_select_from_x0_f64: unknown system id"); return HOP_E_BADARG; }
+    if (workspace_bytes < hop_select_from_x0_workspace_bytes(B, N, n, m) || (!workspace && B > 0)) {
+        set_last_error("hop_select_from_x0_f64: workspace too small");
+        return HOP_E_WORKSPACE;
+    }
+    if (B == 0) return 0;
+    char* ws = (char*)workspace;
+    double* X = (double*)ws;
+    double* A = (double*)(ws + align256(sizeof(double) * (size_t)B * (N + 1) * n));
+    double* Bm = (double*)((char*)A + align256(sizeof(double) * (size_t)B * N * n * n));
+    int rc = hop_rollout_f64(B, sys, params_host, N, x0, U, u_batch_stride, 1e6, X, stream);            // solver.py:42
+    if (rc) return rc;
+    rc = hop_linearize_f64(B, sys, params_host, N, X, U, u_batch_stride, central, 1e-5, 1e-5, 1e-6, 1e-6, A, Bm,
+                           stream);                                                                      // linearization.py:177,216
+    if (rc) return rc;
+    // a_resid = NULL: on a trajectory produced by the rollout above F(X_k,U_k) - X_{k+1} is exactly 0
+    return hop_select_fused_f64(B, N, n, m, T_min, T_max, A, Bm, nullptr, X, U, u_batch_stride, xg, w, u_ref, Q, R, Qf,
+                                wrap_mask, 1e-9, 1e-12, mode, J_out, Tstar_out, Jstar_out, status, stream);
+}
+
+// ---- FP64 pipe probe (roofline denominator; MEASURED_PEAKS.json has no FP64 figure) ---------------
+__global__ void k_probe_dfma(int iters, double seed, double* sink) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0 - 1e-9, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678) sink[0] = r;   // never true; keeps the chain alive
+}
+
+int hop_probe_fp64_tflops(int iters, double* tflops_out, double* ms_out) {
+    if (int rc = need_device()) return rc;
+    if (iters < 1 || !tflops_out) { set_last_error("hop_probe_fp64_tflops: bad argument"); return HOP_E_BADARG; }
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaGetDeviceProperties(&prop, dev);
+    const int threads = 512, blocks = prop.multiProcessorCount * 4;
+    double* sink = nullptr;
+    if (int rc = report_cuda(cudaMalloc(&sink, sizeof(double)), "cudaMalloc(probe)")) return rc;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_probe_dfma<<<blocks, threads>>>(iters / 8 + 1, 0.5, sink);   // warm-up
+    cudaEventRecord(e0);
+    k_probe_dfma<<<blocks, threads>>>(iters, 0.5, sink);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (e != cudaSuccess) return report_cuda(e, "hop_probe_fp64_tflops");
+    const double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)threads * (double)blocks;
+    *tflops_out = flops / (ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return 0;
+}
+
+// ---- host-buffer variant ------------------------------------------------------------------------
+namespace {
+struct HostCtx {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    void* buf = nullptr;
+    size_t cap = 0;
+    int device = -1;
+};
+HostCtx g_host;
+}  // namespace
+
+int hop_select_from_x0_host_f64(int B, int sys, const double* params_host, int N, int T_min, int T_max,
+                                const double* x0, const double* U, long u_batch_stride, const double* xg,
+                                const double* w, const double* u_ref, const double* Q, const double* R,
+                                const double* Qf, unsigned wrap_mask, int central, int mode, double* J_out,
+                                int* Tstar_out, double* Jstar_out, int* status) {
+    int n = 0, m = 0;
+    if (sys_dims(sys, &n, &m)) { set_last_error("hop_select_from_x0_host_f64: unknown system id"); return HOP_E_BADARG; }
+    if (int rc = need_device()) return rc;
+    if (B <= 0) return B == 0 ? 0 : HOP_E_BADARG;
+    std::lock_guard<std::mutex> lock(g_host.mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_host.device != dev) {   // one cached arena per process; re-created when the current device changes
+        if (g_host.buf) cudaFree(g_host.buf);
+        if (g_host.stream) cudaStreamDestroy(g_host.stream);
+        g_host.buf = nullptr; g_host.cap = 0; g_host.stream = nullptr; g_host.device = dev;
+    }
+    if (!g_host.stream) {
+        if (int rc = report_cuda(cudaStreamCreateWithFlags(&g_host.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return rc;
+    }
+    const size_t nU = (u_batch_stride == 0) ? (size_t)N * m : (size_t)B * N * m;
+    const size_t s_x0 = align256(sizeof(double) * (size_t)B * n), s_xg = s_x0, s_w = align256(sizeof(double) * (size_t)B);
+    const size_t s_U = align256(sizeof(double) * nU), s_c = align256(sizeof(double) * (size_t)(m + 2 * n * n + m * m));
+    const size_t s_J = align256(sizeof(double) * (size_t)B * T_max), s_T = align256(sizeof(int) * (size_t)B);
+    const size_t s_Js = align256(sizeof(double) * (size_t)B);
+    const size_t s_ws = (size_t)hop_select_from_x0_workspace_bytes(B, N, n, m);
+    const size_t total = s_x0 + s_xg + s_w + s_U + s_c + s_J + 2 * s_T + s_Js + s_ws;
+    if (total > g_host.cap) {
+        if (g_host.buf) cudaFree(g_host.buf);
+        g_host.buf = nullptr; g_host.cap = 0;
+        if (int rc = report_cuda(cudaMalloc(&g_host.buf, total), "cudaMalloc(host-variant arena)")) return rc;
+        g_host.cap = total;
+    }
+    char* q = (char*)g_host.buf;
+    double* d_x0 = (double*)q; q += s_x0;
+    double* d_xg = (double*)q; q += s_xg;
+    double* d_w = (double*)q; q += s_w;
+    double* d_U = (double*)q; q += s_U;
+    double* d_c = (double*)q; q += s_c;
+    double* d_J = (double*)q; q += s_J;
+    int* d_T = (int*)q; q += s_T;
+    int* d_st = (int*)q; q += s_T;
+    double* d_Js = (double*)q; q += s_Js;
+    void* d_ws = q;
+    cudaStream_t st = g_host.stream;
+    double* d_uref = d_c; double* d_Q = d_uref + m; double* d_R = d_Q + n * n; double* d_Qf = d_R + m * m;
+    cudaMemcpyAsync(d_x0, x0, sizeof(double) * (size_t)B * n, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_xg, xg, sizeof(double) * (size_t)B * n, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_w, w, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_U, U, sizeof(double) * nU, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_uref, u_ref, sizeof(double) * m, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_Q, Q, sizeof(double) * n * n, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_R, R, sizeof(double) * m * m, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_Qf, Qf, sizeof(double) * n * n, cudaMemcpyHostToDevice, st);
+    int rc = hop_select_from_x0_f64(B, sys, params_host, N, T_min, T_max, d_x0, d_U, u_batch_stride, d_xg, d_w, d_uref,
+                                    d_Q, d_R, d_Qf, wrap_mask, central, mode, d_ws, s_ws, d_J, d_T, d_Js, d_st, st);
+    if (rc) return rc;
+    if (J_out) cudaMemcpyAsync(J_out, d_J, sizeof(double) * (size_t)B * T_max, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(Tstar_out, d_T, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st);
+    if (Jstar_out) cudaMemcpyAsync(Jstar_out, d_Js, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st);
+    if (status) cudaMemcpyAsync(status, d_st, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st);
+    return report_cuda(cudaStreamSynchronize(st), "hop_select_from_x0_host_f64");
+}
+
+}  // extern "C"

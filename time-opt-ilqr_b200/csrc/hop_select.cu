@@ -1,0 +1,80 @@
+// hop_select.cu -- __global__ wrappers + launchers of the horizon-selection kernels.
+//
+// Grid: one G-lane group per problem, 32/G problems per warp, WARPS warps per CTA; every warp is
+// independent (warp-synchronous code, no CTA barrier inside the sweep), so the hardware scheduler
+// load-balances warps across the 148 SMs.  Dynamic shared memory = per-group slab (Geo::SLAB
+// doubles) [+ the CTA-wide case constants for the fused form].
+#include "hop_common.cuh"
+#include "hop_select_body.cuh"
+#include "../../include/hop_b200.h"
+
+namespace hop {
+
+constexpr int kWarps = 2;   // warps per CTA (64 threads): small CTAs pack the register file tightly
+
+template <int D, int M, int G>
+__global__ void __launch_bounds__(kWarps * 32) k_select_generic(const SelectArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int GPW = 32 / G;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = warp * GPW + lane / G;
+    const int b = blockIdx.x * (kWarps * GPW) + slot;
+    select_generic_body<D, M, G>(p, b, smem + (size_t)slot * Geo<D, M, G>::SLAB);
+}
+
+template <int D, int M, int G>
+__global__ void __launch_bounds__(kWarps * 32) k_select_fused(const FusedArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int GPW = 32 / G;
+    double* cst = smem + (size_t)(kWarps * GPW) * Geo<D, M, G>::SLAB;
+    fused_const_fill<D, M>(p, cst, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = warp * GPW + lane / G;
+    const int b = blockIdx.x * (kWarps * GPW) + slot;
+    select_fused_body<D, M, G>(p, b, smem + (size_t)slot * Geo<D, M, G>::SLAB, cst);
+}
+
+template <int D, int M, int G>
+static int launch_generic(const SelectArgs& p, cudaStream_t st) {
+    constexpr int GPW = 32 / G;
+    const size_t smem = sizeof(double) * (size_t)(kWarps * GPW) * Geo<D, M, G>::SLAB;
+    cudaError_t e = cudaFuncSetAttribute(k_select_generic<D, M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return report_cuda(e, "cudaFuncSetAttribute(k_select_generic)");
+    const int per_cta = kWarps * GPW;
+    const int grid = (p.B + per_cta - 1) / per_cta;
+    k_select_generic<D, M, G><<<grid, kWarps * 32, smem, st>>>(p);
+    return check_launch("k_select_generic");
+}
+
+template <int D, int M, int G>
+static int launch_fused(const FusedArgs& p, cudaStream_t st) {
+    constexpr int GPW = 32 / G;
+    const size_t smem = sizeof(double) * ((size_t)(kWarps * GPW) * Geo<D, M, G>::SLAB + FusedConst<D, M>::SIZE);
+    cudaError_t e = cudaFuncSetAttribute(k_select_fused<D, M, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return report_cuda(e, "cudaFuncSetAttribute(k_select_fused)");
+    const int per_cta = kWarps * GPW;
+    const int grid = (p.B + per_cta - 1) / per_cta;
+    k_select_fused<D, M, G><<<grid, kWarps * 32, smem, st>>>(p);
+    return check_launch("k_select_fused");
+}
+
+int dispatch_select_generic(int d, int m, const SelectArgs& p, cudaStream_t st) {
+    if (d == 3 && m == 1) return launch_generic<3, 1, 4>(p, st);
+    if (d == 4 && m == 2) return launch_generic<4, 2, 4>(p, st);
+    if (d == 5 && m == 1) return launch_generic<5, 1, 8>(p, st);
+    if (d == 12 && m == 4) return launch_generic<12, 4, 16>(p, st);
+    if (d == 13 && m == 4) return launch_generic<13, 4, 16>(p, st);
+    set_last_error("hop_select_f64: (d, m) not instantiated; supported: (3,1) (4,2) (5,1) (12,4) (13,4)");
+    return HOP_E_UNSUPPORTED_DIMS;
+}
+
+int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st) {
+    if (n == 2 && m == 1) return launch_fused<3, 1, 4>(p, st);
+    if (n == 4 && m == 1) return launch_fused<5, 1, 8>(p, st);
+    if (n == 12 && m == 4) return launch_fused<13, 4, 16>(p, st);
+    set_last_error("hop_select_fused_f64: (n, m) not instantiated; supported: (2,1) (4,1) (12,4)");
+    return HOP_E_UNSUPPORTED_DIMS;
+}
+
+}  // namespace hop

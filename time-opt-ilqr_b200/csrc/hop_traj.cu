@@ -1,0 +1,170 @@
+// hop_traj.cu -- batched nominal rollout and finite-difference linearisation.
+//
+//   k_rollout   : solver.py:42-62   one thread per problem, sequential in k
+//   k_linearize : linearization.py:216-262 (forward) / :177-211 (central)
+//                 one thread per (problem, step, perturbed coordinate); the n+m threads of a
+//                 (problem, step) pair are adjacent, so each row of A_k / B_k is written coalesced.
+#include "hop_common.cuh"
+#include "hop_dynamics.cuh"
+#include "../../include/hop_b200.h"
+
+namespace hop {
+
+struct DynParams { double p[HOP_NPARAMS]; };
+
+template <int SYS>
+__global__ void k_rollout(int B, DynParams prm, int N, const double* __restrict__ x0, const double* __restrict__ U,
+                          long ustride, double max_norm, double* __restrict__ X) {
+    constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double x[n], xn[n], u[m];
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = x0[(size_t)b * n + i];
+    double* Xb = X + (size_t)b * (N + 1) * n;
+#pragma unroll
+    for (int i = 0; i < n; ++i) Xb[i] = x[i];
+    const double* Ub = U + (size_t)b * ustride;
+    bool dead = false;
+    for (int k = 0; k < N; ++k) {
+        if (!dead) {
+#pragma unroll
+            for (int i = 0; i < m; ++i) u[i] = Ub[(size_t)k * m + i];
+            dynamics<SYS>(prm.p, x, u, xn);
+            double ss = 0.0;
+            bool fin = true;
+#pragma unroll
+            for (int i = 0; i < n; ++i) { fin = fin && isfinite(xn[i]); ss = add(ss, mul(xn[i], xn[i])); }
+            if (!fin || sqrt(ss) > max_norm) dead = true;   // solver.py:57-59: NaN-fill the remainder
+        }
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            x[i] = dead ? nan("") : xn[i];
+            Xb[(size_t)(k + 1) * n + i] = x[i];
+        }
+    }
+}
+
+template <int SYS>
+__global__ void k_linearize(int B, DynParams prm, int N, const double* __restrict__ X, const double* __restrict__ U,
+                            long ustride, int central, double epsx, double epsu, double relx, double relu,
+                            double* __restrict__ A, double* __restrict__ Bm) {
+    constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m, P = n + m;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)B * N * P;
+    if (gid >= total) return;
+    const int c = (int)(gid % P);            // perturbed coordinate: state c < n, else control c - n
+    const size_t bk = gid / P;
+    const int k = (int)(bk % N);
+    const size_t b = bk / N;
+    double x[n], u[m], f0[n], fp[n], fm[n];
+    const double* xs = X + (b * (N + 1) + k) * n;
+    const double* us = U + b * ustride + (size_t)k * m;
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = xs[i];
+#pragma unroll
+    for (int i = 0; i < m; ++i) u[i] = us[i];
+    double h = 0.0, base = 0.0;
+    // h = max(eps, rel * max(1, |v|))  (linearization.py:253,257)
+#pragma unroll
+    for (int i = 0; i < n; ++i) if (i == c) { base = x[i]; h = fmax(epsx, mul(relx, fmax(1.0, fabs(x[i])))); }
+#pragma unroll
+    for (int i = 0; i < m; ++i) if (i + n == c) { base = u[i]; h = fmax(epsu, mul(relu, fmax(1.0, fabs(u[i])))); }
+    bool nanout = false;
+    if (!central) {
+        dynamics<SYS>(prm.p, x, u, f0);
+        bool fin = true;
+#pragma unroll
+        for (int i = 0; i < n; ++i) fin = fin && isfinite(f0[i]);
+        nanout = !fin;                        // linearization.py:243-248
+    }
+    const double vp = add(base, h), vm = sub(base, h);
+#pragma unroll
+    for (int i = 0; i < n; ++i) if (i == c) x[i] = vp;
+#pragma unroll
+    for (int i = 0; i < m; ++i) if (i + n == c) u[i] = vp;
+    dynamics<SYS>(prm.p, x, u, fp);
+    double col[n];
+    if (central) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) if (i == c) x[i] = vm;
+#pragma unroll
+        for (int i = 0; i < m; ++i) if (i + n == c) u[i] = vm;
+        dynamics<SYS>(prm.p, x, u, fm);
+        const double den = mul(2.0, h);
+#pragma unroll
+        for (int i = 0; i < n; ++i) col[i] = sub(fp[i], fm[i]) / den;
+    } else {
+#pragma unroll
+        for (int i = 0; i < n; ++i) col[i] = nanout ? nan("") : sub(fp[i], f0[i]) / h;
+    }
+    if (c < n) {
+        double* Ak = A + bk * n * n;
+#pragma unroll
+        for (int i = 0; i < n; ++i) Ak[i * n + c] = col[i];
+    } else {
+        double* Bk = Bm + bk * n * m;
+#pragma unroll
+        for (int i = 0; i < n; ++i) Bk[i * m + (c - n)] = col[i];
+    }
+}
+
+template <int SYS>
+static int launch_rollout(int B, const DynParams& prm, int N, const double* x0, const double* U, long ustride,
+                          double max_norm, double* X, cudaStream_t st) {
+    const int threads = 128;
+    k_rollout<SYS><<<(B + threads - 1) / threads, threads, 0, st>>>(B, prm, N, x0, U, ustride, max_norm, X);
+    return check_launch("k_rollout");
+}
+template <int SYS>
+static int launch_linearize(int B, const DynParams& prm, int N, const double* X, const double* U, long ustride,
+                            int central, double epsx, double epsu, double relx, double relu, double* A, double* Bm,
+                            cudaStream_t st) {
+    constexpr int P = SysDims<SYS>::n + SysDims<SYS>::m;
+    const size_t total = (size_t)B * N * P;
+    const int threads = 128;
+    const size_t grid = (total + threads - 1) / threads;
+    k_linearize<SYS><<<(unsigned)grid, threads, 0, st>>>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, A, Bm);
+    return check_launch("k_linearize");
+}
+
+int dispatch_rollout(int B, int sys, const double* params_host, int N, const double* x0, const double* U, long ustride,
+                     double max_norm, double* X, cudaStream_t st) {
+    DynParams prm;
+    for (int i = 0; i < HOP_NPARAMS; ++i) prm.p[i] = params_host[i];
+    switch (sys) {
+        case 0: return launch_rollout<0>(B, prm, N, x0, U, ustride, max_norm, X, st);
+        case 1: return launch_rollout<1>(B, prm, N, x0, U, ustride, max_norm, X, st);
+        case 2: return launch_rollout<2>(B, prm, N, x0, U, ustride, max_norm, X, st);
+        case 3: return launch_rollout<3>(B, prm, N, x0, U, ustride, max_norm, X, st);
+    }
+    set_last_error("hop_rollout_f64: unknown system id");
+    return HOP_E_BADARG;
+}
+
+int dispatch_linearize(int B, int sys, const double* params_host, int N, const double* X, const double* U, long ustride,
+                       int central, double epsx, double epsu, double relx, double relu, double* A, double* Bm,
+                       cudaStream_t st) {
+    DynParams prm;
+    for (int i = 0; i < HOP_NPARAMS; ++i) prm.p[i] = params_host[i];
+    switch (sys) {
+        case 0: return launch_linearize<0>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, A, Bm, st);
+        case 1: return launch_linearize<1>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, A, Bm, st);
+        case 2: return launch_linearize<2>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, A, Bm, st);
+        case 3: return launch_linearize<3>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, A, Bm, st);
+    }
+    set_last_error("hop_linearize_f64: unknown system id");
+    return HOP_E_BADARG;
+}
+
+int sys_dims(int sys, int* n, int* m) {
+    switch (sys) {
+        case 0: *n = 2; *m = 1; return 0;
+        case 1: *n = 4; *m = 1; return 0;
+        case 2: *n = 12; *m = 4; return 0;
+        case 3: *n = 4; *m = 1; return 0;
+    }
+    return HOP_E_BADARG;
+}
+
+}  // namespace hop
