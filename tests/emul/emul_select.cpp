@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "hop_select_body.cuh"
+#include "hop_select_mma_body.cuh"
 
 namespace {
 template <int D, int M, int G>
@@ -46,7 +47,52 @@ int run_fused(const hop::FusedArgs& p) {
     }
     return 0;
 }
+// ---- one-problem-per-warp DMMA bodies
+template <int D, int M>
+struct MmaGenericJob { const hop::SelectArgs* p; int b; double* scratch; };
+template <int D, int M>
+void mma_generic_lane(void* a) {
+    auto* j = (MmaGenericJob<D, M>*)a;
+    hop::mma::select_generic_body<D, M>(*j->p, j->b, j->scratch);
+}
+template <int D, int M>
+int run_generic_mma(const hop::SelectArgs& p) {
+    std::vector<double> scratch(hop::mma::kWarpScratch, -7.0);
+    for (int b = 0; b < p.B; ++b) {
+        MmaGenericJob<D, M> j{&p, b, scratch.data()};
+        if (hop::simt::run_warp(mma_generic_lane<D, M>, &j)) return -1;
+    }
+    return 0;
+}
+template <int D, int M>
+struct MmaFusedJob { const hop::FusedArgs* p; int b; double* scratch; const double* cst; };
+template <int D, int M>
+void mma_fused_lane(void* a) {
+    auto* j = (MmaFusedJob<D, M>*)a;
+    hop::mma::select_fused_body<D, M>(*j->p, j->b, j->scratch, j->cst);
+}
+template <int D, int M>
+int run_fused_mma(const hop::FusedArgs& p) {
+    std::vector<double> scratch(hop::mma::kWarpScratch, -7.0);
+    std::vector<double> cst(hop::FusedConst<D, M>::SIZE, 0.0);
+    hop::fused_const_fill<D, M>(p, cst.data(), 0, 1);
+    for (int b = 0; b < p.B; ++b) {
+        MmaFusedJob<D, M> j{&p, b, scratch.data(), cst.data()};
+        if (hop::simt::run_warp(mma_fused_lane<D, M>, &j)) return -1;
+    }
+    return 0;
+}
 }  // namespace
+
+extern "C" int emul_select_generic_mma(int d, int m, const hop::SelectArgs* p) {
+    if (d == 12 && m == 4) return run_generic_mma<12, 4>(*p);
+    if (d == 13 && m == 4) return run_generic_mma<13, 4>(*p);
+    return -2;
+}
+extern "C" int emul_select_fused_mma(int n, int m, const hop::FusedArgs* p) {
+    if (n == 12 && m == 4) return run_fused_mma<13, 4>(*p);
+    return -2;
+}
 
 extern "C" int emul_select_generic(int d, int m, const hop::SelectArgs* p) {
     if (d == 3 && m == 1) return run_generic<3, 1, 4>(*p);

@@ -18,7 +18,7 @@ struct Warp {
     int cur;
     int arrived;
     unsigned long generation;
-    double xchg[W];
+    double xchg[W], xchg2[W];
     bool pred[W];
     void (*fn)(void*);
     void* arg;
@@ -100,6 +100,22 @@ unsigned ballot(bool p) {
     return m;
 }
 bool all(bool p) { return ballot(p) == 0xffffffffu; }
+
+void dmma(double& c0, double& c1, double a, double b) {
+    Warp* w = g;
+    const int me = w->cur, gg = me >> 2, t = me & 3;
+    w->xchg[me] = a;    // A[g][t]
+    w->xchg2[me] = b;   // B[t][g]
+    sync();
+    double acc[2] = {c0, c1};
+    for (int s = 0; s < 2; ++s) {
+        const int n = 2 * t + s;
+        for (int k = 0; k < 4; ++k) acc[s] = std::fma(w->xchg[(gg << 2) | k], w->xchg2[(n << 2) | k], acc[s]);
+    }
+    sync();
+    c0 = acc[0];
+    c1 = acc[1];
+}
 
 int run_warp(void (*fn)(void*), void* arg) {
     Warp* w = (Warp*)calloc(1, sizeof(Warp));

@@ -1,6 +1,6 @@
 // simt_emul.h -- TEST INFRASTRUCTURE: run the HOP kernel bodies on the host.
 //
-// The 32 lanes of a warp are cooperative fibers (ucontext); sync()/shfl()/ballot() are barriers
+// The 32 lanes of a warp are cooperative fibers (ucontext); sync()/shfl()/ballot()/dmma() are barriers
 // among them.  This lets `pytest -m "not gpu"` execute the very same kernel source
 // (time-opt-ilqr_b200/csrc/hop_select_body.cuh, compiled with -DHOP_HOST_EMUL by g++) in a container
 // without a GPU.  It is never linked into the product library and is not a CPU fallback: the
@@ -21,6 +21,7 @@ double shfl(double v, int src_in_group, int width);
 double shfl_xor(double v, int mask, int width);
 unsigned ballot(bool p);
 bool all(bool p);
+void dmma(double& c0, double& c1, double a, double b);   // mma.m8n8k4.f64 semantics
 // Run fn(arg) once per lane of one emulated warp.  Returns 0, or -1 if lanes exited non-uniformly
 // (some lane still waiting at a barrier when another finished), which on a GPU would be a hang.
 int run_warp(void (*fn)(void*), void* arg);

@@ -59,3 +59,31 @@ def test_emulated_kernel_ladder_fallback_and_nonfinite_status():
     _, sto = O.propagator_batch(A, B, Q, Rinv, z0, QT)
     assert (st[0] & 0xFF) == 1 and sto[0] == 1        # FloatingPointError in the reference
     assert (st[1] & 0xFF) == 0 and (st[2] & 0xFF) == 0
+
+
+@pytest.mark.parametrize("d,m,N", [(12, 4, 12), (13, 4, 16)])
+def test_emulated_dmma_generic_kernel_matches_oracle(d, m, N):
+    """One-problem-per-warp DMMA mapping (hop_select_mma_body.cuh): register-fragment layout, shuffle
+    transposes and the Gauss-Jordan pivot exchange, checked on the host emulator."""
+    A, B, Q, R, z0, w, QT = s2_batch(range(2), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    Q[1, 3] = np.diag(np.r_[np.ones(d - 1), -1e-4])       # ladder
+    QT[1, 5] = -np.eye(d)                                  # LU fallback
+    J, T, Js, st = emul.select_generic(A, B, Q, Rinv, z0, QT, 1, N, w_explicit=w, mma=True)
+    Jo, sto = O.propagator_batch(A, B, Q, Rinv, z0, QT)
+    assert st[0] == 0 and st[1] == 0x300 and not sto.any()
+    assert rel(J, Jo) <= 1e-9
+    assert np.array_equal(T, np.argmin(Jo + w[:, None] * np.arange(1, N + 1), axis=1) + 1)
+
+
+def test_emulated_dmma_fused_kernel_matches_reference_golden():
+    g = golden("case_Quadrotor")
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case("Quadrotor", N=128)
+    T_max = 60
+    J, T, Js, st = emul.select_fused(g["A_fwd"][None], g["B_fwd"][None], g["a_resid"][None], g["X"][None], g["U"][None],
+                                     xg[None], np.array([w]), u_ref, Q, R, O.as_terminal_weight(alpha, 12),
+                                     O.wrap_mask(wrap_idx), T_min, T_max, mma=True)
+    Jr, Tr = g["J_curve0"], int(g["T0"])
+    assert (st[0] & 0xFF) == 0 and int(T[0]) == Tr
+    assert abs(J[0, Tr - 1] - Jr[Tr - 1]) <= 1e-8 * abs(Jr[Tr - 1])
+    assert rel(J[0, T_min - 1:T_max], Jr[T_min - 1:T_max]) <= 1e-6

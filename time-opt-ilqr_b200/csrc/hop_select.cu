@@ -6,6 +6,7 @@
 // doubles) [+ the CTA-wide case constants for the fused form].
 #include "hop_common.cuh"
 #include "hop_select_body.cuh"
+#include "hop_select_mma_body.cuh"
 #include "../../include/hop_b200.h"
 
 namespace hop {
@@ -59,12 +60,47 @@ static int launch_fused(const FusedArgs& p, cudaStream_t st) {
     return check_launch("k_select_fused");
 }
 
+// ---- one problem per warp, DMMA register fragments (d in 9..16) -----------------------------------
+constexpr int kMmaWarps = 4;   // warps (= problems) per CTA
+
+template <int D, int M>
+__global__ void __launch_bounds__(kMmaWarps * 32) k_select_generic_mma(const SelectArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5;
+    mma::select_generic_body<D, M>(p, blockIdx.x * kMmaWarps + warp, smem + (size_t)warp * mma::kWarpScratch);
+}
+
+template <int D, int M>
+__global__ void __launch_bounds__(kMmaWarps * 32) k_select_fused_mma(const FusedArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    double* cst = smem + (size_t)kMmaWarps * mma::kWarpScratch;
+    fused_const_fill<D, M>(p, cst, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    mma::select_fused_body<D, M>(p, blockIdx.x * kMmaWarps + warp, smem + (size_t)warp * mma::kWarpScratch, cst);
+}
+
+template <int D, int M>
+static int launch_generic_mma(const SelectArgs& p, cudaStream_t st) {
+    const size_t smem = sizeof(double) * (size_t)kMmaWarps * mma::kWarpScratch;
+    const int grid = (p.B + kMmaWarps - 1) / kMmaWarps;
+    k_select_generic_mma<D, M><<<grid, kMmaWarps * 32, smem, st>>>(p);
+    return check_launch("k_select_generic_mma");
+}
+template <int D, int M>
+static int launch_fused_mma(const FusedArgs& p, cudaStream_t st) {
+    const size_t smem = sizeof(double) * ((size_t)kMmaWarps * mma::kWarpScratch + FusedConst<D, M>::SIZE);
+    const int grid = (p.B + kMmaWarps - 1) / kMmaWarps;
+    k_select_fused_mma<D, M><<<grid, kMmaWarps * 32, smem, st>>>(p);
+    return check_launch("k_select_fused_mma");
+}
+
 int dispatch_select_generic(int d, int m, const SelectArgs& p, cudaStream_t st) {
     if (d == 3 && m == 1) return launch_generic<3, 1, 4>(p, st);
     if (d == 4 && m == 2) return launch_generic<4, 2, 4>(p, st);
     if (d == 5 && m == 1) return launch_generic<5, 1, 8>(p, st);
-    if (d == 12 && m == 4) return launch_generic<12, 4, 16>(p, st);
-    if (d == 13 && m == 4) return launch_generic<13, 4, 16>(p, st);
+    if (d == 12 && m == 4) return launch_generic_mma<12, 4>(p, st);
+    if (d == 13 && m == 4) return launch_generic_mma<13, 4>(p, st);
     set_last_error("hop_select_f64: (d, m) not instantiated; supported: (3,1) (4,2) (5,1) (12,4) (13,4)");
     return HOP_E_UNSUPPORTED_DIMS;
 }
@@ -72,7 +108,7 @@ int dispatch_select_generic(int d, int m, const SelectArgs& p, cudaStream_t st) 
 int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st) {
     if (n == 2 && m == 1) return launch_fused<3, 1, 4>(p, st);
     if (n == 4 && m == 1) return launch_fused<5, 1, 8>(p, st);
-    if (n == 12 && m == 4) return launch_fused<13, 4, 16>(p, st);
+    if (n == 12 && m == 4) return launch_fused_mma<13, 4>(p, st);
     set_last_error("hop_select_fused_f64: (n, m) not instantiated; supported: (2,1) (4,1) (12,4)");
     return HOP_E_UNSUPPORTED_DIMS;
 }

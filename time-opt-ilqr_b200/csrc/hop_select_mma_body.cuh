@@ -1,0 +1,280 @@
+// hop_select_mma_body.cuh -- HOP horizon selection, ONE PROBLEM PER WARP, blocks held as DMMA
+// register fragments (hop_mma.cuh).  Same algorithm and operation order as hop_select_core.cuh /
+// the reference (horizon_selection.py:36-86, augmented.py:10-87, solver.py:522); only the mapping
+// of the d x d algebra onto the machine differs:
+//     products      -> DMMA.8x8x4 (D = X Z^T form, no operand movement)
+//     chol_inv      -> Gauss-Jordan sweeps with shuffle-exchanged pivot row/column
+//     _sym          -> shuffle transpose
+// Used for 9 <= d <= 16 (quadrotor d = 13, synthetic d = 12); small d stays on the multi-problem-
+// per-warp kernels of hop_select_body.cuh.
+#pragma once
+#include "hop_mma.cuh"
+#include "hop_select_body.cuh"   // SelectArgs, FusedArgs, FusedConst, wrap_pi, ArgMin
+
+namespace hop { namespace mma {
+
+constexpr int kWarpScratch = 512 + 64;   // doubles of shared memory per warp: LU scratch + small vectors
+
+template <int D>
+struct PrefixL { Mat eb, fb, gb; };
+
+HOP_DEVICE double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += simt::shfl_xor(v, o, 32);
+    return v;
+}
+
+// Stage + prefix of step k (horizon_selection.py:57-75).  Qs: symmetrised Q_k; A: A_k; Bm: B_k (d x m);
+// RinvT: (R^-1)^T.  All in layout L with zero padding.
+template <int D, int M>
+HOP_DEVICE void stage_prefix_step(int k, PrefixL<D>& P, const Mat& Qs, const Mat& A, const Mat& Bm, const Mat& RinvT,
+                                  const LaneGeo& L, double* scratch, double jitter, int max_tries, int& status) {
+    constexpr int NT = (D + 7) / 8, KB = (D + 3) / 4, KBM = (M + 3) / 4, NTM = (M + 7) / 8;
+    Mat E;
+    chol_inv<D>(Qs, E, L, scratch, jitter, max_tries, status);                 // E_k = chol_inv(Q_k)          (:59)
+    Mat W;
+    if (k > 0) {
+        Mat S;
+        mat_add(S, E, P.gb);
+        mat_sym(S, L);
+        chol_inv<D>(S, W, L, scratch, jitter, max_tries, status);              // W = chol_inv(E_k + Gbar)     (:72)
+    }
+    Mat Ft, G;
+    mma_nt<NT, NT, KB, false>(Ft, A, E);                                       // F_k^T = A_k E_k
+    mma_nt<NT, NT, KB, false>(G, Ft, A);                                       // (A_k E_k) A_k^T              (:61)
+    {
+        Mat BR;
+        mma_nt<NT, NTM, KBM, false>(BR, Bm, RinvT);                            // B_k R^-1
+        mma_nt<NT, NT, KBM, true>(G, BR, Bm);                                  // + (B_k R^-1) B_k^T
+    }
+    mat_sym(G, L);                                                             // G_k = sym(...)               (:64)
+    if (k == 0) {
+        mma_nt<NT, NT, KB, false>(P.fb, E, A);                                 // F_0 = E_0 A_0^T              (:60)
+        mat_copy(P.eb, E);
+        mat_copy(P.gb, G);
+    } else {
+        Mat T1, acc;
+        mma_nt<NT, NT, KB, false>(T1, P.fb, W);                                // Fbar W                       (:73)
+        mma_nt<NT, NT, KB, false>(acc, T1, P.fb);                              // (Fbar W) Fbar^T
+        mat_sub(P.eb, P.eb, acc);
+        mat_sym(P.eb, L);                                                      // Ebar                         (:73)
+        mma_nt<NT, NT, KB, false>(acc, T1, Ft);                                // (Fbar W) F_k  -> new Fbar    (:74)
+        mma_nt<NT, NT, KB, false>(T1, Ft, W);                                  // F_k^T W                      (:75)
+        mat_copy(P.fb, acc);
+        mma_nt<NT, NT, KB, false>(acc, T1, Ft);                                // (F_k^T W) F_k
+        mat_sub(P.gb, G, acc);
+        mat_sym(P.gb, L);                                                      // Gbar                         (:75)
+    }
+}
+
+// Query for horizon t = k+1 (:77-86).  Returns P0 = chol_inv(X0) (the caller forms 0.5 z0^T P0 z0).
+template <int D>
+HOP_DEVICE void query_step(const PrefixL<D>& P, const Mat& QTs, Mat& P0, const LaneGeo& L, double* scratch, double jitter,
+                           int max_tries, int& status) {
+    constexpr int NT = (D + 7) / 8, KB = (D + 3) / 4;
+    Mat Xt, Wt;
+    chol_inv<D>(QTs, Xt, L, scratch, jitter, max_tries, status);               // X_t = chol_inv(QT_t)         (:79)
+    {
+        Mat S;
+        mat_add(S, Xt, P.gb);
+        mat_sym(S, L);
+        chol_inv<D>(S, Wt, L, scratch, jitter, max_tries, status);             // W_t                          (:82)
+    }
+    Mat T3, X0;
+    mma_nt<NT, NT, KB, false>(T3, P.fb, Wt);                                   // Fbar W_t
+    mma_nt<NT, NT, KB, false>(X0, T3, P.fb);                                   // (Fbar W_t) Fbar^T
+    mat_sub(X0, P.eb, X0);
+    mat_sym(X0, L);                                                            // X0                           (:83)
+    chol_inv<D>(X0, P0, L, scratch, jitter, max_tries, status);                // P0                           (:84)
+}
+
+// ---- LQR-boundary form: drop-in for propagator_all_Jt_aug + argmin ---------------------------------
+template <int D, int M>
+HOP_DEVICE void select_generic_body(const SelectArgs& p, int b_raw, double* scratch) {
+    LaneGeo L;
+    L.init();
+    const bool valid = b_raw < p.B;
+    const int b = valid ? b_raw : p.B - 1;
+    Mat RinvT;
+    mat_load_t(RinvT, p.R_inv + (size_t)b * M * M, M, M, M, L);
+    double zr[2], zc[2][2];
+#pragma unroll
+    for (int I = 0; I < 2; ++I) zr[I] = (L.row(I) < D) ? p.z0[(size_t)b * D + L.row(I)] : 0.0;
+#pragma unroll
+    for (int J = 0; J < 2; ++J)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) zc[J][s] = (L.col(J, s) < D) ? p.z0[(size_t)b * D + L.col(J, s)] : 0.0;
+    PrefixL<D> P;
+    mat_zero(P.eb); mat_zero(P.fb); mat_zero(P.gb);
+    int status = 0;
+    ArgMin am;
+    am.init();
+    const double wexp = p.w_explicit ? p.w_explicit[b] : 0.0;
+    const size_t base = (size_t)b * p.N;
+    for (int k = 0; k < p.T_max; ++k) {
+        {
+            Mat A, Bm, Qs;
+            mat_load(A, p.A_aug + (base + k) * D * D, D, D, D, L);
+            mat_load(Bm, p.B_aug + (base + k) * D * M, D, M, M, L);
+            mat_load(Qs, p.Q_aug + (base + k) * D * D, D, D, D, L);
+            mat_sym(Qs, L);                                                    // chol_inv symmetrises its input (utils.py:74)
+            stage_prefix_step<D, M>(k, P, Qs, A, Bm, RinvT, L, scratch, p.jitter, p.max_tries, status);
+        }
+        Mat P0;
+        {
+            Mat QTs;
+            mat_load(QTs, p.QT + (base + k) * D * D, D, D, D, L);
+            mat_sym(QTs, L);
+            query_step<D>(P, QTs, P0, L, scratch, p.jitter, p.max_tries, status);
+        }
+        double part = 0.0;                                                     // 0.5 z0^T P0 z0               (:85)
+        HOP_FOR_ELEMS(I, J, s) part = fma(zr[I] * P0.v[I][J][s], zc[J][s], part);
+        const double Jt = 0.5 * warp_sum(part);
+        if (L.lane == 0 && valid) {
+            p.J_out[(size_t)b * p.T_max + k] = Jt;
+            const int t = k + 1;
+            if (t >= p.T_min) am.push(Jt + wexp * (double)t, t);
+        }
+    }
+    if (L.lane == 0 && valid) {
+        p.T_out[b] = am.idx;
+        p.Jstar_out[b] = am.best;
+        p.status[b] = status;
+    }
+}
+
+// ---- fused form: augmented embedding built in registers from (A_k, B_k, a_k, X, U) -------------------
+template <int D, int M>
+HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch, const double* cst) {
+    using FC = FusedConst<D, M>;
+    constexpr int n = D - 1;
+    LaneGeo L;
+    L.init();
+    const bool valid = b_raw < p.B;
+    const int b = valid ? b_raw : p.B - 1;
+    double* EV = scratch + 512;   // e = wrap(X - xg)
+    double* QE = EV + 16;         // Q e  /  P e
+    double* DU = QE + 16;         // U_k - u_ref
+    int status = 0;
+
+    // R_inv = chol_inv(sym(R)) (augmented.py:23), then its transpose as the Z operand of B R^-1
+    Mat RinvT;
+    {
+        Mat Rs, Ri;
+        HOP_FOR_ELEMS(I, J, s) {
+            const int R = L.row(I), C = L.col(J, s);
+            Rs.v[I][J][s] = (R < M && C < M) ? cst[FC::RS + R * M + C] : 0.0;
+        }
+        chol_inv<M>(Rs, Ri, L, scratch, p.jitter, p.max_tries, status);
+        mat_transpose(RinvT, Ri, L);
+    }
+    const bool isx = L.lane < n;
+    const double xg_l = isx ? p.xg[(size_t)b * n + L.lane] : 0.0;
+    const bool wrap_l = isx && ((p.wrap_mask >> L.lane) & 1u);
+    const double w = p.w[b];
+    // the lane that owns element (n, n) of a block: J = 0.5 P0[n][n] because z0 = e_n (augmented.py:59)
+    constexpr int own_I = n >> 3, own_J = n >> 3, own_s = (n & 7) >> 2;
+    constexpr int own_lane = (rho_inv(n & 7) << 2) | (n & 3);
+
+    PrefixL<D> P;
+    mat_zero(P.eb); mat_zero(P.fb); mat_zero(P.gb);
+    ArgMin am;
+    am.init();
+    const size_t baseN = (size_t)b * p.N;
+    const size_t baseX = (size_t)b * (p.N + 1);
+
+    for (int k = 0; k < p.T_max; ++k) {
+        const double* Ak = p.A + (baseN + k) * n * n;
+        const double* Bk = p.Bm + (baseN + k) * n * M;
+        simt::sync();
+        double ev = 0.0;
+        if (isx) {
+            ev = p.X[(baseX + k) * n + L.lane] - xg_l;                          // e = wrap(X_k - xg)  (augmented.py:28)
+            if (wrap_l) ev = wrap_pi(ev);
+            EV[L.lane] = ev;
+        }
+        if (L.lane < M) DU[L.lane] = p.U[(size_t)b * p.u_stride + (size_t)k * M + L.lane] - cst[FC::UREF + L.lane];
+        simt::sync();
+        double qe = 0.0, qc = 0.0;
+        if (isx) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                qe = fma(cst[FC::QRAW + L.lane * n + j], EV[j], qe);            // (Q e)_i
+                qc = fma(EV[j], cst[FC::QRAW + j * n + L.lane], qc);            // (e^T Q)_i
+            }
+            QE[L.lane] = qe;
+        }
+        const double eQe = warp_sum(isx ? qc * ev : 0.0);
+        simt::sync();
+        {
+            Mat A, Bm, Qs;
+            HOP_FOR_ELEMS(I, J, s) {
+                const int R = L.row(I), C = L.col(J, s);
+                double a = 0.0, q = 0.0;
+                if (R < n && C < n) {
+                    a = Ak[R * n + C];
+                    q = cst[FC::QS + R * n + C];
+                } else if (R < n && C == n) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int c = 0; c < M; ++c) sacc = fma(Bk[R * M + c], DU[c], sacc);
+                    a = (p.a_resid ? p.a_resid[(baseN + k) * n + R] : 0.0) - sacc;   // a_k - B_k du   (augmented.py:50)
+                    q = QE[R];
+                } else if (R == n && C < n) {
+                    q = QE[C];
+                } else if (R == n && C == n) {
+                    a = 1.0;
+                    q = eQe + 2.0 * w + p.rho_reg;                                    // augmented.py:37
+                }
+                A.v[I][J][s] = a;
+                Qs.v[I][J][s] = q;
+                Bm.v[I][J][s] = (R < n && C < M) ? Bk[R * M + C] : 0.0;
+            }
+            stage_prefix_step<D, M>(k, P, Qs, A, Bm, RinvT, L, scratch, p.jitter, p.max_tries, status);
+        }
+        // ---- terminal block QT_{k+1} from X[k+1] (augmented.py:78-86)
+        simt::sync();
+        double et = 0.0;
+        if (isx) {
+            et = p.X[(baseX + k + 1) * n + L.lane] - xg_l;
+            if (wrap_l) et = wrap_pi(et);
+            EV[L.lane] = et;
+        }
+        simt::sync();
+        double px = 0.0;
+        if (isx) {
+#pragma unroll
+            for (int j = 0; j < n; ++j) px = fma(cst[FC::PF + L.lane * n + j], EV[j], px);   // (P e)_i
+            QE[L.lane] = px;
+        }
+        const double ePe = warp_sum(isx ? et * px : 0.0);
+        simt::sync();
+        Mat P0;
+        {
+            Mat QTs;
+            HOP_FOR_ELEMS(I, J, s) {
+                const int R = L.row(I), C = L.col(J, s);
+                double q = 0.0;
+                if (R < n && C < n) q = cst[FC::PF + R * n + C];
+                else if (R < n && C == n) q = QE[R];
+                else if (R == n && C < n) q = QE[C];
+                else if (R == n && C == n) q = 2.0 * (0.5 * ePe) + p.rho_reg;
+                QTs.v[I][J][s] = q;
+            }
+            query_step<D>(P, QTs, P0, L, scratch, p.jitter, p.max_tries, status);
+        }
+        const double Jt = 0.5 * simt::shfl(P0.v[own_I][own_J][own_s], own_lane, 32);
+        if (L.lane == 0 && valid) {
+            p.J_out[(size_t)b * p.T_max + k] = Jt;
+            const int t = k + 1;
+            if (t >= p.T_min) am.push(Jt, t);
+        }
+    }
+    if (L.lane == 0 && valid) {
+        p.T_out[b] = am.idx;
+        p.Jstar_out[b] = am.best;
+        p.status[b] = status;
+    }
+}
+
+}}  // namespace hop::mma

@@ -20,5 +20,11 @@ HOP_DEVICE double shfl(double v, int src_in_group, int width) { return __shfl_sy
 HOP_DEVICE double shfl_xor(double v, int mask, int width) { return __shfl_xor_sync(0xffffffffu, v, mask, width); }
 HOP_DEVICE unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 HOP_DEVICE bool all(bool p) { return __all_sync(0xffffffffu, p) != 0; }
+// D(8x8) += A(8x4) * B(4x8) in fp64 on the tensor pipe (SASS: DMMA.8x8x4).  Fragments (g = lane>>2,
+// t = lane&3): a = A[g][t], b = B[t][g], c0/c1 = C[g][2t], C[g][2t+1].
+HOP_DEVICE void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 }}  // namespace hop::simt
 #endif
