@@ -50,7 +50,7 @@ def s1_x0(B, seed=0):
 # (window rel tol, rel tol at T*, allowed |T - T_ref|)
 J_TOL = {
     "DoubleIntegrator": (1e-5, 1e-7, 0),
-    "Quadrotor": (1e-6, 1e-8, 0),
+    "Quadrotor": (1e-6, 5e-8, 0),           # reference vs fp80 truth at T*: 3.5e-10 (nominal) .. 4.8e-9 (converged)
     "Segway_Balance": (None, 1e-6, 0),      # uncontrolled diverging tail beyond T*: window is O(0.1) noise
     "Cartpole_SwingUp": (None, 1e-3, 1),    # argmin gap 1.3e-5 < reference noise 3e-5: T* ill-posed
 }

@@ -83,3 +83,13 @@ def select_fused(A, Bm, a_resid, X, U, xg, w, u_ref, Q, R, Qf, wrap_mask, T_min,
     rc = (lib().emul_select_fused_mma if mma else lib().emul_select_fused)(n, m, C.byref(a))
     assert rc == 0, f"emulated kernel failed rc={rc}"
     return J, T, Js, st
+
+
+def chol_inv_mma(A):
+    """hop::mma::chol_inv (layout L, blocked Gauss-Jordan) on one matrix, through the emulator."""
+    A = _d(A)
+    d = A.shape[0]
+    X = np.zeros((d, d)); st = C.c_int(0)
+    rc = lib().emul_chol_inv_mma(d, _p(A), _p(X), C.byref(st))
+    assert rc == 0, rc
+    return X, st.value

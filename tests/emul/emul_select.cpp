@@ -84,6 +84,34 @@ int run_fused_mma(const hop::FusedArgs& p) {
 }
 }  // namespace
 
+namespace {
+struct InvJob { const double* A; double* X; int* status; int* ok_first; double* scratch; };
+template <int D>
+void inv_lane(void* a) {
+    auto* j = (InvJob*)a;
+    hop::mma::LaneGeo L;
+    L.init();
+    hop::mma::Mat S, out;
+    hop::mma::mat_load(S, j->A, D, D, D, L);
+    hop::mma::mat_sym(S, L);
+    int st = 0;
+    hop::mma::chol_inv<D>(S, out, L, j->scratch, 1e-9, 8, st);
+    HOP_FOR_ELEMS(I, J, s) {
+        const int R = L.row(I), C = L.col(J, s);
+        if (R < D && C < D) j->X[R * D + C] = out.v[I][J][s];
+    }
+    if (L.lane == 0) *j->status = st;
+}
+}  // namespace
+extern "C" int emul_chol_inv_mma(int d, const double* A, double* X, int* status) {
+    std::vector<double> scratch(hop::mma::kWarpScratch, 0.0);
+    InvJob j{A, X, status, nullptr, scratch.data()};
+    if (d == 13) return hop::simt::run_warp(inv_lane<13>, &j);
+    if (d == 12) return hop::simt::run_warp(inv_lane<12>, &j);
+    if (d == 4) return hop::simt::run_warp(inv_lane<4>, &j);
+    return -2;
+}
+
 extern "C" int emul_select_generic_mma(int d, int m, const hop::SelectArgs* p) {
     if (d == 12 && m == 4) return run_generic_mma<12, 4>(*p);
     if (d == 13 && m == 4) return run_generic_mma<13, 4>(*p);

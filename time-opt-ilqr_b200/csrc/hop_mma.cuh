@@ -90,39 +90,60 @@ HOP_DEVICE bool mat_all_finite(const Mat& M) {
     return simt::all(fin);
 }
 
-// One in-place Gauss-Jordan inversion attempt of the leading D x D block (no pivoting).  Returns
-// (warp-uniform) whether all D pivots were > 0 <=> np.linalg.cholesky would have succeeded.
+// 1/p for a pivot.  Device: MUFU.RCP64H seed + two Newton steps (<= 1 ulp; the IEEE-correct `1.0/p`
+// costs ~3x the instructions and sits on the critical path of every elimination step).
+HOP_DEVICE double pivot_rcp(double p) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    double e = fma(-p, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-p, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+#else
+    return 1.0 / p;
+#endif
+}
+
+// One in-place Gauss-Jordan inversion attempt of the leading D x D block (no pivoting, natural pivot
+// order).  The pivots met are those of LDL^T, so "some pivot <= 0" <=> np.linalg.cholesky fails; the
+// function returns (warp-uniform) whether all D pivots were > 0.
+//
+// NOTE (numerics): a blocked (8, D-8) elimination with DMMA Schur updates was tried and rejected: it
+// needs the explicit inverse of the leading tile, and for the query matrices X_t + Gbar (one ~1e8
+// direction from the rank-deficient terminal block, augmented.py:85) that loses the last pivot
+// completely (-3.6 instead of +1e-3).  The sequential sweep below forms every pivot as a running
+// Schur complement, like Cholesky, and keeps it to ~1e-8 absolute.
 template <int D>
 HOP_DEVICE bool gj_attempt(Mat& a, const LaneGeo& L) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-        constexpr int dummy = 0; (void)dummy;
-        const int Ij = j >> 3, gj = rho_inv(j & 7);          // pivot row lives on lanes (gj, *), tile row Ij
-        const int Jj = j >> 3, tj = j & 3, sj = (j & 7) >> 2;  // pivot column: tile col Jj, lanes (*, tj), slot sj
+        const int Ij = j >> 3, gj = rho_inv(j & 7);             // pivot row: tile row Ij, lanes (gj, *)
+        const int Jj = j >> 3, tj = j & 3, sj = (j & 7) >> 2;   // pivot column: tile col Jj, lanes (*, tj), slot sj
         const double p = simt::shfl(a.v[Ij][Jj][sj], (gj << 2) | tj, 32);
         ok = ok && (p > 0.0);
-        const double rinv = 1.0 / p;
-        double pr[2][2], pc[2];
+        const double rinv = pivot_rcp(p);
+        double pr[2][2], f[2];
 #pragma unroll
         for (int J = 0; J < 2; ++J)
 #pragma unroll
             for (int s = 0; s < 2; ++s) pr[J][s] = simt::shfl(a.v[Ij][J][s], (gj << 2) | L.t, 32);   // M[j][my cols]
 #pragma unroll
-        for (int I = 0; I < 2; ++I) pc[I] = simt::shfl(a.v[I][Jj][sj], (L.g << 2) | tj, 32);          // M[my rows][j]
-#pragma unroll
-        for (int I = 0; I < 2; ++I) {
-            const bool isrow = (I == Ij) && (L.g == gj);
-            const double nf = isrow ? rinv : -(pc[I] * rinv);
+        for (int I = 0; I < 2; ++I) f[I] = simt::shfl(a.v[I][Jj][sj], (L.g << 2) | tj, 32) * rinv;   // M[my rows][j] / p
+        HOP_FOR_ELEMS(I, J, s) a.v[I][J][s] = fma(-f[I], pr[J][s], a.v[I][J][s]);
+        const bool isrow = (L.g == gj), iscol = (L.t == tj);
+        if (isrow) {                                             // pivot row: M[j][c] / p
 #pragma unroll
             for (int J = 0; J < 2; ++J)
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const bool iscol = (J == Jj) && (s == sj) && (L.t == tj);
-                    const double base = isrow ? 0.0 : a.v[I][J][s];
-                    const double upd = fma(nf, pr[J][s], base);
-                    a.v[I][J][s] = iscol ? nf : upd;
-                }
+                for (int s = 0; s < 2; ++s) a.v[Ij][J][s] = pr[J][s] * rinv;
+        }
+        if (iscol) {                                             // pivot column: -M[i][j] / p ; pivot: 1 / p
+            a.v[0][Jj][sj] = -f[0];
+            a.v[1][Jj][sj] = -f[1];
+            if (isrow) a.v[Ij][Jj][sj] = rinv;
         }
     }
     return ok;
