@@ -164,7 +164,8 @@ def run_hop(args):
     x0_host.copy_(torch.from_numpy(s1_x0(B, seed=rank)))
 
     # ---- resident inputs for the kernel-only number: rollout + linearisation done once, on device
-    sel = api.HorizonSelector(case, B, device=dev)
+    mode = api.MODE_FAST if args.mode == "fast" else api.MODE_EXACT
+    sel = api.HorizonSelector(case, B, device=dev, mode=mode)
     x0_dev = x0_host.to(dev)
     res = sel(x0_dev)                                   # also warms everything up
     X, A, Bm = sel.views()   # (X, A, Bm) stay resident in the selector's workspace
@@ -216,11 +217,11 @@ def run_hop(args):
     J_h = torch.empty((B, T_max), dtype=torch.float64).pin_memory().numpy()
     x0_np = x0_host.numpy()
     for _ in range(max(args.warmup, 3)):
-        api.select_horizon_host(case, x0_np, out=(J_h, T_h, Js_h, st_h))
+        api.select_horizon_host(case, x0_np, mode=mode, out=(J_h, T_h, Js_h, st_h))
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        api.select_horizon_host(case, x0_np, out=(J_h, T_h, Js_h, st_h))
+        api.select_horizon_host(case, x0_np, mode=mode, out=(J_h, T_h, Js_h, st_h))
     torch.cuda.synchronize(dev)
     el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -250,7 +251,7 @@ def run_hop(args):
     ach_tf = flop_launch / (ms_launch * 1e-3) / 1e12
     ach_gb = byte_launch / (ms_launch * 1e-3) / 1e9
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": ach_tf / tf.value,
-                "traffic": None, "kernel": "k_select_fused<13,4,16>",
+                "traffic": None, "kernel": "k_select_fused_mma<13,4,%d>" % mode,
                 "peak_source": "DFMA microbenchmark in this run (hop_probe_fp64_tflops); nominal 37.2 TFLOP/s",
                 "algorithmic_flop_per_solve": f_alg(N_HORIZON, D_AUG, M_CTRL),
                 "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
@@ -276,7 +277,7 @@ def run_hop(args):
             "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": "S1 quadrotor n=12 m=4 d=13 N=128 T in [40,128] (iteration-0 HOP selection)",
-                       "batch_per_gpu": B, "global_batch": world * B, "mode": "exact-sequential",
+                       "batch_per_gpu": B, "global_batch": world * B, "mode": args.mode + "-sequential",
                        "l2": "inputs (A,B,X = %.1f GB per GPU) exceed the 126 MB L2" % (byte_launch / 1e9),
                        "parallelism": f"batch-sharded x{world}, final all_gather of T*/J*" if world > 1 else "single GPU"},
             "clocks": clocks,
@@ -297,6 +298,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["hop", "reference"], default="hop")
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU (weak scaling)")
+    ap.add_argument("--mode", choices=["exact", "fast"], default="fast",
+                    help="selection variant (include/hop_b200.h HOP_MODE_*); both compute the same function")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -35,8 +35,12 @@ enum { HOP_E_BADARG = -1, HOP_E_UNSUPPORTED_DIMS = -2, HOP_E_NO_DEVICE = -3, HOP
 enum { HOP_ST_OK = 0, HOP_ST_NONFINITE = 1, HOP_ST_LINALG = 2, HOP_ST_ERRMASK = 0xff,
        HOP_ST_FLAG_RETRY = 0x100, HOP_ST_FLAG_LU = 0x200 };
 
-/* selection variants */
-enum { HOP_MODE_EXACT = 0 /* sequential sweep in the reference's operation order */ };
+/* selection variants (both are sequential in k and compute the same function)
+ *   EXACT: every augmented block is materialised and inverted through the generic chol_inv, in the
+ *          reference's operation order.
+ *   FAST : fused entry points only (ignored elsewhere): closed-form block inverses for E_k and X_t,
+ *          pivot-only evaluation of J(t) = 0.5 / pivot_n(X0), _sym only on the carried state. */
+enum { HOP_MODE_EXACT = 0, HOP_MODE_FAST = 1 };
 
 /* device dynamics registry (systems.py closures cannot run on the GPU) */
 enum { HOP_SYS_DOUBLE_INTEGRATOR = 0, /* systems.py:28-50   params [dt]                               */

@@ -65,20 +65,29 @@ int run_generic_mma(const hop::SelectArgs& p) {
     return 0;
 }
 template <int D, int M>
-struct MmaFusedJob { const hop::FusedArgs* p; int b; double* scratch; const double* cst; };
-template <int D, int M>
+struct MmaFusedJob { const hop::FusedArgs* p; int b; double* scratch; double* cst; };
+template <int D, int M, int MODE>
 void mma_fused_lane(void* a) {
     auto* j = (MmaFusedJob<D, M>*)a;
-    hop::mma::select_fused_body<D, M>(*j->p, j->b, j->scratch, j->cst);
+    hop::mma::select_fused_body<D, M, MODE>(*j->p, j->b, j->scratch, j->cst);
+}
+template <int D, int M>
+void mma_fast_const_lane(void* a) {
+    auto* j = (MmaFusedJob<D, M>*)a;
+    hop::mma::fast_const_fill_warp<D, M>(*j->p, j->cst, j->scratch);
 }
 template <int D, int M>
 int run_fused_mma(const hop::FusedArgs& p) {
     std::vector<double> scratch(hop::mma::kWarpScratch, -7.0);
-    std::vector<double> cst(hop::FusedConst<D, M>::SIZE, 0.0);
+    std::vector<double> cst(hop::mma::FastConst<D, M>::SIZE, 0.0);
     hop::fused_const_fill<D, M>(p, cst.data(), 0, 1);
+    if (p.mode == 1) {
+        MmaFusedJob<D, M> j{&p, 0, scratch.data(), cst.data()};
+        if (hop::simt::run_warp(mma_fast_const_lane<D, M>, &j)) return -1;
+    }
     for (int b = 0; b < p.B; ++b) {
         MmaFusedJob<D, M> j{&p, b, scratch.data(), cst.data()};
-        if (hop::simt::run_warp(mma_fused_lane<D, M>, &j)) return -1;
+        if (hop::simt::run_warp(p.mode == 1 ? mma_fused_lane<D, M, 1> : mma_fused_lane<D, M, 0>, &j)) return -1;
     }
     return 0;
 }

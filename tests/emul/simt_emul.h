@@ -10,7 +10,7 @@
 #include <cstddef>
 
 #define HOP_DEVICE inline
-#define HOP_DEVICE_NOINLINE
+#define HOP_DEVICE_NOINLINE inline
 
 using std::isfinite;
 

@@ -76,13 +76,14 @@ def test_emulated_dmma_generic_kernel_matches_oracle(d, m, N):
     assert np.array_equal(T, np.argmin(Jo + w[:, None] * np.arange(1, N + 1), axis=1) + 1)
 
 
-def test_emulated_dmma_fused_kernel_matches_reference_golden():
+@pytest.mark.parametrize("mode", [0, 1])
+def test_emulated_dmma_fused_kernel_matches_reference_golden(mode):
     g = golden("case_Quadrotor")
     F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case("Quadrotor", N=128)
     T_max = 60
     J, T, Js, st = emul.select_fused(g["A_fwd"][None], g["B_fwd"][None], g["a_resid"][None], g["X"][None], g["U"][None],
                                      xg[None], np.array([w]), u_ref, Q, R, O.as_terminal_weight(alpha, 12),
-                                     O.wrap_mask(wrap_idx), T_min, T_max, mma=True)
+                                     O.wrap_mask(wrap_idx), T_min, T_max, mma=True, mode=mode)
     Jr, Tr = g["J_curve0"], int(g["T0"])
     assert (st[0] & 0xFF) == 0 and int(T[0]) == Tr
     assert abs(J[0, Tr - 1] - Jr[Tr - 1]) <= 1e-8 * abs(Jr[Tr - 1])

@@ -47,7 +47,8 @@ def test_select_generic_matches_reference_golden_s2():
 
 @pytest.mark.parametrize("name", CASE_NAMES)
 @pytest.mark.parametrize("traj", ["nominal", "converged"])
-def test_select_fused_matches_reference_golden(name, traj):
+@pytest.mark.parametrize("mode", [api.MODE_EXACT, api.MODE_FAST])
+def test_select_fused_matches_reference_golden(name, traj, mode):
     g = golden("case_" + name)
     F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case(name, N=int(g["N"]))
     if traj == "nominal":
@@ -57,7 +58,7 @@ def test_select_fused_matches_reference_golden(name, traj):
         A, Bm = O.linearize(F.hop_sys, F.hop_params, X, U)
         Jr, Tr = g["conv_J_curve"], int(g["conv_T"])
     sel = api.select_fused_batched(_t(A[None]), _t(Bm[None]), _t(X[None]), _t(U[None]), xg, w, u_ref, Q, R, alpha,
-                                   T_min, T_max, wrap_idx)
+                                   T_min, T_max, wrap_idx, mode=mode)
     J = sel.J.cpu().numpy()[0]
     tol_win, tol_star, dT = J_TOL[name]
     assert (int(sel.status[0]) & 0xFF) == 0
@@ -131,14 +132,15 @@ def test_rollout_divergence_guard_nan_fills_like_the_reference():
     assert np.isfinite(X[0]).all() and np.isfinite(X[1, 0]).all() and np.isnan(X[1, 1:]).all()
 
 
-def test_s1_from_x0_device_and_host_paths_match_reference_and_oracle():
+@pytest.mark.parametrize("mode", [api.MODE_EXACT, api.MODE_FAST])
+def test_s1_from_x0_device_and_host_paths_match_reference_and_oracle(mode):
     """Headline workload S1: quadrotor n=12, N=128, x0 ~ x0 + sigma xi (first 16 = reference golden)."""
     g = golden("s1_quadrotor_batch")
     case = cases.make_case("Quadrotor", N=128)
     F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = case
     B = 300
     x0s = s1_x0(B)
-    sel = api.select_horizon_batched(case, _t(x0s))
+    sel = api.select_horizon_batched(case, _t(x0s), mode=mode)
     T = sel.T_star.cpu().numpy(); J = sel.J.cpu().numpy()
     assert not (sel.status.cpu().numpy() & 0xFF).any()
     assert np.array_equal(T[:16], g["T"])                                          # vs the reference
@@ -152,7 +154,7 @@ def test_s1_from_x0_device_and_host_paths_match_reference_and_oracle():
         gap = abs(Jo[b, T[b] - 1] - Jo[b, To[b] - 1]) / abs(Jo[b, To[b] - 1])
         assert gap < 1e-7, (b, T[b], To[b], gap)
     assert len(mism) <= 3
-    Jh, Th, Jsh, sth = api.select_horizon_host(case, x0s)
+    Jh, Th, Jsh, sth = api.select_horizon_host(case, x0s, mode=mode)
     assert np.array_equal(Th, T) and np.array_equal(Jh, J) and np.array_equal(sth, sel.status.cpu().numpy())
 
 
@@ -162,7 +164,7 @@ def test_full_size_properties_without_oracle():
     case = cases.make_case("Quadrotor", N=128)
     B = 4096
     x0s = s1_x0(B, seed=7)
-    sel = api.HorizonSelector(case, B, device=DEV)
+    sel = api.HorizonSelector(case, B, device=DEV, mode=api.MODE_FAST)
     r1 = sel(_t(x0s)); T1 = r1.T_star.clone(); J1 = r1.J.clone()
     r2 = sel(_t(x0s))
     assert torch.equal(T1, r2.T_star) and torch.equal(J1, r2.J)
@@ -172,3 +174,21 @@ def test_full_size_properties_without_oracle():
     assert int(T1.min()) >= 40 and int(T1.max()) <= 128 and torch.isfinite(J1).all()
     Jw = J1[:, 39:]
     assert torch.equal(Jw.argmin(dim=1).int() + 40, T1)
+
+
+def test_fast_and_exact_modes_agree_on_4096_instances():
+    """MODE_FAST restructures the block inverses algebraically; on the headline workload it must select
+    the same horizon as MODE_EXACT except on near-ties, and agree on J to the fp64 noise floor."""
+    case = cases.make_case("Quadrotor", N=128)
+    x0s = _t(s1_x0(4096, seed=11))
+    a = api.select_horizon_batched(case, x0s, mode=api.MODE_EXACT)
+    Ta, Ja = a.T_star.cpu().numpy(), a.J.cpu().numpy()
+    b = api.select_horizon_batched(case, x0s, mode=api.MODE_FAST)
+    Tb, Jb = b.T_star.cpu().numpy(), b.J.cpu().numpy()
+    assert not (a.status.cpu().numpy() & 0xFF).any() and not (b.status.cpu().numpy() & 0xFF).any()
+    assert rel(Jb[:, 39:], Ja[:, 39:]) <= 1e-6
+    mism = np.nonzero(Ta != Tb)[0]
+    for i in mism:
+        gap = abs(Ja[i, Ta[i] - 1] - Ja[i, Tb[i] - 1]) / abs(Ja[i, Ta[i] - 1])
+        assert gap < 1e-7
+    assert len(mism) <= 8

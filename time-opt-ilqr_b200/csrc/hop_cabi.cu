@@ -75,14 +75,14 @@ int hop_select_fused_f64(int B, int N, int n, int m, int T_min, int T_max, const
                          const double* u_ref, const double* Q, const double* R, const double* Qf, unsigned wrap_mask,
                          double q_reg, double rho_reg, int mode, double* J_out, int* Tstar_out, double* Jstar_out,
                          int* status, void* stream) {
-    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || mode != HOP_MODE_EXACT) {
-        set_last_error("hop_select_fused_f64: bad argument (need 1 <= T_min <= T_max <= N, mode = HOP_MODE_EXACT)");
+    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || (mode != HOP_MODE_EXACT && mode != HOP_MODE_FAST)) {
+        set_last_error("hop_select_fused_f64: bad argument (need 1 <= T_min <= T_max <= N, mode in {EXACT, FAST})");
         return HOP_E_BADARG;
     }
     if (int rc = need_device()) return rc;
     if (B == 0) return 0;
     FusedArgs p{B, N, T_min, T_max, kJitter, kMaxTries, A, Bm, a_resid, X, U, u_batch_stride, xg, w, u_ref, Q, R, Qf,
-                wrap_mask, q_reg, rho_reg, J_out, Tstar_out, Jstar_out, status};
+                wrap_mask, q_reg, rho_reg, mode, J_out, Tstar_out, Jstar_out, status};
     return dispatch_select_fused(n, m, p, (cudaStream_t)stream);
 }
 

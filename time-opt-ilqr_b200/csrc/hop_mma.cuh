@@ -231,6 +231,14 @@ HOP_DEVICE void chol_inv(const Mat& S, Mat& out, const LaneGeo& L, double* scrat
     }
 }
 
+// Out-of-line copy for cold call sites (fallbacks of the closed-form paths): keeps the hot loop small.
+template <int D>
+HOP_DEVICE_NOINLINE void chol_inv_cold(const Mat& S, Mat& out, double* scratch, double jitter, int max_tries, int& status) {
+    LaneGeo L;
+    L.init();
+    chol_inv<D>(S, out, L, scratch, jitter, max_tries, status);
+}
+
 // Element-wise loaders: every lane fetches its 8 entries of a rows x cols row-major block
 // (leading dimension ld); entries outside the block are zero.
 HOP_DEVICE void mat_load(Mat& M, const double* __restrict__ src, int rows, int cols, int ld, const LaneGeo& L) {

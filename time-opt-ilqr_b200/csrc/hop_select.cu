@@ -70,14 +70,18 @@ __global__ void __launch_bounds__(kMmaWarps * 32) k_select_generic_mma(const Sel
     mma::select_generic_body<D, M>(p, blockIdx.x * kMmaWarps + warp, smem + (size_t)warp * mma::kWarpScratch);
 }
 
-template <int D, int M>
+template <int D, int M, int MODE>
 __global__ void __launch_bounds__(kMmaWarps * 32) k_select_fused_mma(const FusedArgs p) {
     extern __shared__ __align__(16) double smem[];
     double* cst = smem + (size_t)kMmaWarps * mma::kWarpScratch;
+    const int warp = threadIdx.x >> 5;
     fused_const_fill<D, M>(p, cst, threadIdx.x, blockDim.x);
     __syncthreads();
-    const int warp = threadIdx.x >> 5;
-    mma::select_fused_body<D, M>(p, blockIdx.x * kMmaWarps + warp, smem + (size_t)warp * mma::kWarpScratch, cst);
+    if (MODE == 1) {   // K = (Qs + eps I)^-1, K' = (P + eps I)^-1 once per CTA
+        if (warp == 0) mma::fast_const_fill_warp<D, M>(p, cst, smem);
+        __syncthreads();
+    }
+    mma::select_fused_body<D, M, MODE>(p, blockIdx.x * kMmaWarps + warp, smem + (size_t)warp * mma::kWarpScratch, cst);
 }
 
 template <int D, int M>
@@ -87,11 +91,11 @@ static int launch_generic_mma(const SelectArgs& p, cudaStream_t st) {
     k_select_generic_mma<D, M><<<grid, kMmaWarps * 32, smem, st>>>(p);
     return check_launch("k_select_generic_mma");
 }
-template <int D, int M>
+template <int D, int M, int MODE>
 static int launch_fused_mma(const FusedArgs& p, cudaStream_t st) {
-    const size_t smem = sizeof(double) * ((size_t)kMmaWarps * mma::kWarpScratch + FusedConst<D, M>::SIZE);
+    const size_t smem = sizeof(double) * ((size_t)kMmaWarps * mma::kWarpScratch + mma::FastConst<D, M>::SIZE);
     const int grid = (p.B + kMmaWarps - 1) / kMmaWarps;
-    k_select_fused_mma<D, M><<<grid, kMmaWarps * 32, smem, st>>>(p);
+    k_select_fused_mma<D, M, MODE><<<grid, kMmaWarps * 32, smem, st>>>(p);
     return check_launch("k_select_fused_mma");
 }
 
@@ -108,7 +112,7 @@ int dispatch_select_generic(int d, int m, const SelectArgs& p, cudaStream_t st) 
 int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st) {
     if (n == 2 && m == 1) return launch_fused<3, 1, 4>(p, st);
     if (n == 4 && m == 1) return launch_fused<5, 1, 8>(p, st);
-    if (n == 12 && m == 4) return launch_fused_mma<13, 4>(p, st);
+    if (n == 12 && m == 4) return p.mode == HOP_MODE_FAST ? launch_fused_mma<13, 4, 1>(p, st) : launch_fused_mma<13, 4, 0>(p, st);
     set_last_error("hop_select_fused_f64: (n, m) not instantiated; supported: (2,1) (4,1) (12,4)");
     return HOP_E_UNSUPPORTED_DIMS;
 }

@@ -33,6 +33,7 @@ struct FusedArgs {
     const double *u_ref, *Q, *R, *Qf;          // shared case constants: [m], [n][n], [m][m], [n][n]
     unsigned wrap_mask;
     double q_reg, rho_reg;
+    int mode;                                  // HOP_MODE_EXACT / HOP_MODE_FAST
     double* J_out;
     int* T_out;
     double* Jstar_out;

@@ -13,7 +13,7 @@
 
 namespace hop { namespace mma {
 
-constexpr int kWarpScratch = 512 + 64;   // doubles of shared memory per warp: LU scratch + small vectors
+constexpr int kWarpScratch = 512 + 64;   // doubles of shared memory per warp: LU scratch (512) + EV(16) QE(16) DU(8) YV(16) + pad
 
 template <int D>
 struct PrefixL { Mat eb, fb, gb; };
@@ -144,10 +144,92 @@ HOP_DEVICE void select_generic_body(const SelectArgs& p, int b_raw, double* scra
 }
 
 // ---- fused form: augmented embedding built in registers from (A_k, B_k, a_k, X, U) -------------------
+//
+// MODE 0 (exact): every block of augmented.py is materialised (in registers) and goes through the
+//   generic chol_inv, exactly as the reference does.
+// MODE 1 (fast): same function, restructured where the embedding makes a block inverse available in
+//   closed form (all algebraically exact, the jitter eps = 1e-9 is kept where the reference adds it):
+//     * E_k = chol_inv(Q_aug[k]):  Q_aug + eps I = [[Qs + eps I, q], [q^T, c + eps]] with the SAME top-left
+//       block for every k, so with K = (Qs + eps I)^-1 (once per launch), y = K q, sigma = c + eps - q^T y:
+//           E_k = [[K + y y^T / sigma, -y / sigma], [-y^T / sigma, 1 / sigma]]
+//     * X_t = chol_inv(QT_t): same with K' = (P + eps I)^-1, p = P e and the cancellation-free pivot
+//           sigma' = rho + eps + eps * (K' p)^T e     (= e^T P e + rho + eps - p^T K' p exactly)
+//     * z0 = e_n, so J(t) = 0.5 P0[n][n] = 0.5 / (last LDL^T pivot of X0 + eps I): forward elimination only.
+//     * _sym is kept on the carried state (Ebar, Gbar); it is dropped where the operand is symmetric by
+//       construction (E_k + Gbar, X_t + Gbar) or only feeds the pivots (G_k, X0).
+//   Any non-positive pivot falls back to the generic chol_inv (jitter ladder / LU) of MODE 0.
 template <int D, int M>
+struct FastConst {
+    static constexpr int n = D - 1;
+    static constexpr int KQ = FusedConst<D, M>::SIZE, KP = KQ + n * n, FLAG = KP + n * n, SIZE = FLAG + 2;
+};
+
+// One warp computes K = (Qs + eps I)^-1 and K' = (P + eps I)^-1 into the CTA constant block.
+template <int D, int M>
+HOP_DEVICE void fast_const_fill_warp(const FusedArgs& p, double* cst, double* scratch) {
+    using FC = FusedConst<D, M>;
+    using XC = FastConst<D, M>;
+    constexpr int n = D - 1;
+    LaneGeo L;
+    L.init();
+    int st = 0;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        Mat S, Kinv;
+        HOP_FOR_ELEMS(I, J, s) {
+            const int R = L.row(I), C = L.col(J, s);
+            S.v[I][J][s] = (R < n && C < n) ? cst[(which ? FC::PF : FC::QS) + R * n + C] : 0.0;
+        }
+        chol_inv<n>(S, Kinv, L, scratch, p.jitter, p.max_tries, st);
+        mat_sym(Kinv, L);
+        HOP_FOR_ELEMS(I, J, s) {
+            const int R = L.row(I), C = L.col(J, s);
+            if (R < n && C < n) cst[(which ? XC::KP : XC::KQ) + R * n + C] = Kinv.v[I][J][s];
+        }
+    }
+    if (L.lane == 0) cst[XC::FLAG] = (st != 0) ? 1.0 : 0.0;   // ladder needed: the closed forms do not apply
+}
+
+// Last LDL^T pivot of (S + eps I) by forward elimination (no back-substitution).  ok &= all pivots > 0.
+template <int D>
+HOP_DEVICE double last_pivot(const Mat& S, double eps, const LaneGeo& L, bool& ok) {
+    Mat a;
+    HOP_FOR_ELEMS(I, J, s) {
+        const int R = L.row(I), C = L.col(J, s);
+        a.v[I][J][s] = S.v[I][J][s] + ((R == C && R < D) ? eps : 0.0);
+    }
+    double p = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const int Ij = j >> 3, gj = rho_inv(j & 7), Jj = j >> 3, tj = j & 3, sj = (j & 7) >> 2;
+        p = simt::shfl(a.v[Ij][Jj][sj], (gj << 2) | tj, 32);
+        ok = ok && (p > 0.0);
+        if (j == D - 1) break;
+        const double rinv = pivot_rcp(p);
+        // rows/cols <= j are dead from here on: once j >= 8 only tile (1,1) is live
+        double pr[2][2];
+#pragma unroll
+        for (int J = (j >= 8 ? 1 : 0); J < 2; ++J)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) pr[J][s] = simt::shfl(a.v[Ij][J][s], (gj << 2) | L.t, 32);
+#pragma unroll
+        for (int I = (j >= 8 ? 1 : 0); I < 2; ++I) {
+            const double f = simt::shfl(a.v[I][Jj][sj], (L.g << 2) | tj, 32) * rinv;
+#pragma unroll
+            for (int J = (j >= 8 ? 1 : 0); J < 2; ++J)
+#pragma unroll
+                for (int s = 0; s < 2; ++s) a.v[I][J][s] = fma(-f, pr[J][s], a.v[I][J][s]);
+        }
+    }
+    return p;
+}
+
+template <int D, int M, int MODE>
 HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch, const double* cst) {
     using FC = FusedConst<D, M>;
+    using XC = FastConst<D, M>;
     constexpr int n = D - 1;
+    constexpr int NT = (D + 7) / 8, KB = (D + 3) / 4;
     LaneGeo L;
     L.init();
     const bool valid = b_raw < p.B;
@@ -155,6 +237,7 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch
     double* EV = scratch + 512;   // e = wrap(X - xg)
     double* QE = EV + 16;         // Q e  /  P e
     double* DU = QE + 16;         // U_k - u_ref
+    double* YV = DU + 8;          // K q  /  K' p      (fast mode)
     int status = 0;
 
     // R_inv = chol_inv(sym(R)) (augmented.py:23), then its transpose as the Z operand of B R^-1
@@ -169,9 +252,11 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch
         mat_transpose(RinvT, Ri, L);
     }
     const bool isx = L.lane < n;
+    const int lx = isx ? L.lane : 0;
     const double xg_l = isx ? p.xg[(size_t)b * n + L.lane] : 0.0;
     const bool wrap_l = isx && ((p.wrap_mask >> L.lane) & 1u);
     const double w = p.w[b];
+    const bool closed_ok = (MODE == 1) && (cst[XC::FLAG] == 0.0);
     // the lane that owns element (n, n) of a block: J = 0.5 P0[n][n] because z0 = e_n (augmented.py:59)
     constexpr int own_I = n >> 3, own_J = n >> 3, own_s = (n & 7) >> 2;
     constexpr int own_lane = (rho_inv(n & 7) << 2) | (n & 3);
@@ -205,34 +290,103 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch
             QE[L.lane] = qe;
         }
         const double eQe = warp_sum(isx ? qc * ev : 0.0);
+        const double corner = eQe + 2.0 * w + p.rho_reg;                        // augmented.py:37
         simt::sync();
-        {
-            Mat A, Bm, Qs;
+        Mat A, Bm;
+        HOP_FOR_ELEMS(I, J, s) {
+            const int R = L.row(I), C = L.col(J, s);
+            double a = 0.0;
+            if (R < n && C < n) {
+                a = Ak[R * n + C];
+            } else if (R < n && C == n) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int c = 0; c < M; ++c) sacc = fma(Bk[R * M + c], DU[c], sacc);
+                a = (p.a_resid ? p.a_resid[(baseN + k) * n + R] : 0.0) - sacc;  // a_k - B_k du   (augmented.py:50)
+            } else if (R == n && C == n) {
+                a = 1.0;
+            }
+            A.v[I][J][s] = a;
+            Bm.v[I][J][s] = (R < n && C < M) ? Bk[R * M + C] : 0.0;
+        }
+        // ---------------- stage: E_k
+        Mat E;
+        bool have_E = false;
+        if (closed_ok) {
+            double y = 0.0;
+            if (isx) {
+#pragma unroll
+                for (int j = 0; j < n; ++j) y = fma(cst[XC::KQ + L.lane * n + j], QE[j], y);   // y = K q
+                YV[L.lane] = y;
+            }
+            const double sigma = (corner + p.jitter) - warp_sum(isx ? qe * y : 0.0);
+            simt::sync();
+            if (simt::all(sigma > 0.0)) {
+                const double rs = 1.0 / sigma;
+                HOP_FOR_ELEMS(I, J, s) {
+                    const int R = L.row(I), C = L.col(J, s);
+                    double e = 0.0;
+                    if (R < n && C < n) e = fma(YV[R] * YV[C], rs, cst[XC::KQ + R * n + C]);
+                    else if (R < n && C == n) e = -YV[R] * rs;
+                    else if (R == n && C < n) e = -YV[C] * rs;
+                    else if (R == n && C == n) e = rs;
+                    E.v[I][J][s] = e;
+                }
+                have_E = true;
+            }
+        }
+        if (!have_E) {
+            Mat Qs;
             HOP_FOR_ELEMS(I, J, s) {
                 const int R = L.row(I), C = L.col(J, s);
-                double a = 0.0, q = 0.0;
-                if (R < n && C < n) {
-                    a = Ak[R * n + C];
-                    q = cst[FC::QS + R * n + C];
-                } else if (R < n && C == n) {
-                    double sacc = 0.0;
-#pragma unroll
-                    for (int c = 0; c < M; ++c) sacc = fma(Bk[R * M + c], DU[c], sacc);
-                    a = (p.a_resid ? p.a_resid[(baseN + k) * n + R] : 0.0) - sacc;   // a_k - B_k du   (augmented.py:50)
-                    q = QE[R];
-                } else if (R == n && C < n) {
-                    q = QE[C];
-                } else if (R == n && C == n) {
-                    a = 1.0;
-                    q = eQe + 2.0 * w + p.rho_reg;                                    // augmented.py:37
-                }
-                A.v[I][J][s] = a;
+                double q = 0.0;
+                if (R < n && C < n) q = cst[FC::QS + R * n + C];
+                else if (R < n && C == n) q = QE[R];
+                else if (R == n && C < n) q = QE[C];
+                else if (R == n && C == n) q = corner;
                 Qs.v[I][J][s] = q;
-                Bm.v[I][J][s] = (R < n && C < M) ? Bk[R * M + C] : 0.0;
             }
-            stage_prefix_step<D, M>(k, P, Qs, A, Bm, RinvT, L, scratch, p.jitter, p.max_tries, status);
+            if (MODE == 0) chol_inv<D>(Qs, E, L, scratch, p.jitter, p.max_tries, status);   // E_k = chol_inv(Q_k) (:59)
+            else chol_inv_cold<D>(Qs, E, scratch, p.jitter, p.max_tries, status);
         }
-        // ---- terminal block QT_{k+1} from X[k+1] (augmented.py:78-86)
+        // ---------------- prefix
+        {
+            constexpr int KBM = (M + 3) / 4, NTM = (M + 7) / 8;
+            Mat W;
+            if (k > 0) {
+                Mat S;
+                mat_add(S, E, P.gb);
+                if (MODE == 0) mat_sym(S, L);
+                chol_inv<D>(S, W, L, scratch, p.jitter, p.max_tries, status);  // W = chol_inv(E_k + Gbar)     (:72)
+            }
+            Mat Ft, G;
+            mma_nt<NT, NT, KB, false>(Ft, A, E);                               // F_k^T = A_k E_k
+            mma_nt<NT, NT, KB, false>(G, Ft, A);                               // (A_k E_k) A_k^T              (:61)
+            {
+                Mat BR;
+                mma_nt<NT, NTM, KBM, false>(BR, Bm, RinvT);                    // B_k R^-1
+                mma_nt<NT, NT, KBM, true>(G, BR, Bm);                          // + (B_k R^-1) B_k^T
+            }
+            if (MODE == 0 || k == 0) mat_sym(G, L);                            // G_k = sym(...)               (:64)
+            if (k == 0) {
+                mma_nt<NT, NT, KB, false>(P.fb, E, A);                         // F_0 = E_0 A_0^T              (:60)
+                mat_copy(P.eb, E);
+                mat_copy(P.gb, G);
+            } else {
+                Mat T1, acc;
+                mma_nt<NT, NT, KB, false>(T1, P.fb, W);                        // Fbar W                       (:73)
+                mma_nt<NT, NT, KB, false>(acc, T1, P.fb);                      // (Fbar W) Fbar^T
+                mat_sub(P.eb, P.eb, acc);
+                mat_sym(P.eb, L);                                              // Ebar                         (:73)
+                mma_nt<NT, NT, KB, false>(acc, T1, Ft);                        // (Fbar W) F_k  -> new Fbar    (:74)
+                mma_nt<NT, NT, KB, false>(T1, Ft, W);                          // F_k^T W                      (:75)
+                mat_copy(P.fb, acc);
+                mma_nt<NT, NT, KB, false>(acc, T1, Ft);                        // (F_k^T W) F_k
+                mat_sub(P.gb, G, acc);
+                mat_sym(P.gb, L);                                              // Gbar                         (:75)
+            }
+        }
+        // ---------------- terminal block QT_{k+1} from X[k+1] (augmented.py:78-86) and the query (:77-86)
         simt::sync();
         double et = 0.0;
         if (isx) {
@@ -249,8 +403,32 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch
         }
         const double ePe = warp_sum(isx ? et * px : 0.0);
         simt::sync();
-        Mat P0;
-        {
+        Mat Xt;
+        bool have_Xt = false;
+        if (closed_ok) {
+            double y = 0.0;
+            if (isx) {
+#pragma unroll
+                for (int j = 0; j < n; ++j) y = fma(cst[XC::KP + L.lane * n + j], QE[j], y);   // y' = K' p
+                YV[L.lane] = y;
+            }
+            const double sigma = (p.rho_reg + p.jitter) + p.jitter * warp_sum(isx ? y * et : 0.0);
+            simt::sync();
+            if (simt::all(sigma > 0.0)) {
+                const double rs = 1.0 / sigma;
+                HOP_FOR_ELEMS(I, J, s) {
+                    const int R = L.row(I), C = L.col(J, s);
+                    double x = 0.0;
+                    if (R < n && C < n) x = fma(YV[R] * YV[C], rs, cst[XC::KP + R * n + C]);
+                    else if (R < n && C == n) x = -YV[R] * rs;
+                    else if (R == n && C < n) x = -YV[C] * rs;
+                    else if (R == n && C == n) x = rs;
+                    Xt.v[I][J][s] = x;
+                }
+                have_Xt = true;
+            }
+        }
+        if (!have_Xt) {
             Mat QTs;
             HOP_FOR_ELEMS(I, J, s) {
                 const int R = L.row(I), C = L.col(J, s);
@@ -261,15 +439,44 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch
                 else if (R == n && C == n) q = 2.0 * (0.5 * ePe) + p.rho_reg;
                 QTs.v[I][J][s] = q;
             }
-            query_step<D>(P, QTs, P0, L, scratch, p.jitter, p.max_tries, status);
+            if (MODE == 0) chol_inv<D>(QTs, Xt, L, scratch, p.jitter, p.max_tries, status);  // X_t = chol_inv(QT_t) (:79)
+            else chol_inv_cold<D>(QTs, Xt, scratch, p.jitter, p.max_tries, status);
         }
-        const double Jt = 0.5 * simt::shfl(P0.v[own_I][own_J][own_s], own_lane, 32);
+        double Jt = 0.0;
+        {
+            Mat Wt;
+            {
+                Mat S;
+                mat_add(S, Xt, P.gb);
+                if (MODE == 0) mat_sym(S, L);
+                chol_inv<D>(S, Wt, L, scratch, p.jitter, p.max_tries, status); // W_t                          (:82)
+            }
+            Mat T3, X0;
+            mma_nt<NT, NT, KB, false>(T3, P.fb, Wt);                           // Fbar W_t
+            mma_nt<NT, NT, KB, false>(X0, T3, P.fb);                           // (Fbar W_t) Fbar^T
+            mat_sub(X0, P.eb, X0);
+            bool done = false;
+            if (MODE == 1) {
+                bool ok = true;
+                const double piv = last_pivot<D>(X0, p.jitter, L, ok);
+                Jt = 0.5 / piv;
+                done = simt::all(ok);
+            }
+            if (!done) {
+                Mat P0;
+                mat_sym(X0, L);                                                // X0                           (:83)
+                if (MODE == 0) chol_inv<D>(X0, P0, L, scratch, p.jitter, p.max_tries, status);   // P0          (:84)
+                else chol_inv_cold<D>(X0, P0, scratch, p.jitter, p.max_tries, status);
+                Jt = 0.5 * simt::shfl(P0.v[own_I][own_J][own_s], own_lane, 32);
+            }
+        }
         if (L.lane == 0 && valid) {
             p.J_out[(size_t)b * p.T_max + k] = Jt;
             const int t = k + 1;
             if (t >= p.T_min) am.push(Jt, t);
         }
     }
+    (void)lx;
     if (L.lane == 0 && valid) {
         p.T_out[b] = am.idx;
         p.Jstar_out[b] = am.best;

@@ -22,7 +22,8 @@ import torch
 from . import _cabi
 from .cases import NPARAMS, SYS_DIMS
 
-MODE_EXACT = 0
+MODE_EXACT = 0   # reference operation order, every block through the generic chol_inv
+MODE_FAST = 1    # fused entry points: closed-form block inverses + pivot-only J(t) (same function)
 
 
 @dataclass
