@@ -25,4 +25,13 @@ void dmma(double& c0, double& c1, double a, double b);   // mma.m8n8k4.f64 seman
 // Run fn(arg) once per lane of one emulated warp.  Returns 0, or -1 if lanes exited non-uniformly
 // (some lane still waiting at a barrier when another finished), which on a GPU would be a hang.
 int run_warp(void (*fn)(void*), void* arg);
+// bulk-copy / mbarrier stand-ins: the copy completes at issue time, waits are no-ops
+inline void mbar_init(unsigned long long*, unsigned) {}
+inline void mbar_fence_init() {}
+inline void mbar_expect_tx(unsigned long long*, unsigned) {}
+inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) {
+    const char* s = (const char*)src; char* d = (char*)dst;
+    for (unsigned i = 0; i < bytes; ++i) d[i] = s[i];
+}
+inline void mbar_wait(unsigned long long*, unsigned) {}
 }}  // namespace hop::simt

@@ -1,0 +1,274 @@
+// hop_ddp_core.cuh -- per-problem device functions of the HOP-DDP iteration that surround the
+// horizon selection (one thread per problem; small dense blocks in thread-local arrays).
+//
+// Replaces (reference file:line):
+//   utils.py:96-120        chol_solve (jitter ladder, NO fallback -> LinAlgError)
+//   solver.py:65-105       cost_timeopt_true
+//   solver.py:156-230      backward_pass_truncated
+//   solver.py:233-286      forward_linesearch_fixedT
+// Operation order follows the numpy expressions (left-to-right products), with unfused mul/add so the
+// rounding matches the reference's scalar arithmetic as closely as a different BLAS allows.
+#pragma once
+#include <math.h>
+
+#include "hop_dynamics.cuh"
+
+namespace hop { namespace ddp {
+
+enum : int { DDP_OK = 0, DDP_NONFINITE = 1, DDP_LINALG = 2 };
+
+template <int N_>
+HOP_DEVICE bool all_finite(const double* x) {
+    bool f = true;
+#pragma unroll
+    for (int i = 0; i < N_; ++i) f = f && isfinite(x[i]);
+    return f;
+}
+
+// e = wrap(x - xg) on the indices of wrap_mask (utils.py:131-137)
+template <int n>
+HOP_DEVICE void wrapped_error(const double* x, const double* xg, unsigned wrap_mask, double* e) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        double v = sub(x[i], xg[i]);
+        if ((wrap_mask >> i) & 1u) v = wrap_pi(v);
+        e[i] = v;
+    }
+}
+
+// v^T (M v) as `v @ (M @ v)`
+template <int n>
+HOP_DEVICE double quad_form(const double* M, const double* v) {
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < n; ++j) s = add(s, mul(M[i * n + j], v[j]));
+        acc = add(acc, mul(v[i], s));
+    }
+    return acc;
+}
+
+// LAPACK dpotf2-style lower Cholesky of M (d x d); returns false on a non-positive pivot.
+template <int d>
+HOP_DEVICE bool cholesky_lower(const double* M, double* Lo) {
+    for (int i = 0; i < d * d; ++i) Lo[i] = 0.0;
+    for (int j = 0; j < d; ++j) {
+        double ajj = M[j * d + j];
+        for (int p = 0; p < j; ++p) ajj = sub(ajj, mul(Lo[j * d + p], Lo[j * d + p]));
+        if (!(ajj > 0.0)) return false;
+        ajj = sqrt(ajj);
+        Lo[j * d + j] = ajj;
+        const double rinv = 1.0 / ajj;
+        for (int i = j + 1; i < d; ++i) {
+            double s = M[i * d + j];
+            for (int p = 0; p < j; ++p) s = sub(s, mul(Lo[i * d + p], Lo[j * d + p]));
+            Lo[i * d + j] = mul(s, rinv);
+        }
+    }
+    return true;
+}
+
+// utils.py:96-120: solve sym(A) X = B (d x c) with the jitter ladder; DDP_LINALG when it is exhausted.
+template <int d, int c>
+HOP_DEVICE int chol_solve(const double* A, const double* Bm, double* X, double jitter, int max_tries) {
+    double S[d * d], M[d * d], Lo[d * d], Y[d * c];
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) S[i * d + j] = 0.5 * add(A[i * d + j], A[j * d + i]);
+    if (!all_finite<d * d>(S) || !all_finite<d * c>(Bm)) return DDP_NONFINITE;
+    double eps = jitter;
+    for (int t = 0; t < max_tries; ++t) {
+        for (int i = 0; i < d * d; ++i) M[i] = S[i];
+        for (int i = 0; i < d; ++i) M[i * d + i] = add(S[i * d + i], eps);
+        if (cholesky_lower<d>(M, Lo)) {
+            for (int col = 0; col < c; ++col) {
+                for (int i = 0; i < d; ++i) {
+                    double s = Bm[i * c + col];
+                    for (int p = 0; p < i; ++p) s = sub(s, mul(Lo[i * d + p], Y[p * c + col]));
+                    Y[i * c + col] = s / Lo[i * d + i];
+                }
+                for (int i = d - 1; i >= 0; --i) {
+                    double s = Y[i * c + col];
+                    for (int p = i + 1; p < d; ++p) s = sub(s, mul(Lo[p * d + i], X[p * c + col]));
+                    X[i * c + col] = s / Lo[i * d + i];
+                }
+            }
+            if (all_finite<d * c>(X)) return DDP_OK;
+        }
+        eps *= 10.0;
+    }
+    return DDP_LINALG;
+}
+
+struct CostConst {   // shared case constants, row-major
+    const double *xg, *u_ref, *Q, *R, *Qf;
+    double w;
+    unsigned wrap_mask;
+};
+
+// solver.py:65-105.  X [N+1][n], U [N][m] of ONE problem.
+template <int n, int m>
+HOP_DEVICE double cost_timeopt_true(const double* X, const double* U, const CostConst& c, int T) {
+    const double inf = HUGE_VAL;
+    if (T <= 0) return inf;
+    for (int k = 0; k <= T; ++k)
+        if (!all_finite<n>(X + (size_t)k * n)) return inf;
+    for (int k = 0; k < T; ++k)
+        if (!all_finite<m>(U + (size_t)k * m)) return inf;
+    double acc = 0.0, e[n], du[m];
+    for (int k = 0; k < T; ++k) {
+        wrapped_error<n>(X + (size_t)k * n, c.xg, c.wrap_mask, e);
+#pragma unroll
+        for (int i = 0; i < m; ++i) du[i] = sub(U[(size_t)k * m + i], c.u_ref[i]);
+        if (!all_finite<n>(e) || !all_finite<m>(du)) return inf;
+        acc = add(acc, add(add(mul(0.5, quad_form<n>(c.Q, e)), mul(0.5, quad_form<m>(c.R, du))), c.w));
+    }
+    wrapped_error<n>(X + (size_t)T * n, c.xg, c.wrap_mask, e);
+    if (!all_finite<n>(e)) return inf;
+    return add(acc, mul(0.5, quad_form<n>(c.Qf, e)));
+}
+
+// small dense helpers on thread-local row-major arrays
+template <int r, int k, int c>
+HOP_DEVICE void mm_nn(const double* A, const double* Bm, double* C) {   // C = A B
+    for (int i = 0; i < r; ++i)
+        for (int j = 0; j < c; ++j) {
+            double s = 0.0;
+            for (int l = 0; l < k; ++l) s = add(s, mul(A[i * k + l], Bm[l * c + j]));
+            C[i * c + j] = s;
+        }
+}
+template <int r, int k, int c>
+HOP_DEVICE void mm_tn(const double* A, const double* Bm, double* C) {   // C = A^T B, A is k x r
+    for (int i = 0; i < r; ++i)
+        for (int j = 0; j < c; ++j) {
+            double s = 0.0;
+            for (int l = 0; l < k; ++l) s = add(s, mul(A[l * r + i], Bm[l * c + j]));
+            C[i * c + j] = s;
+        }
+}
+
+// solver.py:156-230.  A [N][n][n], Bm [N][n][m], X, U of ONE problem; writes k_out [T][m], K_out [T][m][n].
+// *ok = 0 reproduces `return None, None, False`; a non-zero return reproduces an escaping exception.
+template <int n, int m>
+HOP_DEVICE int backward_pass(const double* A, const double* Bm, const double* X, const double* U, const CostConst& c,
+                             int T, double lm, double* k_out, double* K_out, int* ok) {
+    *ok = 0;
+    if (T <= 0) return DDP_OK;
+    double e[n], du[m], Vx[n], Vxx[n * n];
+    wrapped_error<n>(X + (size_t)T * n, c.xg, c.wrap_mask, e);
+    if (!all_finite<n>(e)) return DDP_OK;
+    for (int i = 0; i < n; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < n; ++j) s = add(s, mul(c.Qf[i * n + j], e[j]));
+        Vx[i] = s;
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) Vxx[i * n + j] = 0.5 * add(c.Qf[i * n + j], c.Qf[j * n + i]);
+    for (int k = T - 1; k >= 0; --k) {
+        const double* Ak = A + (size_t)k * n * n;
+        const double* Bk = Bm + (size_t)k * n * m;
+        wrapped_error<n>(X + (size_t)k * n, c.xg, c.wrap_mask, e);
+        for (int i = 0; i < m; ++i) du[i] = sub(U[(size_t)k * m + i], c.u_ref[i]);
+        if (!all_finite<n>(e) || !all_finite<m>(du)) return DDP_OK;
+        double Qx[n], Qu[m], Qxx[n * n], Quu[m * m], Qux[m * n], AtV[n * n], BtV[m * n], t[n * n];
+        for (int i = 0; i < n; ++i) {
+            double lx = 0.0, s = 0.0;
+            for (int j = 0; j < n; ++j) lx = add(lx, mul(c.Q[i * n + j], e[j]));
+            for (int l = 0; l < n; ++l) s = add(s, mul(Ak[l * n + i], Vx[l]));
+            Qx[i] = add(lx, s);
+        }
+        for (int i = 0; i < m; ++i) {
+            double lu = 0.0, s = 0.0;
+            for (int j = 0; j < m; ++j) lu = add(lu, mul(c.R[i * m + j], du[j]));
+            for (int l = 0; l < n; ++l) s = add(s, mul(Bk[l * m + i], Vx[l]));
+            Qu[i] = add(lu, s);
+        }
+        mm_tn<n, n, n>(Ak, Vxx, AtV);
+        mm_nn<n, n, n>(AtV, Ak, t);
+        for (int i = 0; i < n * n; ++i) Qxx[i] = add(c.Q[i], t[i]);
+        mm_tn<m, n, n>(Bk, Vxx, BtV);
+        mm_nn<m, n, m>(BtV, Bk, t);
+        for (int i = 0; i < m * m; ++i) Quu[i] = add(c.R[i], t[i]);
+        mm_nn<m, n, n>(BtV, Ak, Qux);
+        double Qreg[m * m], Ltmp[m * m];
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) Qreg[i * m + j] = add(0.5 * add(Quu[i * m + j], Quu[j * m + i]), (i == j) ? lm : 0.0);
+        if (!cholesky_lower<m>(Qreg, Ltmp)) return DDP_OK;                    // solver.py:213-216
+        double kap[m], Kk[m * n];
+        int rc = chol_solve<m, 1>(Qreg, Qu, kap, 1e-9, 8);
+        if (rc) return rc;
+        rc = chol_solve<m, n>(Qreg, Qux, Kk, 1e-9, 8);
+        if (rc) return rc;
+        for (int i = 0; i < m; ++i) kap[i] = -kap[i];
+        for (int i = 0; i < m * n; ++i) Kk[i] = -Kk[i];
+        for (int i = 0; i < m; ++i) k_out[(size_t)k * m + i] = kap[i];
+        for (int i = 0; i < m * n; ++i) K_out[(size_t)k * m * n + i] = Kk[i];
+        double KtQuu[n * m];
+        mm_tn<n, m, m>(Kk, Quu, KtQuu);
+        double Vxn[n];
+        for (int i = 0; i < n; ++i) {
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int l = 0; l < m; ++l) s1 = add(s1, mul(Kk[l * n + i], Qu[l]));
+            for (int l = 0; l < m; ++l) s2 = add(s2, mul(Qux[l * n + i], kap[l]));
+            for (int l = 0; l < m; ++l) s3 = add(s3, mul(KtQuu[i * m + l], kap[l]));
+            Vxn[i] = add(add(add(Qx[i], s1), s2), s3);                         // solver.py:224
+        }
+        double t1[n * n], t2[n * n], t3[n * n];
+        mm_tn<n, m, n>(Kk, Qux, t1);
+        mm_tn<n, m, n>(Qux, Kk, t2);
+        mm_nn<n, m, n>(KtQuu, Kk, t3);
+        for (int i = 0; i < n * n; ++i) t[i] = add(add(add(Qxx[i], t1[i]), t2[i]), t3[i]);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) Vxx[i * n + j] = 0.5 * add(t[i * n + j], t[j * n + i]);   // solver.py:225
+        for (int i = 0; i < n; ++i) Vx[i] = Vxn[i];
+        if (!all_finite<n>(Vx) || !all_finite<n * n>(Vxx)) return DDP_OK;
+    }
+    *ok = 1;
+    return DDP_OK;
+}
+
+// solver.py:233-286, alphas = (1, .5, .25, .1, .05).  Writes the accepted candidate (or a copy of the
+// nominal when nothing improved) into X_new / U_new.
+template <int SYS>
+HOP_DEVICE void forward_linesearch(const double* prm, int N, const double* X, const double* U, const CostConst& c, int T,
+                                   const double* k_list, const double* K_list, double* X_new, double* U_new,
+                                   double* J_out, int* accepted) {
+    constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
+    const double alphas[5] = {1.0, 0.5, 0.25, 0.1, 0.05};
+    const double J_old = cost_timeopt_true<n, m>(X, U, c, T);
+    for (int ai = 0; ai < 5; ++ai) {
+        const double a = alphas[ai];
+        double x[n], xn[n], u[m];
+        for (int i = 0; i < n; ++i) { x[i] = X[i]; X_new[i] = x[i]; }
+        bool ok = true;
+        for (int k = 0; k < N; ++k) {
+            for (int i = 0; i < m; ++i) u[i] = U[(size_t)k * m + i];
+            if (k < T) {
+                double dx[n];
+                for (int i = 0; i < n; ++i) {
+                    double v = sub(x[i], X[(size_t)k * n + i]);
+                    if ((c.wrap_mask >> i) & 1u) v = wrap_pi(v);
+                    dx[i] = v;
+                }
+                for (int i = 0; i < m; ++i) {
+                    double s = 0.0;
+                    for (int j = 0; j < n; ++j) s = add(s, mul(K_list[(size_t)k * m * n + i * n + j], dx[j]));
+                    u[i] = add(u[i], add(s, mul(a, k_list[(size_t)k * m + i])));
+                }
+            }
+            for (int i = 0; i < m; ++i) U_new[(size_t)k * m + i] = u[i];
+            dynamics<SYS>(prm, x, u, xn);
+            for (int i = 0; i < n; ++i) { x[i] = xn[i]; X_new[(size_t)(k + 1) * n + i] = xn[i]; }
+            if (!all_finite<n>(xn)) { ok = false; break; }
+        }
+        if (!ok) continue;
+        const double J_new = cost_timeopt_true<n, m>(X_new, U_new, c, T);
+        if (J_new < J_old) { *J_out = J_new; *accepted = 1; return; }
+    }
+    for (size_t i = 0; i < (size_t)(N + 1) * n; ++i) X_new[i] = X[i];
+    for (size_t i = 0; i < (size_t)N * m; ++i) U_new[i] = U[i];
+    *J_out = J_old;
+    *accepted = 0;
+}
+
+}}  // namespace hop::ddp

@@ -4,6 +4,8 @@
 // independent (warp-synchronous code, no CTA barrier inside the sweep), so the hardware scheduler
 // load-balances warps across the 148 SMs.  Dynamic shared memory = per-group slab (Geo::SLAB
 // doubles) [+ the CTA-wide case constants for the fused form].
+#include <cstdlib>
+
 #include "hop_common.cuh"
 #include "hop_select_body.cuh"
 #include "hop_select_mma_body.cuh"
@@ -70,8 +72,8 @@ __global__ void __launch_bounds__(kMmaWarps * 32) k_select_generic_mma(const Sel
     mma::select_generic_body<D, M>(p, blockIdx.x * kMmaWarps + warp, smem + (size_t)warp * mma::kWarpScratch);
 }
 
-template <int D, int M, int MODE>
-__global__ void __launch_bounds__(kMmaWarps * 32) k_select_fused_mma(const FusedArgs p) {
+template <int D, int M, int MODE, int MINB>
+__global__ void __launch_bounds__(kMmaWarps * 32, MINB) k_select_fused_mma(const FusedArgs p) {
     extern __shared__ __align__(16) double smem[];
     double* cst = smem + (size_t)kMmaWarps * mma::kWarpScratch;
     const int warp = threadIdx.x >> 5;
@@ -91,12 +93,30 @@ static int launch_generic_mma(const SelectArgs& p, cudaStream_t st) {
     k_select_generic_mma<D, M><<<grid, kMmaWarps * 32, smem, st>>>(p);
     return check_launch("k_select_generic_mma");
 }
-template <int D, int M, int MODE>
-static int launch_fused_mma(const FusedArgs& p, cudaStream_t st) {
+// MINB = CTAs per SM the register allocation is bounded for (2 -> 255 regs, 3 -> 168, 4 -> 128).
+static int mma_min_blocks() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("HOP_MMA_MINBLOCKS");
+        v = e ? atoi(e) : 3;
+        if (v < 2 || v > 4) v = 3;
+    }
+    return v;
+}
+template <int D, int M, int MODE, int MINB>
+static int launch_fused_mma_b(const FusedArgs& p, cudaStream_t st) {
     const size_t smem = sizeof(double) * ((size_t)kMmaWarps * mma::kWarpScratch + mma::FastConst<D, M>::SIZE);
     const int grid = (p.B + kMmaWarps - 1) / kMmaWarps;
-    k_select_fused_mma<D, M, MODE><<<grid, kMmaWarps * 32, smem, st>>>(p);
+    k_select_fused_mma<D, M, MODE, MINB><<<grid, kMmaWarps * 32, smem, st>>>(p);
     return check_launch("k_select_fused_mma");
+}
+template <int D, int M, int MODE>
+static int launch_fused_mma(const FusedArgs& p, cudaStream_t st) {
+    switch (mma_min_blocks()) {
+        case 2: return launch_fused_mma_b<D, M, MODE, 2>(p, st);
+        case 4: return launch_fused_mma_b<D, M, MODE, 4>(p, st);
+        default: return launch_fused_mma_b<D, M, MODE, 3>(p, st);
+    }
 }
 
 int dispatch_select_generic(int d, int m, const SelectArgs& p, cudaStream_t st) {

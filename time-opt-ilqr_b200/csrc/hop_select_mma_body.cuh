@@ -13,7 +13,10 @@
 
 namespace hop { namespace mma {
 
-constexpr int kWarpScratch = 512 + 64;   // doubles of shared memory per warp: LU scratch (512) + EV(16) QE(16) DU(8) YV(16) + pad
+// per-warp shared memory (doubles): LU scratch (512) + EV(16) QE(16) DU(8) YV(16) + pad (8)  = 576,
+// then two TMA staging buffers (A_k | B_k | X_k,X_{k+1} | U_k | a_k) of kStage doubles and two mbarriers.
+constexpr int kStage = 240;
+constexpr int kWarpScratch = 576 + 2 * kStage + 8;
 
 template <int D>
 struct PrefixL { Mat eb, fb, gb; };
@@ -268,17 +271,48 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch
     const size_t baseN = (size_t)b * p.N;
     const size_t baseX = (size_t)b * (p.N + 1);
 
+    // ---- TMA-staged input stream: step k+1's (A, B, X_k+1, X_k+2, U, a) land in shared memory while step k
+    // computes.  One elected lane arms the stage's mbarrier with the byte count and issues the bulk copies.
+    static_assert(n * n + n * M + 2 * n + M + n <= kStage, "staging buffer too small");
+    static_assert((n * n) % 2 == 0 && (n * M) % 2 == 0 && (2 * n) % 2 == 0 && M % 2 == 0 && n % 2 == 0,
+                  "bulk copies need 16-byte multiples");
+    double* stage0 = scratch + 576;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(scratch + 576 + 2 * kStage);
+    constexpr int oA = 0, oB = n * n, oX = oB + n * M, oU = oX + 2 * n, oR = oU + M;
+    auto issue = [&](int kk) {
+        double* st = stage0 + (kk & 1) * kStage;
+        unsigned long long* bar = bars + (kk & 1);
+        const unsigned bytes = 8u * (n * n + n * M + 2 * n + M + (p.a_resid ? n : 0));
+        simt::mbar_expect_tx(bar, bytes);
+        simt::bulk_g2s(st + oA, p.A + (baseN + kk) * n * n, 8u * n * n, bar);
+        simt::bulk_g2s(st + oB, p.Bm + (baseN + kk) * n * M, 8u * n * M, bar);
+        simt::bulk_g2s(st + oX, p.X + (baseX + kk) * n, 8u * 2 * n, bar);
+        simt::bulk_g2s(st + oU, p.U + (size_t)b * p.u_stride + (size_t)kk * M, 8u * M, bar);
+        if (p.a_resid) simt::bulk_g2s(st + oR, p.a_resid + (baseN + kk) * n, 8u * n, bar);
+    };
+    if (L.lane == 0) {
+        simt::mbar_init(bars, 1);
+        simt::mbar_init(bars + 1, 1);
+        simt::mbar_fence_init();
+    }
+    simt::sync();
+    if (L.lane == 0) issue(0);
+
     for (int k = 0; k < p.T_max; ++k) {
-        const double* Ak = p.A + (baseN + k) * n * n;
-        const double* Bk = p.Bm + (baseN + k) * n * M;
-        simt::sync();
+        simt::sync();                                                           // everyone is done with the other stage
+        if (L.lane == 0 && k + 1 < p.T_max) issue(k + 1);
+        simt::mbar_wait(bars + (k & 1), (unsigned)((k >> 1) & 1));
+        const double* stg = stage0 + (k & 1) * kStage;
+        const double* Ak = stg + oA;
+        const double* Bk = stg + oB;
+        const double* Xk = stg + oX;
         double ev = 0.0;
         if (isx) {
-            ev = p.X[(baseX + k) * n + L.lane] - xg_l;                          // e = wrap(X_k - xg)  (augmented.py:28)
+            ev = Xk[L.lane] - xg_l;                                             // e = wrap(X_k - xg)  (augmented.py:28)
             if (wrap_l) ev = wrap_pi(ev);
             EV[L.lane] = ev;
         }
-        if (L.lane < M) DU[L.lane] = p.U[(size_t)b * p.u_stride + (size_t)k * M + L.lane] - cst[FC::UREF + L.lane];
+        if (L.lane < M) DU[L.lane] = stg[oU + L.lane] - cst[FC::UREF + L.lane];
         simt::sync();
         double qe = 0.0, qc = 0.0;
         if (isx) {
@@ -302,7 +336,7 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch
                 double sacc = 0.0;
 #pragma unroll
                 for (int c = 0; c < M; ++c) sacc = fma(Bk[R * M + c], DU[c], sacc);
-                a = (p.a_resid ? p.a_resid[(baseN + k) * n + R] : 0.0) - sacc;  // a_k - B_k du   (augmented.py:50)
+                a = (p.a_resid ? stg[oR + R] : 0.0) - sacc;                     // a_k - B_k du   (augmented.py:50)
             } else if (R == n && C == n) {
                 a = 1.0;
             }
@@ -390,7 +424,7 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch
         simt::sync();
         double et = 0.0;
         if (isx) {
-            et = p.X[(baseX + k + 1) * n + L.lane] - xg_l;
+            et = Xk[n + L.lane] - xg_l;
             if (wrap_l) et = wrap_pi(et);
             EV[L.lane] = et;
         }
