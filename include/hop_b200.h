@@ -113,6 +113,37 @@ int hop_select_from_x0_host_f64(int B, int sys, const double *params_host, int N
                                 const double *Qf, unsigned wrap_mask, int central, int mode,
                                 double *J_out, int *Tstar_out, double *Jstar_out, int *status);
 
+/* solver.py:65-105 cost_timeopt_true, batched: J_out[b] at the per-instance horizon T_star[b] (device int). */
+int hop_cost_f64(int B, int N, int n, int m, const double *X, const double *U, const double *xg, const double *w,
+                 const double *u_ref, const double *Q, const double *R, const double *Qf, unsigned wrap_mask,
+                 const int *T_star, double *J_out, void *stream);
+
+/* solver.py:156-230 backward_pass_truncated followed by solver.py:233-286 forward_linesearch_fixedT, batched,
+ * at per-instance horizons T_star[b] and Levenberg-Marquardt weights lm[b].
+ *   k_out [B][N][m], K_out [B][N][m][n] (rows >= T_star[b] untouched), ok_out [B] (0 = the reference's
+ *   `return None, None, False`), err_out [B] (non-zero = chol_solve raised: 1 FloatingPointError, 2 LinAlgError),
+ *   X_new [B][N+1][n], U_new [B][N][m], J_new [B], accepted [B]. */
+int hop_backward_linesearch_f64(int B, int sys, const double *params_host, int N, const double *A, const double *Bm,
+                                const double *X, const double *U, const double *xg, const double *w, const double *u_ref,
+                                const double *Q, const double *R, const double *Qf, unsigned wrap_mask, const int *T_star,
+                                const double *lm, double *k_out, double *K_out, int *ok_out, int *err_out, double *X_new,
+                                double *U_new, double *J_new, int *accepted, void *stream);
+
+/* solver.py:449-765 ilqr_timeopt(method="propagator"), batched over instances (x0, xg, w); the whole
+ * per-instance state machine (warm start, accept/reject, LM schedule, stop rule) runs on the device.
+ *   U_init [B][N][m] or NULL (= tile(u_ref), solver.py:480-481).
+ *   Outputs: X [B][N+1][n], U [B][N][m] (final trajectories), J_hist/T_hist [B][max_iter+1] with n_hist [B]
+ *   valid entries, J_curve [B][T_max] (last selection curve), T_star [B] (= T_hist[-1] or T_bar), status [B]
+ *   (low byte != 0: the reference would have raised -> run_suite "crash"), *iters_run_host (host int, may be NULL).
+ *   The call synchronises the stream once per outer iteration (early exit when every instance stopped). */
+unsigned long long hop_ilqr_workspace_bytes(int B, int N, int n, int m);
+int hop_ilqr_timeopt_f64(int B, int sys, const double *params_host, int N, int T_min, int T_max, const double *x0,
+                         const double *U_init, const double *xg, const double *w, const double *u_ref, const double *Q,
+                         const double *R, const double *Qf, unsigned wrap_mask, int max_iter, double lm_init, int central,
+                         int mode, void *workspace, unsigned long long workspace_bytes, double *X, double *U,
+                         double *J_hist, int *T_hist, int *n_hist, double *J_curve, int *T_star, int *status,
+                         int *iters_run_host, void *stream);
+
 /* Measures the FP64 FMA throughput of the current device with a register-resident DFMA chain
  * (8 independent accumulators per thread, 2048 threads per SM), timed with CUDA events.  This is
  * the roofline denominator bench.py reports against (MEASURED_PEAKS.json holds no FP64 figure). */

@@ -22,7 +22,7 @@ class FusedArgs(C.Structure):
     _fields_ = [("B", C.c_int), ("N", C.c_int), ("T_min", C.c_int), ("T_max", C.c_int), ("jitter", C.c_double),
                 ("max_tries", C.c_int), ("A", _dp), ("Bm", _dp), ("a_resid", _dp), ("X", _dp), ("U", _dp), ("u_stride", C.c_long), ("xg", _dp),
                 ("w", _dp), ("u_ref", _dp), ("Q", _dp), ("R", _dp), ("Qf", _dp), ("wrap_mask", C.c_uint),
-                ("q_reg", C.c_double), ("rho_reg", C.c_double), ("mode", C.c_int), ("J_out", _dp), ("T_out", _ip), ("Jstar_out", _dp),
+                ("q_reg", C.c_double), ("rho_reg", C.c_double), ("mode", C.c_int), ("skip", _ip), ("J_out", _dp), ("T_out", _ip), ("Jstar_out", _dp),
                 ("status", _ip)]
 
 
@@ -78,7 +78,7 @@ def select_fused(A, Bm, a_resid, X, U, xg, w, u_ref, Q, R, Qf, wrap_mask, T_min,
     J = np.full((Bsz, T_max), np.nan); T = np.zeros(Bsz, np.int32); Js = np.zeros(Bsz); st = np.zeros(Bsz, np.int32)
     a = FusedArgs(Bsz, N, T_min, T_max, jitter, max_tries, _p(A), _p(Bm), _p(ar), _p(X), _p(U),
                   0 if U.ndim == 2 else U.shape[1] * U.shape[2], _p(xg), _p(w), _p(u_ref),
-                  _p(Q), _p(R), _p(Qf), wrap_mask, q_reg, rho_reg, mode, _p(J), T.ctypes.data_as(_ip), _p(Js),
+                  _p(Q), _p(R), _p(Qf), wrap_mask, q_reg, rho_reg, mode, None, _p(J), T.ctypes.data_as(_ip), _p(Js),
                   st.ctypes.data_as(_ip))
     rc = (lib().emul_select_fused_mma if mma else lib().emul_select_fused)(n, m, C.byref(a))
     assert rc == 0, f"emulated kernel failed rc={rc}"

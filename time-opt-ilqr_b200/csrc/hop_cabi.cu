@@ -13,8 +13,30 @@ int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st);
 int dispatch_rollout(int B, int sys, const double* params_host, int N, const double* x0, const double* U, long ustride,
                      double max_norm, double* X, cudaStream_t st);
 int dispatch_linearize(int B, int sys, const double* params_host, int N, const double* X, const double* U, long ustride,
-                       int central, double epsx, double epsu, double relx, double relu, double* A, double* Bm,
+                       int central, double epsx, double epsu, double relx, double relu, const int* skip, double* A,
+                       double* Bm, cudaStream_t st);
+struct DdpConst {
+    const double *xg, *w, *u_ref, *Q, *R, *Qf;
+    unsigned wrap_mask;
+};
+int dispatch_backward_linesearch(int sys, int B, const double* params_host, int N, const double* A, const double* Bm,
+                                 const double* X, const double* U, const DdpConst& c, const int* T, const double* lm,
+                                 const int* done, double* kl, double* Kl, int* ok, int* bw_err, double* Xn, double* Un,
+                                 double* Jn, int* acc, cudaStream_t st);
+int dispatch_cost(int n, int m, int B, int N, const double* X, const double* U, const DdpConst& c, const int* T, double* J,
+                  cudaStream_t st);
+int launch_init_state(int B, double lm_init, double* lm, int* done, int* n_hist, int* status_out, cudaStream_t st);
+int launch_tile_u(int B, int N, int m, const double* u_ref, double* U, cudaStream_t st);
+int launch_after_select(int B, const int* sel_status, int* done, int* status_out, cudaStream_t st);
+int launch_warm_update(int B, int cap, const int* T_sel, const int* ok, const int* acc, const double* Jn, const int* bw_err,
+                       int* done, int* T_bar, double* J_hist, int* T_hist, int* n_hist, int* copy, int* status_out,
                        cudaStream_t st);
+int launch_ddp_update(int B, int cap, const int* T_sel, const int* ok, const int* acc, const double* Jn, const int* bw_err,
+                      int* done, int* T_bar, double* lm, double* J_hist, int* T_hist, int* n_hist, int* copy,
+                      int* status_out, int* n_active, cudaStream_t st);
+int launch_copy_accepted(int B, size_t per_x, size_t per_u, const int* copy, const double* Xn, const double* Un, double* X,
+                         double* U, cudaStream_t st);
+int launch_finalize(int B, int cap, const int* n_hist, const int* T_hist, const int* T_bar, int* T_star, cudaStream_t st);
 int sys_dims(int sys, int* n, int* m);
 
 static thread_local std::string g_err;
@@ -82,7 +104,7 @@ int hop_select_fused_f64(int B, int N, int n, int m, int T_min, int T_max, const
     if (int rc = need_device()) return rc;
     if (B == 0) return 0;
     FusedArgs p{B, N, T_min, T_max, kJitter, kMaxTries, A, Bm, a_resid, X, U, u_batch_stride, xg, w, u_ref, Q, R, Qf,
-                wrap_mask, q_reg, rho_reg, mode, J_out, Tstar_out, Jstar_out, status};
+                wrap_mask, q_reg, rho_reg, mode, nullptr, J_out, Tstar_out, Jstar_out, status};
     return dispatch_select_fused(n, m, p, (cudaStream_t)stream);
 }
 
@@ -100,7 +122,7 @@ int hop_linearize_f64(int B, int sys, const double* params_host, int N, const do
     if (B < 0 || N < 1 || !params_host) { set_last_error("hop_linearize_f64: bad argument"); return HOP_E_BADARG; }
     if (int rc = need_device()) return rc;
     if (B == 0) return 0;
-    return dispatch_linearize(B, sys, params_host, N, X, U, u_batch_stride, central, epsx, epsu, relx, relu, A, Bm,
+    return dispatch_linearize(B, sys, params_host, N, X, U, u_batch_stride, central, epsx, epsu, relx, relu, nullptr, A, Bm,
                               (cudaStream_t)stream);
 }
 
@@ -137,6 +159,130 @@ int hop_select_from_x0_f64(int B, int sys, const double* params_host, int N, int
     // a_resid = NULL: on a trajectory produced by the rollout above F(X_k,U_k) - X_{k+1} is exactly 0
     return hop_select_fused_f64(B, N, n, m, T_min, T_max, A, Bm, nullptr, X, U, u_batch_stride, xg, w, u_ref, Q, R, Qf,
                                 wrap_mask, 1e-9, 1e-12, mode, J_out, Tstar_out, Jstar_out, status, stream);
+}
+
+// ---- HOP-DDP pieces and the batched solver loop --------------------------------------------------------
+int hop_cost_f64(int B, int N, int n, int m, const double* X, const double* U, const double* xg, const double* w,
+                 const double* u_ref, const double* Q, const double* R, const double* Qf, unsigned wrap_mask,
+                 const int* T_star, double* J_out, void* stream) {
+    if (int rc = need_device()) return rc;
+    if (B <= 0) return B == 0 ? 0 : HOP_E_BADARG;
+    DdpConst c{xg, w, u_ref, Q, R, Qf, wrap_mask};
+    return dispatch_cost(n, m, B, N, X, U, c, T_star, J_out, (cudaStream_t)stream);
+}
+
+int hop_backward_linesearch_f64(int B, int sys, const double* params_host, int N, const double* A, const double* Bm,
+                                const double* X, const double* U, const double* xg, const double* w, const double* u_ref,
+                                const double* Q, const double* R, const double* Qf, unsigned wrap_mask, const int* T_star,
+                                const double* lm, double* k_out, double* K_out, int* ok_out, int* err_out, double* X_new,
+                                double* U_new, double* J_new, int* accepted, void* stream) {
+    if (int rc = need_device()) return rc;
+    if (B <= 0) return B == 0 ? 0 : HOP_E_BADARG;
+    DdpConst c{xg, w, u_ref, Q, R, Qf, wrap_mask};
+    return dispatch_backward_linesearch(sys, B, params_host, N, A, Bm, X, U, c, T_star, lm, nullptr, k_out, K_out, ok_out,
+                                        err_out, X_new, U_new, J_new, accepted, (cudaStream_t)stream);
+}
+
+namespace {
+struct IlqrWs {
+    double *A, *Bm, *Xn, *Un, *kl, *Kl, *lm, *Jn, *Jstar;
+    int *T_bar, *T_sel, *ok, *acc, *bw_err, *done, *copy, *sel_status, *n_active;
+    size_t total;
+};
+IlqrWs ilqr_layout(char* base, int B, int N, int n, int m) {
+    IlqrWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* q = base ? base + off : nullptr; off += align256(bytes); return q; };
+    w.A = (double*)take(sizeof(double) * (size_t)B * N * n * n);
+    w.Bm = (double*)take(sizeof(double) * (size_t)B * N * n * m);
+    w.Xn = (double*)take(sizeof(double) * (size_t)B * (N + 1) * n);
+    w.Un = (double*)take(sizeof(double) * (size_t)B * N * m);
+    w.kl = (double*)take(sizeof(double) * (size_t)B * N * m);
+    w.Kl = (double*)take(sizeof(double) * (size_t)B * N * m * n);
+    w.lm = (double*)take(sizeof(double) * (size_t)B);
+    w.Jn = (double*)take(sizeof(double) * (size_t)B);
+    w.Jstar = (double*)take(sizeof(double) * (size_t)B);
+    w.T_bar = (int*)take(sizeof(int) * (size_t)B);
+    w.T_sel = (int*)take(sizeof(int) * (size_t)B);
+    w.ok = (int*)take(sizeof(int) * (size_t)B);
+    w.acc = (int*)take(sizeof(int) * (size_t)B);
+    w.bw_err = (int*)take(sizeof(int) * (size_t)B);
+    w.done = (int*)take(sizeof(int) * (size_t)B);
+    w.copy = (int*)take(sizeof(int) * (size_t)B);
+    w.sel_status = (int*)take(sizeof(int) * (size_t)B);
+    w.n_active = (int*)take(sizeof(int) * 4);
+    w.total = off;
+    return w;
+}
+}  // namespace
+
+unsigned long long hop_ilqr_workspace_bytes(int B, int N, int n, int m) {
+    return (unsigned long long)ilqr_layout(nullptr, B, N, n, m).total;
+}
+
+int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T_min, int T_max, const double* x0,
+                         const double* U_init, const double* xg, const double* w, const double* u_ref, const double* Q,
+                         const double* R, const double* Qf, unsigned wrap_mask, int max_iter, double lm_init, int central,
+                         int mode, void* workspace, unsigned long long workspace_bytes, double* X, double* U,
+                         double* J_hist, int* T_hist, int* n_hist, double* J_curve, int* T_star, int* status,
+                         int* iters_run_host, void* stream) {
+    int n = 0, m = 0;
+    if (sys_dims(sys, &n, &m)) { set_last_error("hop_ilqr_timeopt_f64: unknown system id"); return HOP_E_BADARG; }
+    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || max_iter < 0) {
+        set_last_error("hop_ilqr_timeopt_f64: bad argument");
+        return HOP_E_BADARG;
+    }
+    if (int rc = need_device()) return rc;
+    if (B == 0) return 0;
+    if (!workspace || workspace_bytes < hop_ilqr_workspace_bytes(B, N, n, m)) {
+        set_last_error("hop_ilqr_timeopt_f64: workspace too small");
+        return HOP_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    IlqrWs ws = ilqr_layout((char*)workspace, B, N, n, m);
+    const int cap = max_iter + 1;
+    const long ustride = (long)N * m;
+    DdpConst c{xg, w, u_ref, Q, R, Qf, wrap_mask};
+    int rc;
+#define HOP_TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+    auto select = [&](const int* skip) -> int {
+        FusedArgs p{B, N, T_min, T_max, kJitter, kMaxTries, ws.A, ws.Bm, nullptr, X, U, ustride, xg, w, u_ref, Q, R, Qf,
+                    wrap_mask, 1e-9, 1e-12, mode, skip, J_curve, ws.T_sel, ws.Jstar, ws.sel_status};
+        return dispatch_select_fused(n, m, p, st);
+    };
+    HOP_TRY(launch_init_state(B, lm_init, ws.lm, ws.done, n_hist, status, st));
+    if (U_init) HOP_TRY(report_cuda(cudaMemcpyAsync(U, U_init, sizeof(double) * (size_t)B * N * m, cudaMemcpyDeviceToDevice, st), "copy U_init"));
+    else HOP_TRY(launch_tile_u(B, N, m, u_ref, U, st));                                                  // solver.py:480-481
+    HOP_TRY(dispatch_rollout(B, sys, params_host, N, x0, U, ustride, 1e6, X, st));                       // :492
+    HOP_TRY(dispatch_linearize(B, sys, params_host, N, X, U, ustride, central, 1e-5, 1e-5, 1e-6, 1e-6, nullptr, ws.A, ws.Bm, st));
+    HOP_TRY(select(nullptr));                                                                            // :516-522
+    HOP_TRY(launch_after_select(B, ws.sel_status, ws.done, status, st));
+    HOP_TRY(dispatch_backward_linesearch(sys, B, params_host, N, ws.A, ws.Bm, X, U, c, ws.T_sel, ws.lm, ws.done, ws.kl, ws.Kl,
+                                         ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, st));            // :541-551
+    HOP_TRY(launch_warm_update(B, cap, ws.T_sel, ws.ok, ws.acc, ws.Jn, ws.bw_err, ws.done, ws.T_bar, J_hist, T_hist, n_hist,
+                               ws.copy, status, st));
+    HOP_TRY(launch_copy_accepted(B, (size_t)(N + 1) * n, (size_t)N * m, ws.copy, ws.Xn, ws.Un, X, U, st));
+    int iters = 0;
+    for (int it = 0; it < max_iter; ++it) {                                                              // :564
+        ++iters;
+        HOP_TRY(dispatch_linearize(B, sys, params_host, N, X, U, ustride, central, 1e-5, 1e-5, 1e-6, 1e-6, ws.done, ws.A, ws.Bm, st));
+        HOP_TRY(select(ws.done));                                                                        // :581-590
+        HOP_TRY(launch_after_select(B, ws.sel_status, ws.done, status, st));
+        HOP_TRY(dispatch_backward_linesearch(sys, B, params_host, N, ws.A, ws.Bm, X, U, c, ws.T_sel, ws.lm, ws.done, ws.kl,
+                                             ws.Kl, ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, st)); // :594-604
+        HOP_TRY(report_cuda(cudaMemsetAsync(ws.n_active, 0, sizeof(int), st), "memset n_active"));
+        HOP_TRY(launch_ddp_update(B, cap, ws.T_sel, ws.ok, ws.acc, ws.Jn, ws.bw_err, ws.done, ws.T_bar, ws.lm, J_hist, T_hist,
+                                  n_hist, ws.copy, status, ws.n_active, st));                             // :735-748
+        HOP_TRY(launch_copy_accepted(B, (size_t)(N + 1) * n, (size_t)N * m, ws.copy, ws.Xn, ws.Un, X, U, st));
+        int active = 0;
+        HOP_TRY(report_cuda(cudaMemcpyAsync(&active, ws.n_active, sizeof(int), cudaMemcpyDeviceToHost, st), "read n_active"));
+        HOP_TRY(report_cuda(cudaStreamSynchronize(st), "hop_ilqr_timeopt_f64"));
+        if (active == 0) break;
+    }
+    HOP_TRY(launch_finalize(B, cap, n_hist, T_hist, ws.T_bar, T_star, st));
+#undef HOP_TRY
+    if (iters_run_host) *iters_run_host = iters;
+    return 0;
 }
 
 // ---- FP64 pipe probe (roofline denominator; MEASURED_PEAKS.json has no FP64 figure) ---------------

@@ -1,0 +1,247 @@
+// hop_ddp.cu -- batched HOP-DDP iteration around the horizon selection (one thread per problem) and
+// the per-instance solver state machine of solver.py:449-765 (method="propagator").
+//
+//   k_cost        solver.py:65-105    cost_timeopt_true
+//   k_backward    solver.py:156-230   backward_pass_truncated
+//   k_linesearch  solver.py:233-286   forward_linesearch_fixedT
+//   k_after_select / k_ddp_update / k_copy_accepted   accept-reject, LM schedule, histories, stop rule
+//                                                     (solver.py:522,553-555,590,735-748)
+// Every kernel takes the per-instance `done` word and skips finished instances, so a batch whose
+// members stop at different iterations needs no host-side control flow.
+#include "hop_common.cuh"
+#include "hop_ddp_core.cuh"
+#include "../../include/hop_b200.h"
+
+namespace hop {
+
+struct DynParams2 { double p[HOP_NPARAMS]; };
+
+struct DdpConst {   // device pointers to the shared case constants + per-instance xg / w (mirrored in hop_cabi.cu)
+    const double *xg, *w, *u_ref, *Q, *R, *Qf;
+    unsigned wrap_mask;
+};
+
+template <int n>
+__device__ __forceinline__ ddp::CostConst cost_const(const DdpConst& c, int b) {
+    ddp::CostConst cc;
+    cc.xg = c.xg + (size_t)b * n;
+    cc.u_ref = c.u_ref; cc.Q = c.Q; cc.R = c.R; cc.Qf = c.Qf;
+    cc.w = c.w[b];
+    cc.wrap_mask = c.wrap_mask;
+    return cc;
+}
+
+template <int n, int m>
+__global__ void k_cost(int B, int N, const double* X, const double* U, DdpConst c, const int* T, double* J) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const ddp::CostConst cc = cost_const<n>(c, b);
+    J[b] = ddp::cost_timeopt_true<n, m>(X + (size_t)b * (N + 1) * n, U + (size_t)b * N * m, cc, T[b]);
+}
+
+template <int n, int m>
+__global__ void k_backward(int B, int N, const double* A, const double* Bm, const double* X, const double* U, DdpConst c,
+                           const int* T, const double* lm, const int* done, double* k_out, double* K_out, int* ok,
+                           int* err) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (done && done[b]) { ok[b] = 0; return; }
+    const ddp::CostConst cc = cost_const<n>(c, b);
+    int okb = 0;
+    const int rc = ddp::backward_pass<n, m>(A + (size_t)b * N * n * n, Bm + (size_t)b * N * n * m, X + (size_t)b * (N + 1) * n,
+                                            U + (size_t)b * N * m, cc, T[b], lm[b], k_out + (size_t)b * N * m,
+                                            K_out + (size_t)b * N * m * n, &okb);
+    ok[b] = (rc == 0) ? okb : 0;
+    if (err) err[b] = rc;
+}
+
+template <int SYS>
+__global__ void k_linesearch(int B, DynParams2 prm, int N, const double* X, const double* U, DdpConst c, const int* T,
+                             const double* k_list, const double* K_list, const int* ok, const int* done, double* Xn,
+                             double* Un, double* Jn, int* acc) {
+    constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    acc[b] = 0;
+    if ((done && done[b]) || (ok && !ok[b])) return;
+    const ddp::CostConst cc = cost_const<n>(c, b);
+    double J = 0.0;
+    int a = 0;
+    ddp::forward_linesearch<SYS>(prm.p, N, X + (size_t)b * (N + 1) * n, U + (size_t)b * N * m, cc, T[b],
+                                 k_list + (size_t)b * N * m, K_list + (size_t)b * N * m * n, Xn + (size_t)b * (N + 1) * n,
+                                 Un + (size_t)b * N * m, &J, &a);
+    Jn[b] = J;
+    acc[b] = a;
+}
+
+// After a selection: an instance whose selection raised in the reference (status low byte != 0) stops
+// here ("crash", run_suite.py:137-157); otherwise T_sel is the horizon to optimise at.
+__global__ void k_after_select(int B, const int* sel_status, int* done, int* status_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || done[b]) return;
+    const int st = sel_status[b];
+    status_out[b] |= (st & ~0xff);
+    if (st & 0xff) { done[b] = 2; status_out[b] |= (st & 0xff); }
+}
+
+// Warm start bookkeeping (solver.py:546-555): X,U <- line-search result when the backward pass was ok;
+// (J0, T_bar) appended when J0 is finite.  `copy` marks instances whose candidate must be copied in.
+__global__ void k_warm_update(int B, int cap, const int* T_sel, const int* ok, const int* acc, const double* Jn,
+                              const int* bw_err, int* done, int* T_bar, double* J_hist, int* T_hist, int* n_hist,
+                              int* copy, int* status_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    copy[b] = 0;
+    if (done[b]) return;
+    T_bar[b] = T_sel[b];
+    if (bw_err[b]) { done[b] = 2; status_out[b] |= bw_err[b]; return; }     // chol_solve raised (utils.py:120)
+    if (!ok[b]) return;
+    copy[b] = acc[b];
+    if (isfinite(Jn[b])) {
+        J_hist[(size_t)b * cap + n_hist[b]] = Jn[b];
+        T_hist[(size_t)b * cap + n_hist[b]] = T_sel[b];
+        n_hist[b] += 1;
+    }
+}
+
+// Outer-loop bookkeeping (solver.py:735-748).
+__global__ void k_ddp_update(int B, int cap, const int* T_sel, const int* ok, const int* acc, const double* Jn,
+                             const int* bw_err, int* done, int* T_bar, double* lm, double* J_hist, int* T_hist,
+                             int* n_hist, int* copy, int* status_out, int* n_active) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    copy[b] = 0;
+    if (done[b]) return;
+    if (bw_err[b]) { done[b] = 2; status_out[b] |= bw_err[b]; return; }
+    const bool accept = ok[b] && acc[b] && isfinite(Jn[b]);
+    if (accept) {
+        copy[b] = 1;
+        T_bar[b] = T_sel[b];
+        J_hist[(size_t)b * cap + n_hist[b]] = Jn[b];
+        T_hist[(size_t)b * cap + n_hist[b]] = T_sel[b];
+        n_hist[b] += 1;
+        lm[b] = fmax(lm[b] / 10.0, 1e-12);
+    } else {
+        lm[b] = lm[b] * 10.0;
+    }
+    const int nh = n_hist[b];
+    if (nh >= 2) {
+        const double j1 = J_hist[(size_t)b * cap + nh - 1], j2 = J_hist[(size_t)b * cap + nh - 2];
+        const double rel = fabs(j1 - j2) / (fabs(j2) + 1e-12);
+        if (rel < 1e-4 && nh >= 3) {
+            const int* th = T_hist + (size_t)b * cap;
+            if (th[nh - 1] == th[nh - 2] && th[nh - 2] == th[nh - 3]) done[b] = 1;
+        }
+    }
+    if (!done[b]) atomicAdd(n_active, 1);
+}
+
+__global__ void k_copy_accepted(int B, size_t per_x, size_t per_u, const int* copy, const double* Xn, const double* Un,
+                                double* X, double* U) {
+    const size_t per = per_x + per_u;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)B * per) return;
+    const size_t b = gid / per, r = gid % per;
+    if (!copy[b]) return;
+    if (r < per_x) X[b * per_x + r] = Xn[b * per_x + r];
+    else U[b * per_u + (r - per_x)] = Un[b * per_u + (r - per_x)];
+}
+
+__global__ void k_finalize(int B, int cap, const int* n_hist, const int* T_hist, const int* T_bar, int* T_star) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int nh = n_hist[b];
+    T_star[b] = nh ? T_hist[(size_t)b * cap + nh - 1] : T_bar[b];          // solver.py:763
+}
+
+__global__ void k_init_state(int B, double lm_init, double* lm, int* done, int* n_hist, int* status_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    lm[b] = lm_init; done[b] = 0; n_hist[b] = 0; status_out[b] = 0;
+}
+
+__global__ void k_tile_u(int B, int N, int m, const double* u_ref, double* U) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)B * N * m) return;
+    U[gid] = u_ref[gid % m];
+}
+
+static inline int grid1(size_t total, int threads) { return (int)((total + threads - 1) / threads); }
+
+template <int SYS>
+static int ddp_backward_linesearch(int B, const DynParams2& prm, int N, const double* A, const double* Bm, const double* X,
+                                   const double* U, const DdpConst& c, const int* T, const double* lm, const int* done,
+                                   double* kl, double* Kl, int* ok, int* bw_err, double* Xn, double* Un, double* Jn, int* acc,
+                                   cudaStream_t st) {
+    constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
+    const int threads = 64;
+    k_backward<n, m><<<grid1(B, threads), threads, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
+    if (int rc = check_launch("k_backward")) return rc;
+    k_linesearch<SYS><<<grid1(B, threads), threads, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, done, Xn, Un, Jn, acc);
+    return check_launch("k_linesearch");
+}
+
+int dispatch_backward_linesearch(int sys, int B, const double* params_host, int N, const double* A, const double* Bm,
+                                 const double* X, const double* U, const DdpConst& c, const int* T, const double* lm,
+                                 const int* done, double* kl, double* Kl, int* ok, int* bw_err, double* Xn, double* Un,
+                                 double* Jn, int* acc, cudaStream_t st) {
+    DynParams2 prm;
+    for (int i = 0; i < HOP_NPARAMS; ++i) prm.p[i] = params_host[i];
+    switch (sys) {
+        case 0: return ddp_backward_linesearch<0>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, st);
+        case 1: return ddp_backward_linesearch<1>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, st);
+        case 2: return ddp_backward_linesearch<2>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, st);
+        case 3: return ddp_backward_linesearch<3>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, st);
+    }
+    set_last_error("unknown system id");
+    return HOP_E_BADARG;
+}
+
+int dispatch_cost(int n, int m, int B, int N, const double* X, const double* U, const DdpConst& c, const int* T, double* J,
+                  cudaStream_t st) {
+    const int threads = 128;
+    if (n == 2 && m == 1) k_cost<2, 1><<<grid1(B, threads), threads, 0, st>>>(B, N, X, U, c, T, J);
+    else if (n == 4 && m == 1) k_cost<4, 1><<<grid1(B, threads), threads, 0, st>>>(B, N, X, U, c, T, J);
+    else if (n == 12 && m == 4) k_cost<12, 4><<<grid1(B, threads), threads, 0, st>>>(B, N, X, U, c, T, J);
+    else { set_last_error("hop_cost_f64: (n, m) not instantiated"); return HOP_E_UNSUPPORTED_DIMS; }
+    return check_launch("k_cost");
+}
+
+// thin launch helpers used by the solver loop in hop_cabi.cu
+int launch_init_state(int B, double lm_init, double* lm, int* done, int* n_hist, int* status_out, cudaStream_t st) {
+    k_init_state<<<grid1(B, 128), 128, 0, st>>>(B, lm_init, lm, done, n_hist, status_out);
+    return check_launch("k_init_state");
+}
+int launch_tile_u(int B, int N, int m, const double* u_ref, double* U, cudaStream_t st) {
+    k_tile_u<<<grid1((size_t)B * N * m, 256), 256, 0, st>>>(B, N, m, u_ref, U);
+    return check_launch("k_tile_u");
+}
+int launch_after_select(int B, const int* sel_status, int* done, int* status_out, cudaStream_t st) {
+    k_after_select<<<grid1(B, 128), 128, 0, st>>>(B, sel_status, done, status_out);
+    return check_launch("k_after_select");
+}
+int launch_warm_update(int B, int cap, const int* T_sel, const int* ok, const int* acc, const double* Jn, const int* bw_err,
+                       int* done, int* T_bar, double* J_hist, int* T_hist, int* n_hist, int* copy, int* status_out,
+                       cudaStream_t st) {
+    k_warm_update<<<grid1(B, 128), 128, 0, st>>>(B, cap, T_sel, ok, acc, Jn, bw_err, done, T_bar, J_hist, T_hist, n_hist, copy,
+                                                 status_out);
+    return check_launch("k_warm_update");
+}
+int launch_ddp_update(int B, int cap, const int* T_sel, const int* ok, const int* acc, const double* Jn, const int* bw_err,
+                      int* done, int* T_bar, double* lm, double* J_hist, int* T_hist, int* n_hist, int* copy,
+                      int* status_out, int* n_active, cudaStream_t st) {
+    k_ddp_update<<<grid1(B, 128), 128, 0, st>>>(B, cap, T_sel, ok, acc, Jn, bw_err, done, T_bar, lm, J_hist, T_hist, n_hist,
+                                                copy, status_out, n_active);
+    return check_launch("k_ddp_update");
+}
+int launch_copy_accepted(int B, size_t per_x, size_t per_u, const int* copy, const double* Xn, const double* Un, double* X,
+                         double* U, cudaStream_t st) {
+    k_copy_accepted<<<grid1((size_t)B * (per_x + per_u), 256), 256, 0, st>>>(B, per_x, per_u, copy, Xn, Un, X, U);
+    return check_launch("k_copy_accepted");
+}
+int launch_finalize(int B, int cap, const int* n_hist, const int* T_hist, const int* T_bar, int* T_star, cudaStream_t st) {
+    k_finalize<<<grid1(B, 128), 128, 0, st>>>(B, cap, n_hist, T_hist, T_bar, T_star);
+    return check_launch("k_finalize");
+}
+
+}  // namespace hop

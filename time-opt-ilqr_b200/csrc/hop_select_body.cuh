@@ -34,6 +34,7 @@ struct FusedArgs {
     unsigned wrap_mask;
     double q_reg, rho_reg;
     int mode;                                  // HOP_MODE_EXACT / HOP_MODE_FAST
+    const int* skip;                           // optional [B]: non-zero => instance is left untouched
     double* J_out;
     int* T_out;
     double* Jstar_out;
@@ -158,8 +159,8 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* sm, con
     const bool isx = r < n;          // lane owns a state row
     const int rr = act ? r : 0;
     const int rx = isx ? r : 0;
-    const bool valid = b_raw < p.B;
-    const int b = valid ? b_raw : p.B - 1;
+    const int b = (b_raw < p.B) ? b_raw : p.B - 1;
+    const bool valid = (b_raw < p.B) && !(p.skip && p.skip[b]);
 
     for (int i = r; i < Ge::SLAB; i += G) sm[i] = 0.0;
     simt::sync();

@@ -237,6 +237,7 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch
     L.init();
     const bool valid = b_raw < p.B;
     const int b = valid ? b_raw : p.B - 1;
+    if (!valid || (p.skip && p.skip[b])) return;   // warp-uniform: one problem per warp
     double* EV = scratch + 512;   // e = wrap(X - xg)
     double* QE = EV + 16;         // Q e  /  P e
     double* DU = QE + 16;         // U_k - u_ref

@@ -48,7 +48,7 @@ __global__ void k_rollout(int B, DynParams prm, int N, const double* __restrict_
 template <int SYS>
 __global__ void k_linearize(int B, DynParams prm, int N, const double* __restrict__ X, const double* __restrict__ U,
                             long ustride, int central, double epsx, double epsu, double relx, double relu,
-                            double* __restrict__ A, double* __restrict__ Bm) {
+                            const int* __restrict__ skip, double* __restrict__ A, double* __restrict__ Bm) {
     constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m, P = n + m;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)B * N * P;
@@ -57,6 +57,7 @@ __global__ void k_linearize(int B, DynParams prm, int N, const double* __restric
     const size_t bk = gid / P;
     const int k = (int)(bk % N);
     const size_t b = bk / N;
+    if (skip && skip[b]) return;
     double x[n], u[m], f0[n], fp[n], fm[n];
     const double* xs = X + (b * (N + 1) + k) * n;
     const double* us = U + b * ustride + (size_t)k * m;
@@ -118,13 +119,13 @@ static int launch_rollout(int B, const DynParams& prm, int N, const double* x0, 
 }
 template <int SYS>
 static int launch_linearize(int B, const DynParams& prm, int N, const double* X, const double* U, long ustride,
-                            int central, double epsx, double epsu, double relx, double relu, double* A, double* Bm,
-                            cudaStream_t st) {
+                            int central, double epsx, double epsu, double relx, double relu, const int* skip, double* A,
+                            double* Bm, cudaStream_t st) {
     constexpr int P = SysDims<SYS>::n + SysDims<SYS>::m;
     const size_t total = (size_t)B * N * P;
     const int threads = 128;
     const size_t grid = (total + threads - 1) / threads;
-    k_linearize<SYS><<<(unsigned)grid, threads, 0, st>>>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, A, Bm);
+    k_linearize<SYS><<<(unsigned)grid, threads, 0, st>>>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, skip, A, Bm);
     return check_launch("k_linearize");
 }
 
@@ -143,15 +144,15 @@ int dispatch_rollout(int B, int sys, const double* params_host, int N, const dou
 }
 
 int dispatch_linearize(int B, int sys, const double* params_host, int N, const double* X, const double* U, long ustride,
-                       int central, double epsx, double epsu, double relx, double relu, double* A, double* Bm,
-                       cudaStream_t st) {
+                       int central, double epsx, double epsu, double relx, double relu, const int* skip, double* A,
+                       double* Bm, cudaStream_t st) {
     DynParams prm;
     for (int i = 0; i < HOP_NPARAMS; ++i) prm.p[i] = params_host[i];
     switch (sys) {
-        case 0: return launch_linearize<0>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, A, Bm, st);
-        case 1: return launch_linearize<1>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, A, Bm, st);
-        case 2: return launch_linearize<2>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, A, Bm, st);
-        case 3: return launch_linearize<3>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, A, Bm, st);
+        case 0: return launch_linearize<0>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, skip, A, Bm, st);
+        case 1: return launch_linearize<1>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, skip, A, Bm, st);
+        case 2: return launch_linearize<2>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, skip, A, Bm, st);
+        case 3: return launch_linearize<3>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, skip, A, Bm, st);
     }
     set_last_error("hop_linearize_f64: unknown system id");
     return HOP_E_BADARG;

@@ -27,6 +27,12 @@ SIGNATURES = {
                                     _ull, _vp, _vp, _vp, _vp, _vp]),
     "hop_select_from_x0_host_f64": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _u, _i, _i,
                                          _vp, _vp, _vp, _vp]),
+    "hop_cost_f64": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u, _vp, _vp, _vp]),
+    "hop_backward_linesearch_f64": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u, _vp, _vp,
+                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hop_ilqr_workspace_bytes": (_ull, [_i, _i, _i, _i]),
+    "hop_ilqr_timeopt_f64": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u, _i, _d, _i, _i, _vp,
+                                  _ull, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hop_probe_fp64_tflops": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

@@ -305,3 +305,110 @@ def select_horizon_host(case, x0: np.ndarray, xg: Optional[np.ndarray] = None, w
                                          vp(J), vp(T), vp(Js), vp(st))
     _cabi.check(rc, "hop_select_from_x0_host_f64")
     return J, T, Js, st
+
+
+# ------------------------------------------------------------------------------------------------
+# HOP-DDP pieces and the batched solver (solver.py:449-765, method="propagator")
+# ------------------------------------------------------------------------------------------------
+def _case_consts(case, Bsz, dev, xg=None, w=None):
+    F, _x0, xg0, u_ref, Q, R, alpha, w0, N, T_min, T_max, wrap_idx, extra = case
+    if extra is not None:
+        raise NotImplementedError("extra_stage_cost is not supported on the B200 path")
+    n, m = SYS_DIMS[F.hop_sys]
+    xg_t = _dev(np.broadcast_to(np.asarray(xg0, dtype=float), (Bsz, n)).copy(), dev) if xg is None else _dev(xg, dev)
+    if xg_t.dim() == 1:
+        xg_t = xg_t.expand(Bsz, n).contiguous()
+    if w is None:
+        w_t = torch.full((Bsz,), float(w0), dtype=torch.float64, device=dev)
+    else:
+        w_t = _dev(np.broadcast_to(np.asarray(w, dtype=float), (Bsz,)).copy() if not isinstance(w, torch.Tensor) else w, dev)
+    return dict(F=F, n=n, m=m, N=int(N), T_min=int(T_min), T_max=int(min(T_max, N)), wrap=wrap_mask(wrap_idx), xg=xg_t, w=w_t,
+                u_ref=_dev(u_ref, dev), Q=_dev(Q, dev), R=_dev(R, dev), Qf=_dev(as_terminal_weight(alpha, n), dev),
+                params=_params(F))
+
+
+def cost_timeopt_true_batched(case, X, U, T_star, xg=None, w=None) -> torch.Tensor:
+    """solver.cost_timeopt_true over a batch, at per-instance horizons T_star [B] (int32)."""
+    lib = _cabi.require_device()
+    X = _dev(X)
+    dev = X.device
+    U = _dev(U, dev)
+    Bsz = X.shape[0]
+    c = _case_consts(case, Bsz, dev, xg, w)
+    T = T_star.to(device=dev, dtype=torch.int32).contiguous()
+    J = torch.empty(Bsz, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.hop_cost_f64(Bsz, c["N"], c["n"], c["m"], _ptr(X), _ptr(U), _ptr(c["xg"]), _ptr(c["w"]), _ptr(c["u_ref"]),
+                              _ptr(c["Q"]), _ptr(c["R"]), _ptr(c["Qf"]), c["wrap"], _ptr(T), _ptr(J), _stream(dev))
+    _cabi.check(rc, "hop_cost_f64")
+    return J
+
+
+def backward_linesearch_batched(case, A, Bm, X, U, T_star, lm, xg=None, w=None):
+    """solver.backward_pass_truncated + forward_linesearch_fixedT over a batch.
+    Returns dict(k, K, ok, err, X_new, U_new, J_new, accepted)."""
+    lib = _cabi.require_device()
+    A = _dev(A)
+    dev = A.device
+    Bm, X, U = _dev(Bm, dev), _dev(X, dev), _dev(U, dev)
+    Bsz = A.shape[0]
+    c = _case_consts(case, Bsz, dev, xg, w)
+    N, n, m = c["N"], c["n"], c["m"]
+    T = T_star.to(device=dev, dtype=torch.int32).contiguous()
+    lm_t = _dev(np.broadcast_to(np.asarray(lm, dtype=float), (Bsz,)).copy() if not isinstance(lm, torch.Tensor) else lm, dev)
+    k = torch.zeros((Bsz, N, m), dtype=torch.float64, device=dev)
+    K = torch.zeros((Bsz, N, m, n), dtype=torch.float64, device=dev)
+    ok = torch.zeros(Bsz, dtype=torch.int32, device=dev)
+    err = torch.zeros(Bsz, dtype=torch.int32, device=dev)
+    Xn = torch.empty_like(X)
+    Un = torch.empty_like(U)
+    Jn = torch.zeros(Bsz, dtype=torch.float64, device=dev)
+    acc = torch.zeros(Bsz, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.hop_backward_linesearch_f64(Bsz, c["F"].hop_sys, c["params"].ctypes.data_as(C.c_void_p), N, _ptr(A), _ptr(Bm),
+                                             _ptr(X), _ptr(U), _ptr(c["xg"]), _ptr(c["w"]), _ptr(c["u_ref"]), _ptr(c["Q"]),
+                                             _ptr(c["R"]), _ptr(c["Qf"]), c["wrap"], _ptr(T), _ptr(lm_t), _ptr(k), _ptr(K),
+                                             _ptr(ok), _ptr(err), _ptr(Xn), _ptr(Un), _ptr(Jn), _ptr(acc), _stream(dev))
+    _cabi.check(rc, "hop_backward_linesearch_f64")
+    return dict(k=k, K=K, ok=ok, err=err, X_new=Xn, U_new=Un, J_new=Jn, accepted=acc)
+
+
+def ilqr_timeopt_batched(case, x0, xg=None, w=None, U_init=None, max_iter: int = 15, lm_init: float = 1e-3,
+                         use_central_diff: bool = True, mode: int = MODE_EXACT):
+    """Batched HOP-DDP solve (solver.ilqr_timeopt, method="propagator") for B instances (x0 [B,n], optional
+    per-instance xg [B,n] and w [B]).  Returns a dict of CUDA tensors: X [B,N+1,n], U [B,N,m],
+    J_hist / T_hist [B,max_iter+1] with n_hist [B] valid entries, J_curve [B,T_max], T_star [B], status [B],
+    plus ``iters`` (outer iterations actually run)."""
+    lib = _cabi.require_device()
+    x0 = _dev(x0)
+    dev = x0.device
+    Bsz = x0.shape[0]
+    c = _case_consts(case, Bsz, dev, xg, w)
+    N, n, m, T_max = c["N"], c["n"], c["m"], c["T_max"]
+    Ui = None
+    if U_init is not None:
+        Ui = _dev(U_init, dev)
+        if Ui.dim() == 2:
+            Ui = Ui.expand(Bsz, N, m).contiguous()
+    cap = int(max_iter) + 1
+    X = torch.empty((Bsz, N + 1, n), dtype=torch.float64, device=dev)
+    U = torch.empty((Bsz, N, m), dtype=torch.float64, device=dev)
+    J_hist = torch.full((Bsz, cap), float("nan"), dtype=torch.float64, device=dev)
+    T_hist = torch.zeros((Bsz, cap), dtype=torch.int32, device=dev)
+    n_hist = torch.zeros(Bsz, dtype=torch.int32, device=dev)
+    J_curve = torch.zeros((Bsz, T_max), dtype=torch.float64, device=dev)
+    T_star = torch.zeros(Bsz, dtype=torch.int32, device=dev)
+    status = torch.zeros(Bsz, dtype=torch.int32, device=dev)
+    nbytes = int(lib.hop_ilqr_workspace_bytes(Bsz, N, n, m))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    iters = C.c_int(0)
+    with torch.cuda.device(dev):
+        rc = lib.hop_ilqr_timeopt_f64(Bsz, c["F"].hop_sys, c["params"].ctypes.data_as(C.c_void_p), N, c["T_min"], T_max,
+                                      _ptr(x0), _ptr(Ui), _ptr(c["xg"]), _ptr(c["w"]), _ptr(c["u_ref"]), _ptr(c["Q"]),
+                                      _ptr(c["R"]), _ptr(c["Qf"]), c["wrap"], int(max_iter), float(lm_init),
+                                      int(bool(use_central_diff)), int(mode), _ptr(ws), nbytes, _ptr(X), _ptr(U),
+                                      _ptr(J_hist), _ptr(T_hist), _ptr(n_hist), _ptr(J_curve), _ptr(T_star), _ptr(status),
+                                      C.cast(C.byref(iters), C.c_void_p), _stream(dev))
+    _cabi.check(rc, "hop_ilqr_timeopt_f64")
+    return dict(X=X, U=U, J_hist=J_hist, T_hist=T_hist, n_hist=n_hist, J_curve=J_curve, T_star=T_star, status=status,
+                iters=iters.value)
