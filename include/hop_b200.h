@@ -59,14 +59,15 @@ int hop_select_supported(int d, int m);
 
 /* horizon_selection.py:36-86 propagator_all_Jt_aug (+ solver.py:522,590 argmin), batched.
  *   A_aug [B][N][d][d], B_aug [B][N][d][m], Q_aug [B][N][d][d], QT [B][N][d][d] (QT[t-1] = terminal block
- *   of horizon t), R_inv [B][m][m] (the R_inv_cached argument), z0 [B][d].
+ *   of horizon t), R_inv [B][m][m] (the R_inv_cached argument; rinv_step_stride = 0) or [B][N][m][m]
+ *   (chol_inv(R_list[k]) per step; rinv_step_stride = m*m), z0 [B][d].
  *   w_explicit: NULL, or [B] -- argmin is then taken over J(t) + w*t (SURVEY.md s.8d "S2"); J_out is
  *   always the raw curve the reference returns.
  *   Outputs: J_out [B][T_max] (index t-1), Tstar_out [B] = argmin over t in [T_min, T_max] (first
  *   minimum, NaN wins, as np.argmin), Jstar_out [B], status [B]. */
 int hop_select_f64(int B, int N, int d, int m, int T_min, int T_max,
                    const double *A_aug, const double *B_aug, const double *Q_aug, const double *R_inv,
-                   const double *z0, const double *QT, const double *w_explicit, int mode,
+                   long rinv_step_stride, const double *z0, const double *QT, const double *w_explicit, int mode,
                    double *J_out, int *Tstar_out, double *Jstar_out, int *status, void *stream);
 
 /* Fused form: augmented.py:10-60 build_augmented_sequence_QR + augmented.py:63-87
@@ -113,6 +114,27 @@ int hop_select_from_x0_host_f64(int B, int sys, const double *params_host, int N
                                 const double *Qf, unsigned wrap_mask, int central, int mode,
                                 double *J_out, int *Tstar_out, double *Jstar_out, int *status);
 
+/* utils.py:69-93 chol_inv / utils.py:96-120 chol_solve over a batch of d x d matrices (d <= 16), one thread
+ * per matrix, through the same Cholesky route as the reference (L, L^-1, L^-T L^-1; jitter ladder; LU
+ * fallback for the inverse, none for the solve).  status as above. */
+int hop_chol_inv_f64(int B, int d, const double *A, double *X, double jitter, int max_tries, int *status, void *stream);
+int hop_chol_solve_f64(int B, int d, int c, const double *A, const double *Bm, double *X, double jitter, int max_tries,
+                       int *status, void *stream);
+
+/* linearization.py:269-270 compute_affine_residuals: a_out [B][N][n] = F(X_k, U_k) - X_{k+1}. */
+int hop_affine_residuals_f64(int B, int sys, const double *params_host, int N, const double *X, const double *U,
+                             long u_batch_stride, double *a_out, void *stream);
+
+/* augmented.py:10-60 build_augmented_sequence_QR (blocks materialised in HBM: A_aug [B][N][d][d],
+ * B_aug [B][N][d][m], Q_aug [B][N][d][d]; R_inv is hop_chol_inv_f64 of sym(R)) and augmented.py:63-87
+ * build_terminal_aug_list (QT [B][N][d][d], QT[t-1] from X[t]).  a_resid may be NULL (= 0). */
+int hop_build_augmented_f64(int B, int N, int n, int m, const double *A, const double *Bm, const double *a_resid,
+                            const double *X, const double *U, long u_batch_stride, const double *xg, const double *w,
+                            const double *u_ref, const double *Q, unsigned wrap_mask, double q_reg, double rho_reg,
+                            double *A_aug, double *B_aug, double *Q_aug, void *stream);
+int hop_build_terminal_f64(int B, int N, int n, const double *X, const double *xg, const double *Qf, unsigned wrap_mask,
+                           double rho_reg, double *QT, void *stream);
+
 /* solver.py:65-105 cost_timeopt_true, batched: J_out[b] at the per-instance horizon T_star[b] (device int). */
 int hop_cost_f64(int B, int N, int n, int m, const double *X, const double *U, const double *xg, const double *w,
                  const double *u_ref, const double *Q, const double *R, const double *Qf, unsigned wrap_mask,
@@ -129,12 +151,21 @@ int hop_backward_linesearch_f64(int B, int sys, const double *params_host, int N
                                 const double *lm, double *k_out, double *K_out, int *ok_out, int *err_out, double *X_new,
                                 double *U_new, double *J_new, int *accepted, void *stream);
 
+/* solver.py:233-286 forward_linesearch_fixedT alone, with caller-provided gains k_list [B][N][m],
+ * K_list [B][N][m][n] (rows >= T_star[b] ignored); ok [B] or NULL masks instances to skip. */
+int hop_linesearch_f64(int B, int sys, const double *params_host, int N, const double *X, const double *U, const double *xg,
+                       const double *w, const double *u_ref, const double *Q, const double *R, const double *Qf,
+                       unsigned wrap_mask, const int *T_star, const double *k_list, const double *K_list, const int *ok,
+                       double *X_new, double *U_new, double *J_new, int *accepted, void *stream);
+
 /* solver.py:449-765 ilqr_timeopt(method="propagator"), batched over instances (x0, xg, w); the whole
  * per-instance state machine (warm start, accept/reject, LM schedule, stop rule) runs on the device.
  *   U_init [B][N][m] or NULL (= tile(u_ref), solver.py:480-481).
  *   Outputs: X [B][N+1][n], U [B][N][m] (final trajectories), J_hist/T_hist [B][max_iter+1] with n_hist [B]
  *   valid entries, J_curve [B][T_max] (last selection curve), T_star [B] (= T_hist[-1] or T_bar), status [B]
- *   (low byte != 0: the reference would have raised -> run_suite "crash"), *iters_run_host (host int, may be NULL).
+ *   (low byte != 0: the reference would have raised -> run_suite "crash"), *iters_run_host (host int, may be NULL),
+ *   timers_host (host double[4] or NULL): device seconds spent in linearize / select / backward / forward, the
+ *   keys of the reference's `timers` dict (solver.py:497).
  *   The call synchronises the stream once per outer iteration (early exit when every instance stopped). */
 unsigned long long hop_ilqr_workspace_bytes(int B, int N, int n, int m);
 int hop_ilqr_timeopt_f64(int B, int sys, const double *params_host, int N, int T_min, int T_max, const double *x0,
@@ -142,7 +173,7 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double *params_host, int N, int T
                          const double *R, const double *Qf, unsigned wrap_mask, int max_iter, double lm_init, int central,
                          int mode, void *workspace, unsigned long long workspace_bytes, double *X, double *U,
                          double *J_hist, int *T_hist, int *n_hist, double *J_curve, int *T_star, int *status,
-                         int *iters_run_host, void *stream);
+                         int *iters_run_host, double *timers_host, void *stream);
 
 /* Measures the FP64 FMA throughput of the current device with a register-resident DFMA chain
  * (8 independent accumulators per thread, 2048 threads per SM), timed with CUDA events.  This is

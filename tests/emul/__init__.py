@@ -15,7 +15,7 @@ _ip = C.POINTER(C.c_int)
 class SelectArgs(C.Structure):
     _fields_ = [("B", C.c_int), ("N", C.c_int), ("T_min", C.c_int), ("T_max", C.c_int), ("jitter", C.c_double),
                 ("max_tries", C.c_int), ("A_aug", _dp), ("B_aug", _dp), ("Q_aug", _dp), ("R_inv", _dp), ("z0", _dp),
-                ("QT", _dp), ("w_explicit", _dp), ("J_out", _dp), ("T_out", _ip), ("Jstar_out", _dp), ("status", _ip)]
+                ("QT", _dp), ("rinv_step_stride", C.c_long), ("w_explicit", _dp), ("J_out", _dp), ("T_out", _ip), ("Jstar_out", _dp), ("status", _ip)]
 
 
 class FusedArgs(C.Structure):
@@ -63,7 +63,7 @@ def select_generic(A_aug, B_aug, Q_aug, R_inv, z0, QT, T_min, T_max, w_explicit=
     wexp = None if w_explicit is None else _d(w_explicit)
     J = np.full((Bsz, T_max), np.nan); T = np.zeros(Bsz, np.int32); Js = np.zeros(Bsz); st = np.zeros(Bsz, np.int32)
     a = SelectArgs(Bsz, N, T_min, T_max, jitter, max_tries, _p(A_aug), _p(B_aug), _p(Q_aug), _p(R_inv), _p(z0), _p(QT),
-                   _p(wexp), _p(J), T.ctypes.data_as(_ip), _p(Js), st.ctypes.data_as(_ip))
+                   (m * m if R_inv.ndim == 4 else 0), _p(wexp), _p(J), T.ctypes.data_as(_ip), _p(Js), st.ctypes.data_as(_ip))
     rc = (lib().emul_select_generic_mma if mma else lib().emul_select_generic)(d, m, C.byref(a))
     assert rc == 0, f"emulated kernel failed rc={rc}"
     return J, T, Js, st

@@ -214,7 +214,38 @@ def gold_s2():
     save("s2_synthetic", **out)
 
 
+def gold_signatures():
+    """Public signatures of the reference's hot-path API (parameter names, kinds, defaults)."""
+    import inspect
+    import json
+    import run_suite
+    mods = {"utils": utils, "linearization": linearization, "augmented": augmented, "horizon_selection": horizon_selection,
+            "solver": solver, "systems": systems, "run_suite": run_suite}
+    names = {
+        "utils": ["_sym", "as_terminal_weight", "chol_inv", "chol_solve", "angle_normalize", "wrap_error"],
+        "linearization": ["linearize_central_diff_traj", "linearize_forward_diff_traj", "compute_affine_residuals"],
+        "augmented": ["build_augmented_sequence_QR", "build_terminal_aug_list"],
+        "horizon_selection": ["propagator_all_Jt_aug"],
+        "solver": ["rollout", "cost_timeopt_true", "backward_pass_truncated", "forward_linesearch_fixedT", "ilqr_timeopt",
+                   "ilqr_timeopt_ourmethod", "ilqr_timeopt_baseline1", "ilqr_timeopt_baseline2"],
+        "systems": ["make_double_integrator", "make_cartpole_swingup", "make_quadrotor", "make_segway_balance"],
+        "run_suite": ["sample_x", "run_case", "main"],
+    }
+    out = {}
+    for mod, fns in names.items():
+        for fn in fns:
+            sig = inspect.signature(getattr(mods[mod], fn))
+            out[f"{mod}.{fn}"] = [[p.name, p.kind.name, None if p.default is inspect.Parameter.empty else repr(p.default)]
+                                  for p in sig.parameters.values()]
+    out["run_suite.CASES"] = [c[0] for c in run_suite.CASES]
+    out["run_suite.SOLVERS"] = sorted(run_suite.SOLVERS)
+    with open(os.path.join(OUT, "signatures.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+    print("signatures.json", len(out), "entries")
+
+
 if __name__ == "__main__":
+    gold_signatures()
     gold_utils()
     gold_dynamics()
     gold_cases()

@@ -39,14 +39,14 @@ def test_supported_dims_table():
 
 def test_bad_arguments_are_rejected_before_any_device_work():
     lib = _cabi.load()
-    rc = lib.hop_select_f64(1, 8, 13, 4, 5, 9, None, None, None, None, None, None, None, 0, None, None, None, None, None)
+    rc = lib.hop_select_f64(1, 8, 13, 4, 5, 9, None, None, None, None, 0, None, None, None, 0, None, None, None, None, None)
     assert rc == -1 and b"T_max" in lib.hop_last_error_string()       # T_max > N
 
 
 @pytest.mark.skipif(_cabi.load().hop_device_count() > 0, reason="a GPU is present")
 def test_no_cpu_fallback_without_a_device():
     lib = _cabi.load()
-    rc = lib.hop_select_f64(1, 8, 13, 4, 1, 8, None, None, None, None, None, None, None, 0, None, None, None, None, None)
+    rc = lib.hop_select_f64(1, 8, 13, 4, 1, 8, None, None, None, None, 0, None, None, None, 0, None, None, None, None, None)
     assert rc == -3 and b"no CPU fallback" in lib.hop_last_error_string()
     from hop import api
     with pytest.raises(_cabi.HopError):

@@ -22,9 +22,12 @@ struct DdpConst {
 int dispatch_backward_linesearch(int sys, int B, const double* params_host, int N, const double* A, const double* Bm,
                                  const double* X, const double* U, const DdpConst& c, const int* T, const double* lm,
                                  const int* done, double* kl, double* Kl, int* ok, int* bw_err, double* Xn, double* Un,
-                                 double* Jn, int* acc, cudaStream_t st);
+                                 double* Jn, int* acc, cudaEvent_t mid, cudaStream_t st);
 int dispatch_cost(int n, int m, int B, int N, const double* X, const double* U, const DdpConst& c, const int* T, double* J,
                   cudaStream_t st);
+int dispatch_linesearch(int sys, int B, const double* params_host, int N, const double* X, const double* U, const DdpConst& c,
+                        const int* T, const double* kl, const double* Kl, const int* ok, double* Xn, double* Un, double* Jn,
+                        int* acc, cudaStream_t st);
 int launch_init_state(int B, double lm_init, double* lm, int* done, int* n_hist, int* status_out, cudaStream_t st);
 int launch_tile_u(int B, int N, int m, const double* u_ref, double* U, cudaStream_t st);
 int launch_after_select(int B, const int* sel_status, int* done, int* status_out, cudaStream_t st);
@@ -37,6 +40,16 @@ int launch_ddp_update(int B, int cap, const int* T_sel, const int* ok, const int
 int launch_copy_accepted(int B, size_t per_x, size_t per_u, const int* copy, const double* Xn, const double* Un, double* X,
                          double* U, cudaStream_t st);
 int launch_finalize(int B, int cap, const int* n_hist, const int* T_hist, const int* T_bar, int* T_star, cudaStream_t st);
+int launch_chol(int B, int d, int c, const double* A, const double* Bm, double* X, double jitter, int max_tries, int* status,
+                cudaStream_t st);
+int launch_affine_residuals(int B, int sys, const double* params_host, int N, const double* X, const double* U, long ustride,
+                            double* a, cudaStream_t st);
+int launch_build_augmented(int B, int N, int n, int m, const double* A, const double* Bm, const double* a, const double* X,
+                           const double* U, long ustride, const double* xg, const double* w, const double* u_ref,
+                           const double* Q, unsigned wrap_mask, double q_reg, double rho_reg, double* A_aug, double* B_aug,
+                           double* Q_aug, cudaStream_t st);
+int launch_build_terminal(int B, int N, int n, const double* X, const double* xg, const double* Qf, unsigned wrap_mask,
+                          double rho_reg, double* QT, cudaStream_t st);
 int sys_dims(int sys, int* n, int* m);
 
 static thread_local std::string g_err;
@@ -77,16 +90,17 @@ int hop_select_supported(int d, int m) {
 }
 
 int hop_select_f64(int B, int N, int d, int m, int T_min, int T_max, const double* A_aug, const double* B_aug,
-                   const double* Q_aug, const double* R_inv, const double* z0, const double* QT,
+                   const double* Q_aug, const double* R_inv, long rinv_step_stride, const double* z0, const double* QT,
                    const double* w_explicit, int mode, double* J_out, int* Tstar_out, double* Jstar_out, int* status,
                    void* stream) {
-    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || mode != HOP_MODE_EXACT) {
-        set_last_error("hop_select_f64: bad argument (need 1 <= T_min <= T_max <= N, mode = HOP_MODE_EXACT)");
+    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || (mode != HOP_MODE_EXACT && mode != HOP_MODE_FAST) ||
+        (rinv_step_stride != 0 && rinv_step_stride != (long)m * m)) {
+        set_last_error("hop_select_f64: bad argument (need 1 <= T_min <= T_max <= N, rinv_step_stride in {0, m*m})");
         return HOP_E_BADARG;
     }
     if (int rc = need_device()) return rc;
     if (B == 0) return 0;
-    SelectArgs p{B, N, T_min, T_max, kJitter, kMaxTries, A_aug, B_aug, Q_aug, R_inv, z0, QT, w_explicit,
+    SelectArgs p{B, N, T_min, T_max, kJitter, kMaxTries, A_aug, B_aug, Q_aug, R_inv, z0, QT, rinv_step_stride, w_explicit,
                  J_out, Tstar_out, Jstar_out, status};
     return dispatch_select_generic(d, m, p, (cudaStream_t)stream);
 }
@@ -161,6 +175,44 @@ int hop_select_from_x0_f64(int B, int sys, const double* params_host, int N, int
                                 wrap_mask, 1e-9, 1e-12, mode, J_out, Tstar_out, Jstar_out, status, stream);
 }
 
+// ---- utilities of the reference API (utils.py, linearization.py:269, augmented.py) -----------------------
+int hop_chol_inv_f64(int B, int d, const double* A, double* X, double jitter, int max_tries, int* status, void* stream) {
+    if (d < 1 || d > 16 || B < 0) { set_last_error("hop_chol_inv_f64: need 1 <= d <= 16"); return HOP_E_BADARG; }
+    if (int rc = need_device()) return rc;
+    if (B == 0) return 0;
+    return launch_chol(B, d, 0, A, nullptr, X, jitter, max_tries, status, (cudaStream_t)stream);
+}
+int hop_chol_solve_f64(int B, int d, int c, const double* A, const double* Bm, double* X, double jitter, int max_tries,
+                       int* status, void* stream) {
+    if (d < 1 || d > 16 || c < 1 || B < 0) { set_last_error("hop_chol_solve_f64: need 1 <= d <= 16, c >= 1"); return HOP_E_BADARG; }
+    if (int rc = need_device()) return rc;
+    if (B == 0) return 0;
+    return launch_chol(B, d, c, A, Bm, X, jitter, max_tries, status, (cudaStream_t)stream);
+}
+int hop_affine_residuals_f64(int B, int sys, const double* params_host, int N, const double* X, const double* U,
+                             long u_batch_stride, double* a_out, void* stream) {
+    if (int rc = need_device()) return rc;
+    if (B <= 0) return B == 0 ? 0 : HOP_E_BADARG;
+    return launch_affine_residuals(B, sys, params_host, N, X, U, u_batch_stride, a_out, (cudaStream_t)stream);
+}
+int hop_build_augmented_f64(int B, int N, int n, int m, const double* A, const double* Bm, const double* a_resid,
+                            const double* X, const double* U, long u_batch_stride, const double* xg, const double* w,
+                            const double* u_ref, const double* Q, unsigned wrap_mask, double q_reg, double rho_reg,
+                            double* A_aug, double* B_aug, double* Q_aug, void* stream) {
+    if (n < 1 || n > 15 || m < 1 || m > 8) { set_last_error("hop_build_augmented_f64: need n <= 15, m <= 8"); return HOP_E_BADARG; }
+    if (int rc = need_device()) return rc;
+    if (B <= 0) return B == 0 ? 0 : HOP_E_BADARG;
+    return launch_build_augmented(B, N, n, m, A, Bm, a_resid, X, U, u_batch_stride, xg, w, u_ref, Q, wrap_mask, q_reg, rho_reg,
+                                  A_aug, B_aug, Q_aug, (cudaStream_t)stream);
+}
+int hop_build_terminal_f64(int B, int N, int n, const double* X, const double* xg, const double* Qf, unsigned wrap_mask,
+                           double rho_reg, double* QT, void* stream) {
+    if (n < 1 || n > 15) { set_last_error("hop_build_terminal_f64: need n <= 15"); return HOP_E_BADARG; }
+    if (int rc = need_device()) return rc;
+    if (B <= 0) return B == 0 ? 0 : HOP_E_BADARG;
+    return launch_build_terminal(B, N, n, X, xg, Qf, wrap_mask, rho_reg, QT, (cudaStream_t)stream);
+}
+
 // ---- HOP-DDP pieces and the batched solver loop --------------------------------------------------------
 int hop_cost_f64(int B, int N, int n, int m, const double* X, const double* U, const double* xg, const double* w,
                  const double* u_ref, const double* Q, const double* R, const double* Qf, unsigned wrap_mask,
@@ -180,7 +232,18 @@ int hop_backward_linesearch_f64(int B, int sys, const double* params_host, int N
     if (B <= 0) return B == 0 ? 0 : HOP_E_BADARG;
     DdpConst c{xg, w, u_ref, Q, R, Qf, wrap_mask};
     return dispatch_backward_linesearch(sys, B, params_host, N, A, Bm, X, U, c, T_star, lm, nullptr, k_out, K_out, ok_out,
-                                        err_out, X_new, U_new, J_new, accepted, (cudaStream_t)stream);
+                                        err_out, X_new, U_new, J_new, accepted, nullptr, (cudaStream_t)stream);
+}
+
+int hop_linesearch_f64(int B, int sys, const double* params_host, int N, const double* X, const double* U, const double* xg,
+                       const double* w, const double* u_ref, const double* Q, const double* R, const double* Qf,
+                       unsigned wrap_mask, const int* T_star, const double* k_list, const double* K_list, const int* ok,
+                       double* X_new, double* U_new, double* J_new, int* accepted, void* stream) {
+    if (int rc = need_device()) return rc;
+    if (B <= 0) return B == 0 ? 0 : HOP_E_BADARG;
+    DdpConst c{xg, w, u_ref, Q, R, Qf, wrap_mask};
+    return dispatch_linesearch(sys, B, params_host, N, X, U, c, T_star, k_list, K_list, ok, X_new, U_new, J_new, accepted,
+                               (cudaStream_t)stream);
 }
 
 namespace {
@@ -225,7 +288,7 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T
                          const double* R, const double* Qf, unsigned wrap_mask, int max_iter, double lm_init, int central,
                          int mode, void* workspace, unsigned long long workspace_bytes, double* X, double* U,
                          double* J_hist, int* T_hist, int* n_hist, double* J_curve, int* T_star, int* status,
-                         int* iters_run_host, void* stream) {
+                         int* iters_run_host, double* timers_host, void* stream) {
     int n = 0, m = 0;
     if (sys_dims(sys, &n, &m)) { set_last_error("hop_ilqr_timeopt_f64: unknown system id"); return HOP_E_BADARG; }
     if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || max_iter < 0) {
@@ -250,38 +313,62 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T
                     wrap_mask, 1e-9, 1e-12, mode, skip, J_curve, ws.T_sel, ws.Jstar, ws.sel_status};
         return dispatch_select_fused(n, m, p, st);
     };
+    // optional per-phase device timing (the reference's timers dict: linearize / select / backward / forward)
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double tsum[4] = {0.0, 0.0, 0.0, 0.0};
+    if (timers_host) for (auto& e : ev) cudaEventCreate(&e);
+    auto mark = [&](int i) { if (timers_host) cudaEventRecord(ev[i], st); };
+    auto collect = [&]() {
+        if (!timers_host) return;
+        cudaEventSynchronize(ev[4]);
+        for (int i = 0; i < 4; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); tsum[i] += 1e-3 * ms; }
+    };
     HOP_TRY(launch_init_state(B, lm_init, ws.lm, ws.done, n_hist, status, st));
     if (U_init) HOP_TRY(report_cuda(cudaMemcpyAsync(U, U_init, sizeof(double) * (size_t)B * N * m, cudaMemcpyDeviceToDevice, st), "copy U_init"));
     else HOP_TRY(launch_tile_u(B, N, m, u_ref, U, st));                                                  // solver.py:480-481
     HOP_TRY(dispatch_rollout(B, sys, params_host, N, x0, U, ustride, 1e6, X, st));                       // :492
+    mark(0);
     HOP_TRY(dispatch_linearize(B, sys, params_host, N, X, U, ustride, central, 1e-5, 1e-5, 1e-6, 1e-6, nullptr, ws.A, ws.Bm, st));
+    mark(1);
     HOP_TRY(select(nullptr));                                                                            // :516-522
     HOP_TRY(launch_after_select(B, ws.sel_status, ws.done, status, st));
+    mark(2);
     HOP_TRY(dispatch_backward_linesearch(sys, B, params_host, N, ws.A, ws.Bm, X, U, c, ws.T_sel, ws.lm, ws.done, ws.kl, ws.Kl,
-                                         ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, st));            // :541-551
+                                         ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, ev[3], st));     // :541-551
     HOP_TRY(launch_warm_update(B, cap, ws.T_sel, ws.ok, ws.acc, ws.Jn, ws.bw_err, ws.done, ws.T_bar, J_hist, T_hist, n_hist,
                                ws.copy, status, st));
     HOP_TRY(launch_copy_accepted(B, (size_t)(N + 1) * n, (size_t)N * m, ws.copy, ws.Xn, ws.Un, X, U, st));
+    mark(4);
+    collect();
     int iters = 0;
     for (int it = 0; it < max_iter; ++it) {                                                              // :564
         ++iters;
+        mark(0);
         HOP_TRY(dispatch_linearize(B, sys, params_host, N, X, U, ustride, central, 1e-5, 1e-5, 1e-6, 1e-6, ws.done, ws.A, ws.Bm, st));
+        mark(1);
         HOP_TRY(select(ws.done));                                                                        // :581-590
         HOP_TRY(launch_after_select(B, ws.sel_status, ws.done, status, st));
+        mark(2);
         HOP_TRY(dispatch_backward_linesearch(sys, B, params_host, N, ws.A, ws.Bm, X, U, c, ws.T_sel, ws.lm, ws.done, ws.kl,
-                                             ws.Kl, ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, st)); // :594-604
+                                             ws.Kl, ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, ev[3], st)); // :594-604
         HOP_TRY(report_cuda(cudaMemsetAsync(ws.n_active, 0, sizeof(int), st), "memset n_active"));
         HOP_TRY(launch_ddp_update(B, cap, ws.T_sel, ws.ok, ws.acc, ws.Jn, ws.bw_err, ws.done, ws.T_bar, ws.lm, J_hist, T_hist,
                                   n_hist, ws.copy, status, ws.n_active, st));                             // :735-748
         HOP_TRY(launch_copy_accepted(B, (size_t)(N + 1) * n, (size_t)N * m, ws.copy, ws.Xn, ws.Un, X, U, st));
+        mark(4);
         int active = 0;
         HOP_TRY(report_cuda(cudaMemcpyAsync(&active, ws.n_active, sizeof(int), cudaMemcpyDeviceToHost, st), "read n_active"));
         HOP_TRY(report_cuda(cudaStreamSynchronize(st), "hop_ilqr_timeopt_f64"));
+        collect();
         if (active == 0) break;
     }
     HOP_TRY(launch_finalize(B, cap, n_hist, T_hist, ws.T_bar, T_star, st));
 #undef HOP_TRY
     if (iters_run_host) *iters_run_host = iters;
+    if (timers_host) {
+        for (int i = 0; i < 4; ++i) timers_host[i] = tsum[i];
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
     return 0;
 }
 

@@ -172,11 +172,12 @@ template <int SYS>
 static int ddp_backward_linesearch(int B, const DynParams2& prm, int N, const double* A, const double* Bm, const double* X,
                                    const double* U, const DdpConst& c, const int* T, const double* lm, const int* done,
                                    double* kl, double* Kl, int* ok, int* bw_err, double* Xn, double* Un, double* Jn, int* acc,
-                                   cudaStream_t st) {
+                                   cudaEvent_t mid, cudaStream_t st) {
     constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
     const int threads = 64;
     k_backward<n, m><<<grid1(B, threads), threads, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
     if (int rc = check_launch("k_backward")) return rc;
+    if (mid) cudaEventRecord(mid, st);
     k_linesearch<SYS><<<grid1(B, threads), threads, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, done, Xn, Un, Jn, acc);
     return check_launch("k_linesearch");
 }
@@ -184,14 +185,36 @@ static int ddp_backward_linesearch(int B, const DynParams2& prm, int N, const do
 int dispatch_backward_linesearch(int sys, int B, const double* params_host, int N, const double* A, const double* Bm,
                                  const double* X, const double* U, const DdpConst& c, const int* T, const double* lm,
                                  const int* done, double* kl, double* Kl, int* ok, int* bw_err, double* Xn, double* Un,
-                                 double* Jn, int* acc, cudaStream_t st) {
+                                 double* Jn, int* acc, cudaEvent_t mid, cudaStream_t st) {
     DynParams2 prm;
     for (int i = 0; i < HOP_NPARAMS; ++i) prm.p[i] = params_host[i];
     switch (sys) {
-        case 0: return ddp_backward_linesearch<0>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, st);
-        case 1: return ddp_backward_linesearch<1>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, st);
-        case 2: return ddp_backward_linesearch<2>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, st);
-        case 3: return ddp_backward_linesearch<3>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, st);
+        case 0: return ddp_backward_linesearch<0>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, mid, st);
+        case 1: return ddp_backward_linesearch<1>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, mid, st);
+        case 2: return ddp_backward_linesearch<2>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, mid, st);
+        case 3: return ddp_backward_linesearch<3>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, mid, st);
+    }
+    set_last_error("unknown system id");
+    return HOP_E_BADARG;
+}
+
+template <int SYS>
+static int launch_linesearch_only(int B, const DynParams2& prm, int N, const double* X, const double* U, const DdpConst& c,
+                                  const int* T, const double* kl, const double* Kl, const int* ok, double* Xn, double* Un,
+                                  double* Jn, int* acc, cudaStream_t st) {
+    k_linesearch<SYS><<<grid1(B, 64), 64, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, nullptr, Xn, Un, Jn, acc);
+    return check_launch("k_linesearch");
+}
+int dispatch_linesearch(int sys, int B, const double* params_host, int N, const double* X, const double* U, const DdpConst& c,
+                        const int* T, const double* kl, const double* Kl, const int* ok, double* Xn, double* Un, double* Jn,
+                        int* acc, cudaStream_t st) {
+    DynParams2 prm;
+    for (int i = 0; i < HOP_NPARAMS; ++i) prm.p[i] = params_host[i];
+    switch (sys) {
+        case 0: return launch_linesearch_only<0>(B, prm, N, X, U, c, T, kl, Kl, ok, Xn, Un, Jn, acc, st);
+        case 1: return launch_linesearch_only<1>(B, prm, N, X, U, c, T, kl, Kl, ok, Xn, Un, Jn, acc, st);
+        case 2: return launch_linesearch_only<2>(B, prm, N, X, U, c, T, kl, Kl, ok, Xn, Un, Jn, acc, st);
+        case 3: return launch_linesearch_only<3>(B, prm, N, X, U, c, T, kl, Kl, ok, Xn, Un, Jn, acc, st);
     }
     set_last_error("unknown system id");
     return HOP_E_BADARG;

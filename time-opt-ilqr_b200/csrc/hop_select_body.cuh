@@ -16,6 +16,7 @@ struct SelectArgs {
     double jitter;
     int max_tries;
     const double *A_aug, *B_aug, *Q_aug, *R_inv, *z0, *QT;
+    long rinv_step_stride;      // 0: one R^-1 [m][m] per instance; m*m: R_inv is [B][N][m][m] (R_list varies with k)
     const double* w_explicit;   // optional [B]: argmin is taken over J(t) + w t (S2 workload)
     double* J_out;              // [B][T_max]
     int* T_out;                 // [B]
@@ -67,7 +68,8 @@ HOP_DEVICE void select_generic_body(const SelectArgs& p, int b_raw, double* sm) 
 
     for (int i = r; i < Ge::SLAB; i += G) sm[i] = 0.0;
     simt::sync();
-    for (int i = r; i < M * M; i += G) sm[Ge::SR + (i / M) * Ge::MP + (i % M)] = p.R_inv[(size_t)b * M * M + i];
+    const size_t rinv_inst = (size_t)(p.rinv_step_stride ? p.N : 1) * M * M;
+    for (int i = r; i < M * M; i += G) sm[Ge::SR + (i / M) * Ge::MP + (i % M)] = p.R_inv[(size_t)b * rinv_inst + i];
     if (act) sm[Ge::Z0 + r] = p.z0[(size_t)b * D + r];
 
     Prefix<D> P;
@@ -93,6 +95,9 @@ HOP_DEVICE void select_generic_body(const SelectArgs& p, int b_raw, double* sm) 
             SQ[row * DP + col] = Tk[i];
         }
         for (int i = r; i < D * M; i += G) SB[(i % M) * DP + (i / M)] = Bk[i];
+        if (p.rinv_step_stride)
+            for (int i = r; i < M * M; i += G)
+                sm[Ge::SR + (i / M) * Ge::MP + (i % M)] = p.R_inv[(size_t)b * rinv_inst + (size_t)k * p.rinv_step_stride + i];
         simt::sync();
         {
             double q[D];

@@ -98,8 +98,9 @@ HOP_DEVICE void select_generic_body(const SelectArgs& p, int b_raw, double* scra
     L.init();
     const bool valid = b_raw < p.B;
     const int b = valid ? b_raw : p.B - 1;
+    const size_t rinv_inst = (size_t)(p.rinv_step_stride ? p.N : 1) * M * M;
     Mat RinvT;
-    mat_load_t(RinvT, p.R_inv + (size_t)b * M * M, M, M, M, L);
+    mat_load_t(RinvT, p.R_inv + (size_t)b * rinv_inst, M, M, M, L);
     double zr[2], zc[2][2];
 #pragma unroll
     for (int I = 0; I < 2; ++I) zr[I] = (L.row(I) < D) ? p.z0[(size_t)b * D + L.row(I)] : 0.0;
@@ -120,6 +121,7 @@ HOP_DEVICE void select_generic_body(const SelectArgs& p, int b_raw, double* scra
             mat_load(A, p.A_aug + (base + k) * D * D, D, D, D, L);
             mat_load(Bm, p.B_aug + (base + k) * D * M, D, M, M, L);
             mat_load(Qs, p.Q_aug + (base + k) * D * D, D, D, D, L);
+            if (p.rinv_step_stride) mat_load_t(RinvT, p.R_inv + (size_t)b * rinv_inst + (size_t)k * p.rinv_step_stride, M, M, M, L);
             mat_sym(Qs, L);                                                    // chol_inv symmetrises its input (utils.py:74)
             stage_prefix_step<D, M>(k, P, Qs, A, Bm, RinvT, L, scratch, p.jitter, p.max_tries, status);
         }

@@ -17,7 +17,7 @@ SIGNATURES = {
     "hop_last_error_string": (C.c_char_p, []),
     "hop_device_count": (_i, []),
     "hop_select_supported": (_i, [_i, _i]),
-    "hop_select_f64": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hop_select_f64": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "hop_select_fused_f64": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _u,
                                   _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),
     "hop_rollout_f64": (_i, [_i, _i, _vp, _i, _vp, _vp, _l, _d, _vp, _vp]),
@@ -27,12 +27,20 @@ SIGNATURES = {
                                     _ull, _vp, _vp, _vp, _vp, _vp]),
     "hop_select_from_x0_host_f64": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _u, _i, _i,
                                          _vp, _vp, _vp, _vp]),
+    "hop_chol_inv_f64": (_i, [_i, _i, _vp, _vp, _d, _i, _vp, _vp]),
+    "hop_chol_solve_f64": (_i, [_i, _i, _i, _vp, _vp, _vp, _d, _i, _vp, _vp]),
+    "hop_affine_residuals_f64": (_i, [_i, _i, _vp, _i, _vp, _vp, _l, _vp, _vp]),
+    "hop_build_augmented_f64": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _u, _d, _d, _vp, _vp,
+                                     _vp, _vp]),
+    "hop_build_terminal_f64": (_i, [_i, _i, _i, _vp, _vp, _vp, _u, _d, _vp, _vp]),
     "hop_cost_f64": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u, _vp, _vp, _vp]),
     "hop_backward_linesearch_f64": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u, _vp, _vp,
                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hop_linesearch_f64": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _vp, _vp]),
     "hop_ilqr_workspace_bytes": (_ull, [_i, _i, _i, _i]),
     "hop_ilqr_timeopt_f64": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u, _i, _d, _i, _i, _vp,
-                                  _ull, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                  _ull, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hop_probe_fp64_tflops": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

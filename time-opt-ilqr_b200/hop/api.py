@@ -115,6 +115,7 @@ def propagator_all_Jt_aug_batched(A_aug, B_aug, Q_aug, R_inv, z0, QT, T_min: int
     R_inv = _dev(R_inv, dev)
     if R_inv.dim() == 2:
         R_inv = R_inv.expand(Bsz, m, m).contiguous()
+    rstride = m * m if R_inv.dim() == 4 else 0      # [B,N,m,m]: a different R^-1 per step
     z0 = _dev(z0, dev)
     if z0.dim() == 1:
         z0 = z0.expand(Bsz, d).contiguous()
@@ -123,7 +124,7 @@ def propagator_all_Jt_aug_batched(A_aug, B_aug, Q_aug, R_inv, z0, QT, T_min: int
     J, T, Js, st = _outputs(Bsz, T_max, dev)
     with torch.cuda.device(dev):
         rc = lib.hop_select_f64(Bsz, N, d, m, int(T_min), T_max, _ptr(A_aug), _ptr(B_aug), _ptr(Q_aug), _ptr(R_inv),
-                                _ptr(z0), _ptr(QT), _ptr(wx), mode, _ptr(J), _ptr(T), _ptr(Js), _ptr(st), _stream(dev))
+                                rstride, _ptr(z0), _ptr(QT), _ptr(wx), mode, _ptr(J), _ptr(T), _ptr(Js), _ptr(st), _stream(dev))
     _cabi.check(rc, "hop_select_f64")
     return Selection(J, T, Js, st)
 
@@ -402,13 +403,15 @@ def ilqr_timeopt_batched(case, x0, xg=None, w=None, U_init=None, max_iter: int =
     nbytes = int(lib.hop_ilqr_workspace_bytes(Bsz, N, n, m))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     iters = C.c_int(0)
+    timers = (C.c_double * 4)()
     with torch.cuda.device(dev):
         rc = lib.hop_ilqr_timeopt_f64(Bsz, c["F"].hop_sys, c["params"].ctypes.data_as(C.c_void_p), N, c["T_min"], T_max,
                                       _ptr(x0), _ptr(Ui), _ptr(c["xg"]), _ptr(c["w"]), _ptr(c["u_ref"]), _ptr(c["Q"]),
                                       _ptr(c["R"]), _ptr(c["Qf"]), c["wrap"], int(max_iter), float(lm_init),
                                       int(bool(use_central_diff)), int(mode), _ptr(ws), nbytes, _ptr(X), _ptr(U),
                                       _ptr(J_hist), _ptr(T_hist), _ptr(n_hist), _ptr(J_curve), _ptr(T_star), _ptr(status),
-                                      C.cast(C.byref(iters), C.c_void_p), _stream(dev))
+                                      C.cast(C.byref(iters), C.c_void_p), C.cast(timers, C.c_void_p), _stream(dev))
     _cabi.check(rc, "hop_ilqr_timeopt_f64")
     return dict(X=X, U=U, J_hist=J_hist, T_hist=T_hist, n_hist=n_hist, J_curve=J_curve, T_star=T_star, status=status,
-                iters=iters.value)
+                iters=iters.value,
+                timers=dict(zip(("linearize", "select", "backward", "forward"), (float(v) for v in timers))))
