@@ -31,11 +31,12 @@ def build_augmented_sequence_QR(F, A_list, B_list, X, U, xg, u_ref, Q, R, w, wra
     At, Bt, at = dev(stack(A_list)[None]), dev(stack(B_list)[None]), dev(a)
     Xt, Ut = dev(X[None]), dev(U[None])
     xgt, wt = dev(np.asarray(xg, dtype=float).reshape(1, n)), dev([float(w)])
+    urt, Qt_ = dev(u_ref), dev(Q)        # keep every device buffer referenced until the launch has been issued
     A_aug = torch.empty((1, N, d, d), dtype=torch.float64, device=At.device)
     B_aug = torch.empty((1, N, d, m), dtype=torch.float64, device=At.device)
     Q_aug = torch.empty((1, N, d, d), dtype=torch.float64, device=At.device)
     _cabi.check(lib.hop_build_augmented_f64(1, N, n, m, ptr(At), ptr(Bt), ptr(at), ptr(Xt), ptr(Ut), N * m, ptr(xgt), ptr(wt),
-                                            ptr(dev(u_ref)), ptr(dev(Q)), api.wrap_mask(wrap_idx), float(q_reg),
+                                            ptr(urt), ptr(Qt_), api.wrap_mask(wrap_idx), float(q_reg),
                                             float(rho_reg), ptr(A_aug), ptr(B_aug), ptr(Q_aug), stream()),
                 "hop_build_augmented_f64")
     A_aug, B_aug, Q_aug = A_aug[0].cpu().numpy(), B_aug[0].cpu().numpy(), Q_aug[0].cpu().numpy()
@@ -51,8 +52,9 @@ def build_terminal_aug_list(X, xg, alpha, wrap_idx: Optional[List[int]] = None, 
     N = X.shape[0] - 1
     Qf = as_terminal_weight(alpha, n)
     Xt = dev(X[None])
+    xgt, Qft = dev(np.asarray(xg, dtype=float).reshape(1, n)), dev(Qf)
     QT = torch.empty((1, N, n + 1, n + 1), dtype=torch.float64, device=Xt.device)
-    _cabi.check(lib.hop_build_terminal_f64(1, N, n, ptr(Xt), ptr(dev(np.asarray(xg, dtype=float).reshape(1, n))), ptr(dev(Qf)),
+    _cabi.check(lib.hop_build_terminal_f64(1, N, n, ptr(Xt), ptr(xgt), ptr(Qft),
                                            api.wrap_mask(wrap_idx), float(rho_reg), ptr(QT), stream()),
                 "hop_build_terminal_f64")
     QT = QT[0].cpu().numpy()

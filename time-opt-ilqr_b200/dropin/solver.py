@@ -113,10 +113,13 @@ def forward_linesearch_fixedT(F, X, U, xg, u_ref, Q, R, alpha, w: float, T_star:
     Jn = torch.zeros(1, dtype=torch.float64, device=Xt.device); acc = torch.zeros(1, dtype=torch.int32, device=Xt.device)
     T = torch.tensor([T_star], dtype=torch.int32, device=Xt.device)
     ok = torch.ones(1, dtype=torch.int32, device=Xt.device)
-    _cabi.check(lib.hop_linesearch_f64(1, F.hop_sys, api._params(F).ctypes.data_as(C.c_void_p), N, ptr(Xt), ptr(Ut),
-                                       ptr(d(np.asarray(xg, float).reshape(1, n))), ptr(d([float(w)])), ptr(d(u_ref)), ptr(d(Q)),
-                                       ptr(d(R)), ptr(d(as_terminal_weight(alpha, n))), api.wrap_mask(wrap_idx), ptr(T), ptr(d(kl)),
-                                       ptr(d(Kl)), ptr(ok), ptr(Xn), ptr(Un), ptr(Jn), ptr(acc), stream()), "hop_linesearch_f64")
+    # every device buffer stays referenced until the launch has been issued
+    xgt, wt, urt, Qt_, Rt, Qft = d(np.asarray(xg, float).reshape(1, n)), d([float(w)]), d(u_ref), d(Q), d(R), d(as_terminal_weight(alpha, n))
+    klt, Klt = d(kl), d(Kl)
+    prm = api._params(F)
+    _cabi.check(lib.hop_linesearch_f64(1, F.hop_sys, prm.ctypes.data_as(C.c_void_p), N, ptr(Xt), ptr(Ut), ptr(xgt), ptr(wt), ptr(urt),
+                                       ptr(Qt_), ptr(Rt), ptr(Qft), api.wrap_mask(wrap_idx), ptr(T), ptr(klt), ptr(Klt), ptr(ok),
+                                       ptr(Xn), ptr(Un), ptr(Jn), ptr(acc), stream()), "hop_linesearch_f64")
     if not int(acc[0]):
         return X, U, float(Jn[0]), False
     return Xn[0].cpu().numpy(), Un[0].cpu().numpy(), float(Jn[0]), True
