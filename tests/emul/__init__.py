@@ -29,7 +29,7 @@ class FusedArgs(C.Structure):
 def build(force=False):
     srcs = [os.path.join(_HERE, f) for f in ("simt_emul.cpp", "simt_emul.h", "emul_select.cpp")]
     srcs += [os.path.join(_CSRC, f) for f in ("hop_select_core.cuh", "hop_select_body.cuh", "hop_simt.cuh", "hop_mma.cuh",
-                                              "hop_select_mma_body.cuh")]
+                                              "hop_select_mma_body.cuh", "hop_select_pipe_body.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-DHOP_HOST_EMUL", "-Wno-unknown-pragmas", "-I" + _HERE, "-I" + _CSRC, "-fPIC",
                                "-shared", "-o", _SO, os.path.join(_HERE, "simt_emul.cpp"),

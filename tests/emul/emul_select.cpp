@@ -5,6 +5,7 @@
 
 #include "hop_select_body.cuh"
 #include "hop_select_mma_body.cuh"
+#include "hop_select_pipe_body.cuh"
 
 namespace {
 template <int D, int M, int G>
@@ -72,6 +73,12 @@ void mma_fused_lane(void* a) {
     hop::mma::select_fused_body<D, M, MODE>(*j->p, j->b, j->scratch, j->cst);
 }
 template <int D, int M>
+void mma_pipe_lane(void* a) {   // mirrors k_select_fused_mma<.., MODE = 2>
+    auto* j = (MmaFusedJob<D, M>*)a;
+    if (hop::mma::select_fused_pipe_body<D, M>(*j->p, j->b, j->scratch, j->cst)) return;
+    hop::mma::select_fused_body<D, M, 1>(*j->p, j->b, j->scratch, j->cst);
+}
+template <int D, int M>
 void mma_fast_const_lane(void* a) {
     auto* j = (MmaFusedJob<D, M>*)a;
     hop::mma::fast_const_fill_warp<D, M>(*j->p, j->cst, j->scratch);
@@ -79,15 +86,17 @@ void mma_fast_const_lane(void* a) {
 template <int D, int M>
 int run_fused_mma(const hop::FusedArgs& p) {
     std::vector<double> scratch(hop::mma::kWarpScratch, -7.0);
-    std::vector<double> cst(hop::mma::FastConst<D, M>::SIZE, 0.0);
+    std::vector<double> cst(hop::mma::PipeConst<D, M>::SIZE, 0.0);
     hop::fused_const_fill<D, M>(p, cst.data(), 0, 1);
-    if (p.mode == 1) {
+    if (p.mode >= 1) {
         MmaFusedJob<D, M> j{&p, 0, scratch.data(), cst.data()};
         if (hop::simt::run_warp(mma_fast_const_lane<D, M>, &j)) return -1;
     }
+    if (p.mode == 2) hop::mma::pipe_const_fill<D, M>(cst.data(), 0, 1);
     for (int b = 0; b < p.B; ++b) {
         MmaFusedJob<D, M> j{&p, b, scratch.data(), cst.data()};
-        if (hop::simt::run_warp(p.mode == 1 ? mma_fused_lane<D, M, 1> : mma_fused_lane<D, M, 0>, &j)) return -1;
+        auto fn = p.mode == 2 ? mma_pipe_lane<D, M> : (p.mode == 1 ? mma_fused_lane<D, M, 1> : mma_fused_lane<D, M, 0>);
+        if (hop::simt::run_warp(fn, &j)) return -1;
     }
     return 0;
 }

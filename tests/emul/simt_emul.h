@@ -28,6 +28,7 @@ int run_warp(void (*fn)(void*), void* arg);
 // bulk-copy / mbarrier stand-ins: the copy completes at issue time, waits are no-ops
 inline void mbar_init(unsigned long long*, unsigned) {}
 inline void mbar_fence_init() {}
+inline void mbar_inval(unsigned long long*) {}
 inline void mbar_expect_tx(unsigned long long*, unsigned) {}
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) {
     const char* s = (const char*)src; char* d = (char*)dst;

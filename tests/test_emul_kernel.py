@@ -76,7 +76,7 @@ def test_emulated_dmma_generic_kernel_matches_oracle(d, m, N):
     assert np.array_equal(T, np.argmin(Jo + w[:, None] * np.arange(1, N + 1), axis=1) + 1)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])   # 2 = software-pipelined FAST schedule (hop_select_pipe_body.cuh)
 def test_emulated_dmma_fused_kernel_matches_reference_golden(mode):
     g = golden("case_Quadrotor")
     F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case("Quadrotor", N=128)
@@ -88,3 +88,22 @@ def test_emulated_dmma_fused_kernel_matches_reference_golden(mode):
     assert (st[0] & 0xFF) == 0 and int(T[0]) == Tr
     assert abs(J[0, Tr - 1] - Jr[Tr - 1]) <= 1e-8 * abs(Jr[Tr - 1])
     assert rel(J[0, T_min - 1:T_max], Jr[T_min - 1:T_max]) <= 1e-6
+
+
+def test_emulated_pipelined_kernel_falls_back_to_sequential_body():
+    """A non-finite trajectory entry aborts the pipelined sweep mid-horizon; the sequential body then owns the
+    status word (reference: FloatingPointError, utils.py:75).  T_max = N exercises the X-only last stage."""
+    g = golden("case_Quadrotor")
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case("Quadrotor", N=128)
+    Nn = 12
+    A, B, a, X, U = (g[k][:Nn].copy() for k in ("A_fwd", "B_fwd", "a_resid", "X", "U"))
+    X = g["X"][:Nn + 1].copy()
+    args = (xg[None], np.array([w]), u_ref, Q, R, O.as_terminal_weight(alpha, 12), O.wrap_mask(wrap_idx), 1, Nn)
+    J1, T1, _, st1 = emul.select_fused(A[None], B[None], a[None], X[None], U[None], *args, mma=True, mode=1)
+    J2, T2, _, st2 = emul.select_fused(A[None], B[None], a[None], X[None], U[None], *args, mma=True, mode=2)
+    assert st1[0] == 0 and st2[0] == 0 and T1[0] == T2[0] and rel(J2, J1) <= 1e-5
+    A[7, 3, 3] = np.nan
+    J1, T1, _, st1 = emul.select_fused(A[None], B[None], a[None], X[None], U[None], *args, mma=True, mode=1)
+    J2, T2, _, st2 = emul.select_fused(A[None], B[None], a[None], X[None], U[None], *args, mma=True, mode=2)
+    assert (st2[0] & 0xFF) == 1 and st1[0] == st2[0]
+    assert np.array_equal(J1, J2, equal_nan=True) and T1[0] == T2[0]

@@ -9,6 +9,7 @@
 #include "hop_common.cuh"
 #include "hop_select_body.cuh"
 #include "hop_select_mma_body.cuh"
+#include "hop_select_pipe_body.cuh"
 #include "../../include/hop_b200.h"
 
 namespace hop {
@@ -72,6 +73,13 @@ __global__ void __launch_bounds__(kMmaWarps * 32) k_select_generic_mma(const Sel
     mma::select_generic_body<D, M>(p, blockIdx.x * kMmaWarps + warp, smem + (size_t)warp * mma::kWarpScratch);
 }
 
+// sequential FAST body out of line: the cold path of the pipelined kernel (jitter ladder, LU, status word)
+template <int D, int M>
+__device__ __noinline__ void select_fused_seq_cold(const FusedArgs& p, int b, double* scratch, const double* cst) {
+    mma::select_fused_body<D, M, 1>(p, b, scratch, cst);
+}
+
+// MODE 0: EXACT, 1: FAST sequential, 2: FAST software-pipelined (hop_select_pipe_body.cuh) with MODE 1 as its cold path
 template <int D, int M, int MODE, int MINB>
 __global__ void __launch_bounds__(kMmaWarps * 32, MINB) k_select_fused_mma(const FusedArgs p) {
     extern __shared__ __align__(16) double smem[];
@@ -79,11 +87,23 @@ __global__ void __launch_bounds__(kMmaWarps * 32, MINB) k_select_fused_mma(const
     const int warp = threadIdx.x >> 5;
     fused_const_fill<D, M>(p, cst, threadIdx.x, blockDim.x);
     __syncthreads();
-    if (MODE == 1) {   // K = (Qs + eps I)^-1, K' = (P + eps I)^-1 once per CTA
+    if (MODE >= 1) {   // K = (Qs + eps I)^-1, K' = (P + eps I)^-1 once per CTA
         if (warp == 0) mma::fast_const_fill_warp<D, M>(p, cst, smem);
         __syncthreads();
     }
-    mma::select_fused_body<D, M, MODE>(p, blockIdx.x * kMmaWarps + warp, smem + (size_t)warp * mma::kWarpScratch, cst);
+    if (MODE == 2) {
+        mma::pipe_const_fill<D, M>(cst, threadIdx.x, blockDim.x);
+        __syncthreads();
+    }
+    const int b = blockIdx.x * kMmaWarps + warp;
+    double* scratch = smem + (size_t)warp * mma::kWarpScratch;
+    if (MODE == 2) {
+        if (b >= p.B || (p.skip && p.skip[b])) return;
+        if (mma::select_fused_pipe_body<D, M>(p, b, scratch, cst)) return;
+        select_fused_seq_cold<D, M>(p, b, scratch, cst);
+    } else {
+        mma::select_fused_body<D, M, MODE>(p, b, scratch, cst);
+    }
 }
 
 template <int D, int M>
@@ -105,7 +125,7 @@ static int mma_min_blocks() {
 }
 template <int D, int M, int MODE, int MINB>
 static int launch_fused_mma_b(const FusedArgs& p, cudaStream_t st) {
-    const size_t smem = sizeof(double) * ((size_t)kMmaWarps * mma::kWarpScratch + mma::FastConst<D, M>::SIZE);
+    const size_t smem = sizeof(double) * ((size_t)kMmaWarps * mma::kWarpScratch + mma::PipeConst<D, M>::SIZE);
     const int grid = (p.B + kMmaWarps - 1) / kMmaWarps;
     k_select_fused_mma<D, M, MODE, MINB><<<grid, kMmaWarps * 32, smem, st>>>(p);
     return check_launch("k_select_fused_mma");
@@ -132,7 +152,11 @@ int dispatch_select_generic(int d, int m, const SelectArgs& p, cudaStream_t st) 
 int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st) {
     if (n == 2 && m == 1) return launch_fused<3, 1, 4>(p, st);
     if (n == 4 && m == 1) return launch_fused<5, 1, 8>(p, st);
-    if (n == 12 && m == 4) return p.mode == HOP_MODE_FAST ? launch_fused_mma<13, 4, 1>(p, st) : launch_fused_mma<13, 4, 0>(p, st);
+    if (n == 12 && m == 4) {
+        if (p.mode != HOP_MODE_FAST) return launch_fused_mma<13, 4, 0>(p, st);
+        static const bool seq = getenv("HOP_FAST_SEQ") && atoi(getenv("HOP_FAST_SEQ")) != 0;   // A/B switch: old schedule
+        return seq ? launch_fused_mma<13, 4, 1>(p, st) : launch_fused_mma<13, 4, 2>(p, st);
+    }
     set_last_error("hop_select_fused_f64: (n, m) not instantiated; supported: (2,1) (4,1) (12,4)");
     return HOP_E_UNSUPPORTED_DIMS;
 }

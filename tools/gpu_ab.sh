@@ -1,0 +1,16 @@
+#!/bin/bash
+# A/B of the selection-kernel variants on one B200 (run under gpurun).  Output: gpurun_out/ab_*.log
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+for v in "pipe3:HOP_MMA_MINBLOCKS=3" "pipe2:HOP_MMA_MINBLOCKS=2" "pipe4:HOP_MMA_MINBLOCKS=4" "seq3:HOP_FAST_SEQ=1"; do
+  name=${v%%:*}; envs=${v#*:}
+  env $envs timeout 300 python bench.py --steps 3 --warmup 3 > gpurun_out/ab_$name.log 2> gpurun_out/ab_$name.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/ab_$name.log").read().strip().splitlines()[-1])
+    print("$name", "value %.0f"%d["value"], "ms %.2f"%d["ms_per_step"], "e2e %.0f"%d["e2e"]["value"], "frac %.3f"%d["roofline"]["frac"], d["cpu_baseline"]["parity_on_sample"], d["clocks"])
+except Exception as e:
+    print("$name failed", e)
+PY
+done
