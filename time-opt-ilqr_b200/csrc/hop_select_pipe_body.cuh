@@ -18,6 +18,9 @@
 //   * e = wrap(X_{k+1} - xg) serves both Q_aug[k+1] and QT_{k+1} (it is the same vector);
 //   * the matvecs Q e | P e and K q | K' p run on the two half-warps concurrently;
 //   * K, K' are kept in fragment order in shared memory (conflict-free loads);
+//   * the vector stage of step k+2 (e, Q e, P e, K q, K' p, Schur complements) is spread over the pivot
+//     sweep of iteration k, and X / U are read straight from global two iterations ahead;
+//   * pivot row / column fix-ups are folded into the rank-1 update; positivity is tested on the integer pipe;
 //   * X0 is only formed on its lower tiles and its forward elimination reads the pivot row from the
 //     pivot column (X0 is symmetric by construction).
 // Any non-positive pivot / sigma (or non-finite input) aborts the pipelined sweep for that problem and the
@@ -41,8 +44,9 @@ struct PipeConst {
 // per-warp shared memory (doubles)
 struct PipeSlab {
     static constexpr int LU = 0;                  // 512: scratch of the sequential fallback body (its own layout, 576 + stages)
-    static constexpr int EV = 0, QE = 16, PE = 32, YQ = 48, YP = 64, DU = 80;   // vectors of the pipelined sweep
-    static constexpr int STAGE = 96;              // 2 x kStage staging buffers
+    // vectors of the pipelined sweep; YQ, YP (2 x 16) and DU (2 x 8) are double-buffered by step parity
+    static constexpr int EV = 0, QE = 16, PE = 32, YQ = 48, YP = 80, DU = 112;
+    static constexpr int STAGE = 128;             // 2 x kStage staging buffers
     static constexpr int BARS = STAGE + 2 * kStage;
     static constexpr int SIZE = BARS + 2;
 };
@@ -67,14 +71,54 @@ HOP_DEVICE void pipe_const_fill(double* cst, int tid, int nthr) {
     }
 }
 
-// One pivot of the in-place Gauss-Jordan inversion (same arithmetic as gj_attempt).
+// ---- small helpers --------------------------------------------------------------------------------
+// "pivot is not a positive normal number" on the integer pipe (the FP64 pipe is the bottleneck):
+// true for p <= 0, NaN, +inf and p < 2^-1042.  Any hit sends the problem to the sequential body.
+HOP_DEVICE bool pivot_bad(double p) {
+#if defined(__CUDA_ARCH__)
+    const int hi = __double2hiint(p);
+#else
+    long long bits;
+    static_assert(sizeof(bits) == sizeof(p), "");
+    __builtin_memcpy(&bits, &p, 8);
+    const int hi = (int)(bits >> 32);
+#endif
+    return (unsigned)(hi - 1) >= 0x7fefffffu;
+}
+
+// 1/p: MUFU.RCP64H seed r0 (rel. error e <= 2^-23) and r0 (1 + e + e^2): three dependent DFMAs, error ~ e^3.
+HOP_DEVICE double pivot_rcp3(double p) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    const double e = fma(-p, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+#else
+    return 1.0 / p;
+#endif
+}
+
+// utils.py:127-128 with a branch-free exact fast path: for s = a + pi in [-2pi, 4pi) the floored modulo is
+// s, s + 2pi or s - 2pi (the subtraction is exact by Sterbenz), which is what fmod + sign fix-up returns.
+HOP_DEVICE double wrap_pi_fast(double a) {
+    const double pi = 3.141592653589793, two_pi = 6.283185307179586;
+    const double s = a + pi;
+    if (s >= 0.0 && s < two_pi) return s - pi;
+    if (s >= two_pi && s < 2.0 * two_pi) return (s - two_pi) - pi;
+    return wrap_pi(a);
+}
+
+// One pivot of the in-place Gauss-Jordan inversion.  Same values as gj_attempt; the pivot row / column
+// fix-ups are folded into the rank-1 update by zeroing the target and patching f / pr:
+//   row j:  0 - (-1/p) M[j][c] = M[j][c]/p;   column j:  0 - f_i * 1 = -M[i][j]/p;   (j,j):  0 - (-1/p) * 1 = 1/p
 template <int D>
-HOP_DEVICE void gj_pivot(Mat& a, int j, const LaneGeo& L, bool& ok) {
+HOP_DEVICE void gj_pivot(Mat& a, int j, const LaneGeo& L, bool& bad) {
     const int Ij = j >> 3, gj = rho_inv(j & 7);
     const int Jj = j >> 3, tj = j & 3, sj = (j & 7) >> 2;
     const double p = simt::shfl(a.v[Ij][Jj][sj], (gj << 2) | tj, 32);
-    ok = ok && (p > 0.0);
-    const double rinv = pivot_rcp(p);
+    bad = bad || pivot_bad(p);
+    const double rinv = pivot_rcp3(p);
     double pr[2][2], f[2];
 #pragma unroll
     for (int J = 0; J < 2; ++J)
@@ -82,31 +126,32 @@ HOP_DEVICE void gj_pivot(Mat& a, int j, const LaneGeo& L, bool& ok) {
         for (int s = 0; s < 2; ++s) pr[J][s] = simt::shfl(a.v[Ij][J][s], (gj << 2) | L.t, 32);
 #pragma unroll
     for (int I = 0; I < 2; ++I) f[I] = simt::shfl(a.v[I][Jj][sj], (L.g << 2) | tj, 32) * rinv;
-    HOP_FOR_ELEMS(I, J, s) a.v[I][J][s] = fma(-f[I], pr[J][s], a.v[I][J][s]);
     const bool isrow = (L.g == gj), iscol = (L.t == tj);
+    if (iscol) {
+        a.v[0][Jj][sj] = 0.0;
+        a.v[1][Jj][sj] = 0.0;
+        pr[Jj][sj] = 1.0;
+    }
     if (isrow) {
 #pragma unroll
         for (int J = 0; J < 2; ++J)
 #pragma unroll
-            for (int s = 0; s < 2; ++s) a.v[Ij][J][s] = pr[J][s] * rinv;
+            for (int s = 0; s < 2; ++s) a.v[Ij][J][s] = 0.0;
+        f[Ij] = -rinv;
     }
-    if (iscol) {
-        a.v[0][Jj][sj] = -f[0];
-        a.v[1][Jj][sj] = -f[1];
-        if (isrow) a.v[Ij][Jj][sj] = rinv;
-    }
+    HOP_FOR_ELEMS(I, J, s) a.v[I][J][s] = fma(-f[I], pr[J][s], a.v[I][J][s]);
 }
 
 // One pivot of the forward elimination of a SYMMETRIC matrix held on its lower tiles (0,0), (1,0), (1,1)
 // (tile (0,1) is never read or written).  Row j is taken from column j.  p receives the pivot.
 template <int D>
-HOP_DEVICE void fe_pivot_lower(Mat& a, int j, const LaneGeo& L, bool& ok, double& p) {
+HOP_DEVICE void fe_pivot_lower(Mat& a, int j, const LaneGeo& L, bool& bad, double& p) {
     const int Ij = j >> 3, gj = rho_inv(j & 7);
     const int Jj = j >> 3, tj = j & 3, sj = (j & 7) >> 2;
     p = simt::shfl(a.v[Ij][Jj][sj], (gj << 2) | tj, 32);
-    ok = ok && (p > 0.0);
+    bad = bad || pivot_bad(p);
     if (j == D - 1) return;
-    const double rinv = pivot_rcp(p);
+    const double rinv = pivot_rcp3(p);
     double pr[2][2], f[2];
     // rows/cols <= j are dead: once j >= 8 only tile (1,1) is live
 #pragma unroll
@@ -127,32 +172,24 @@ HOP_DEVICE void fe_pivot_lower(Mat& a, int j, const LaneGeo& L, bool& ok, double
 }
 static_assert(rho_inv(0) == 0 && rho_inv(1) == 2 && rho_inv(4) == 1 && rho_inv(7) == 7, "rho_inv(t + 4s) == 2t + s");
 
-// a1 <- a1^-1, a2 <- a2^-1 (Gauss-Jordan), x <- forward elimination; returns the last pivot of x.
-template <int D>
-HOP_DEVICE double gj3(Mat& a1, Mat& a2, Mat& x, const LaneGeo& L, bool& ok) {
-    double p = 0.0;
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        gj_pivot<D>(a1, j, L, ok);
-        gj_pivot<D>(a2, j, L, ok);
-        fe_pivot_lower<D>(x, j, L, ok, p);
-    }
-    return p;
-}
-
 // D = X * Z^T on the lower tiles (0,0), (1,0), (1,1) only (symmetric result).
-template <int KB>
+template <int KB, bool ACC>
 HOP_DEVICE void mma_nt_lower(Mat& Dm, const Mat& X, const Mat& Z) {
 #pragma unroll
     for (int I = 0; I < 2; ++I)
 #pragma unroll
         for (int J = 0; J <= I; ++J) {
-            Dm.v[I][J][0] = 0.0; Dm.v[I][J][1] = 0.0;
+            if (!ACC) { Dm.v[I][J][0] = 0.0; Dm.v[I][J][1] = 0.0; }
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
                 simt::dmma(Dm.v[I][J][0], Dm.v[I][J][1], X.v[I][kb >> 1][kb & 1], Z.v[J][kb >> 1][kb & 1]);
         }
 }
+
+// NOTE (numerics): forming Ebar / Gbar from the lower tiles of their products and mirroring was tried and
+// rejected.  W comes out of the Gauss-Jordan sweep with an antisymmetric rounding component Omega, and
+// Fbar Omega Fbar^T (|Fbar| ~ 1e8) is exactly antisymmetric: 0.5 (M + M^T) removes it, mirroring the lower
+// tiles keeps it (error at T* 8e-8 instead of 4e-10 on the S1 goldens).  X0 only feeds pivots and is fine.
 
 // Returns true when the problem was solved by the pipelined sweep; false => caller must run the sequential body.
 template <int D, int M>
@@ -163,70 +200,63 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
     using PS = PipeSlab;
     constexpr int n = D - 1;
     constexpr int NT = (D + 7) / 8, KB = (D + 3) / 4, KBM = (M + 3) / 4, NTM = (M + 7) / 8;
-    static_assert(D > 8 && D <= 16 && n <= 16, "one-problem-per-warp mapping: 9 <= d <= 16");
+    static_assert(D > 8 && D <= 16 && n <= 16 && M <= 4, "one-problem-per-warp mapping: 9 <= d <= 16, m <= 4");
     if (cst[XC::FLAG] != 0.0) return false;      // K / K' needed the ladder: closed forms do not apply
     LaneGeo L;
     L.init();
-    double* EV = scratch + PS::EV;   // e = wrap(X_{k+1} - xg)
+    double* EV = scratch + PS::EV;   // e = wrap(X_s - xg)
     double* QE = scratch + PS::QE;   // Q e
     double* PE = scratch + PS::PE;   // P e
-    double* YQ = scratch + PS::YQ;   // [K q ; -1 ; 0]
-    double* YP = scratch + PS::YP;   // [K' p ; -1 ; 0]
-    double* DU = scratch + PS::DU;   // U - u_ref
-    bool ok = true;
+    bool bad = false;
 
     // R_inv = chol_inv(sym(R)) (augmented.py:23); its transpose is the Z operand of B R^-1
     Mat RinvT;
     {
-        Mat Rs, Ri;
+        Mat Rs;
         HOP_FOR_ELEMS(I, J, s) {
             const int R = L.row(I), C = L.col(J, s);
             Rs.v[I][J][s] = ((R < M && C < M) ? cst[FC::RS + R * M + C] : 0.0) + ((R == C && R < M) ? p.jitter : 0.0);
         }
-        ok = gj_attempt<M>(Rs, L) && ok;
-        mat_copy(Ri, Rs);
-        mat_transpose(RinvT, Ri, L);
+        bad = !gj_attempt<M>(Rs, L);
+        mat_transpose(RinvT, Rs, L);
     }
     // half-warp roles for the vector work: h = 0 -> Q side (Q e, K q), h = 1 -> terminal side (P e, K' p)
     const int h = L.lane >> 4, li = L.lane & 15;
     const bool isx = li < n;
     const double xg_l = isx ? p.xg[(size_t)b * n + li] : 0.0;
     const bool wrap_l = isx && ((p.wrap_mask >> li) & 1u);
+    const double uref_l = (L.lane < M) ? cst[FC::UREF + L.lane] : 0.0;
     const double w = p.w[b];
-    const double* mat1 = cst + (h ? FC::PF : PC::QRAWT);   // symmetric P | Q^T : element [i][j] at [j*n + i]
-    const double* mat2 = cst + (h ? XC::KP : XC::KQ);      // symmetric K' | K
+    const double* mat1 = cst + (h ? FC::PF : PC::QRAWT) + li;   // symmetric P | Q^T : element [i][j] at [j*n + i]
+    const double* mat2 = cst + (h ? XC::KP : XC::KQ) + li;      // symmetric K' | K
+    const double* matc = cst + FC::QRAW + li;                   // column i of Q
     double* V1 = h ? PE : QE;
-    double* V2 = h ? YP : YQ;
+    // extended vectors [y ; -1 ; 0], control deviations: double-buffered by the parity of the step index
     if (L.lane < 16) {
-        YQ[L.lane] = (L.lane == n) ? -1.0 : 0.0;
-        YP[L.lane] = (L.lane == n) ? -1.0 : 0.0;
+        const double v = (L.lane == n) ? -1.0 : 0.0;
+        scratch[PS::YQ + L.lane] = v; scratch[PS::YQ + 16 + L.lane] = v;
+        scratch[PS::YP + L.lane] = v; scratch[PS::YP + 16 + L.lane] = v;
     }
     const double* KF1 = cst + PC::KQF + L.lane;
     const double* KF2 = cst + PC::KPF + L.lane;
 
     const size_t baseN = (size_t)b * p.N;
-    const size_t baseX = (size_t)b * (p.N + 1);
-    static_assert(n * n + n * M + n + M + n <= kStage, "staging buffer too small");
-    static_assert((n * n) % 2 == 0 && (n * M) % 2 == 0 && M % 2 == 0 && n % 2 == 0, "bulk copies need 16-byte multiples");
+    const double* Xb = p.X + (size_t)b * (p.N + 1) * n;
+    const double* Ub = p.U + (size_t)b * p.u_stride;
+    static_assert(n * n + n * M + n <= kStage, "staging buffer too small");
+    static_assert((n * n) % 2 == 0 && (n * M) % 2 == 0 && n % 2 == 0, "bulk copies need 16-byte multiples");
     double* stage0 = scratch + PS::STAGE;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(scratch + PS::BARS);
-    constexpr int oA = 0, oB = n * n, oX = oB + n * M, oU = oX + n, oR = oU + M;
-    // stage s < T_max: A_s, B_s, X_s, U_s, a_s;  stage T_max: X only
+    constexpr int oA = 0, oB = n * n, oR = oB + n * M;
+    // stage s (< T_max): A_s, B_s, a_s through TMA bulk copies; X and U are read straight from global
     auto issue = [&](int s) {
         double* st = stage0 + (s & 1) * kStage;
         unsigned long long* bar = bars + (s & 1);
-        if (s < p.T_max) {
-            const unsigned bytes = 8u * (n * n + n * M + n + M + (p.a_resid ? n : 0));
-            simt::mbar_expect_tx(bar, bytes);
-            simt::bulk_g2s(st + oA, p.A + (baseN + s) * n * n, 8u * n * n, bar);
-            simt::bulk_g2s(st + oB, p.Bm + (baseN + s) * n * M, 8u * n * M, bar);
-            simt::bulk_g2s(st + oX, p.X + (baseX + s) * n, 8u * n, bar);
-            simt::bulk_g2s(st + oU, p.U + (size_t)b * p.u_stride + (size_t)s * M, 8u * M, bar);
-            if (p.a_resid) simt::bulk_g2s(st + oR, p.a_resid + (baseN + s) * n, 8u * n, bar);
-        } else {
-            simt::mbar_expect_tx(bar, 8u * n);
-            simt::bulk_g2s(st + oX, p.X + (baseX + s) * n, 8u * n, bar);
-        }
+        const unsigned bytes = 8u * (n * n + n * M + (p.a_resid ? n : 0));
+        simt::mbar_expect_tx(bar, bytes);
+        simt::bulk_g2s(st + oA, p.A + (baseN + s) * n * n, 8u * n * n, bar);
+        simt::bulk_g2s(st + oB, p.Bm + (baseN + s) * n * M, 8u * n * M, bar);
+        if (p.a_resid) simt::bulk_g2s(st + oR, p.a_resid + (baseN + s) * n, 8u * n, bar);
     };
     if (L.lane == 0) {
         simt::mbar_init(bars, 1);
@@ -234,9 +264,8 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
         simt::mbar_fence_init();
     }
     simt::sync();
-    if (L.lane == 0) { issue(0); issue(1); }
+    if (L.lane == 0) { issue(0); if (1 < p.T_max) issue(1); }
     simt::sync();   // (host emulation: copies complete at issue time, so order the issue before the first read)
-
     // leave no bulk copy in flight and no live mbarrier behind (the fallback body re-uses the slab)
     auto bail = [&](int pending_stage) {
         if (pending_stage >= 0) simt::mbar_wait(bars + (pending_stage & 1), (unsigned)((pending_stage >> 1) & 1));
@@ -245,53 +274,61 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
         simt::sync();
         return false;
     };
-    // Vector stage for index s (inputs in `stg`): e, Q e, P e, y = K q, y' = K' p, sigma, sigma'.
-    // On return YQ/YP hold the extended vectors, DU the control deviation (s < T_max only).
-    double rsq = 0.0, rsp = 0.0;
-    auto vector_stage = [&](const double* stg, bool with_u) {
+    auto load_x = [&](int s) { return (isx && s <= p.T_max) ? Xb[(size_t)s * n + li] : 0.0; };
+    auto load_u = [&](int s) { return (L.lane < M && s < p.T_max) ? Ub[(size_t)s * M + L.lane] : 0.0; };
+
+    // ---- vector stage of step index s, in four phases (A: e, du; B: Q e | P e, e^T Q e; C: K q | K' p and the
+    // two dot products; D: Schur complements and their reciprocals).  In the main loop the phases of step k+2
+    // are spread over the Gauss-Jordan sweep of iteration k so that their latency hides behind the pivots.
+    struct Vec { double ev, v1, corner, qy, ye, rsq, rsp; };
+    auto vecA = [&](Vec& V, int s, double xs, double us) {
         double ev = 0.0;
         if (isx) {
-            ev = stg[oX + li] - xg_l;                                           // e = wrap(X_s - xg)  (augmented.py:28,80)
-            if (wrap_l) ev = wrap_pi(ev);
+            ev = xs - xg_l;                                                     // e = wrap(X_s - xg)  (augmented.py:28,80)
+            if (wrap_l) ev = wrap_pi_fast(ev);
             if (h == 0) EV[li] = ev;
         }
-        if (with_u && L.lane < M) DU[L.lane] = stg[oU + L.lane] - cst[FC::UREF + L.lane];
+        V.ev = ev;
+        if (L.lane < M) scratch[PS::DU + (s & 1) * 8 + L.lane] = us - uref_l;   // du = U_s - u_ref   (augmented.py:29)
+    };
+    auto vecB = [&](Vec& V) {
         simt::sync();
         double v1 = 0.0, qc = 0.0;
         if (isx) {
 #pragma unroll
             for (int j = 0; j < n; ++j) {
                 const double ej = EV[j];
-                v1 = fma(mat1[j * n + li], ej, v1);                             // (Q e)_i | (P e)_i
-                if (h == 0) qc = fma(ej, cst[FC::QRAW + j * n + li], qc);       // (e^T Q)_i
+                v1 = fma(mat1[j * n], ej, v1);                                  // (Q e)_i | (P e)_i
+                qc = fma(ej, matc[j * n], qc);                                  // (e^T Q)_i
             }
             V1[li] = v1;
         }
-        double r0 = (isx && h == 0) ? qc * ev : 0.0;                            // e^T Q e   (augmented.py:37)
+        V.v1 = v1;
+        double r0 = (isx && h == 0) ? qc * V.ev : 0.0;                          // e^T Q e   (augmented.py:37)
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) r0 += simt::shfl_xor(r0, o, 32);
-        const double eQe = simt::shfl(r0, 0, 32);
-        const double corner = eQe + 2.0 * w + p.rho_reg;
+        V.corner = simt::shfl(r0, 0, 32) + 2.0 * w + p.rho_reg;
+    };
+    auto vecC = [&](Vec& V, int s) {
         simt::sync();
         double y = 0.0;
         if (isx) {
 #pragma unroll
-            for (int j = 0; j < n; ++j) y = fma(mat2[j * n + li], V1[j], y);    // y = K q | y' = K' p
-            V2[li] = y;
+            for (int j = 0; j < n; ++j) y = fma(mat2[j * n], V1[j], y);         // y = K q | y' = K' p
+            scratch[(h ? PS::YP : PS::YQ) + (s & 1) * 16 + li] = y;
         }
-        double r1 = isx ? (h ? y * ev : v1 * y) : 0.0;                          // q^T y | y'^T e
+        double r1 = isx ? (h ? y * V.ev : V.v1 * y) : 0.0;                      // q^T y | y'^T e
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) r1 += simt::shfl_xor(r1, o, 32);
-        const double qy = simt::shfl(r1, 0, 32), ye = simt::shfl(r1, 16, 32);
-        const double sigq = (corner + p.jitter) - qy;                           // Schur complement of Q_aug + eps I
-        const double sigp = (p.rho_reg + p.jitter) + p.jitter * ye;             // ... of QT + eps I, cancellation-free
-        ok = ok && (sigq > 0.0) && (sigp > 0.0);
-#ifdef HOP_DEBUG_PIPE
-        if (L.lane==0) printf("pipe eQe=%.17g corner=%.17g qy=%.17g ye=%.17g sigq=%.17g sigp=%.17g\n", eQe, corner, qy, ye, sigq, sigp);
-#endif
-        rsq = 1.0 / sigq;
-        rsp = 1.0 / sigp;
-        simt::sync();
+        V.qy = simt::shfl(r1, 0, 32);
+        V.ye = simt::shfl(r1, 16, 32);
+    };
+    auto vecD = [&](Vec& V, bool live) {
+        const double sigq = (V.corner + p.jitter) - V.qy;                       // Schur complement of Q_aug + eps I
+        const double sigp = (p.rho_reg + p.jitter) + p.jitter * V.ye;           // ... of QT + eps I, cancellation-free
+        bad = bad || (live && (pivot_bad(sigq) || pivot_bad(sigp)));
+        V.rsq = pivot_rcp(sigq);
+        V.rsp = pivot_rcp(sigp);
     };
     // closed-form block inverse  Kx + rs * yx yx^T  (yx = [y ; -1 ; 0])
     auto closed_inverse = [&](Mat& E, const double* KF, const double* Y, double rs) {
@@ -304,7 +341,7 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
             for (int s = 0; s < 2; ++s) yc[J][s] = Y[L.col(J, s)];
         HOP_FOR_ELEMS(I, J, s) E.v[I][J][s] = fma(yr[I] * yc[J][s], rs, KF[((I * 2 + J) * 2 + s) * 32]);
     };
-    auto load_AB = [&](const double* stg, Mat& A, Mat& Bm) {
+    auto load_AB = [&](const double* stg, const double* DU, Mat& A, Mat& Bm) {
         const double* Ak = stg + oA;
         const double* Bk = stg + oB;
         HOP_FOR_ELEMS(I, J, s) {
@@ -324,23 +361,26 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
             Bm.v[I][J][s] = (R < n && C < M) ? Bk[R * M + C] : 0.0;
         }
     };
-    auto stage_G = [&](Mat& Ft, Mat& G, const Mat& A, const Mat& Bm, const Mat& E) {
-        mma_nt<NT, NT, KB, false>(Ft, A, E);                                   // F_k^T = A_k E_k
-        mma_nt<NT, NT, KB, false>(G, Ft, A);                                   // (A_k E_k) A_k^T              (:61)
-        Mat BR;
-        mma_nt<NT, NTM, KBM, false>(BR, Bm, RinvT);                            // B_k R^-1
-        mma_nt<NT, NT, KBM, true>(G, BR, Bm);                                  // + (B_k R^-1) B_k^T
-    };
 
-    // ---------------- prologue: prefix step 0 (horizon_selection.py:57-64 with k = 0)
+    // ---------------- prologue: vector stages 0 and 1, prefix step 0 (horizon_selection.py:57-64 with k = 0)
+    Vec V0, V1s;
+    vecA(V0, 0, load_x(0), load_u(0)); vecB(V0); vecC(V0, 0); vecD(V0, true);
+    simt::sync();
+    vecA(V1s, 1, load_x(1), load_u(1)); vecB(V1s); vecC(V1s, 1); vecD(V1s, true);
+    simt::sync();
+    double rsq = V1s.rsq, rsp = V1s.rsp;       // reciprocal Schur complements of step k+1 (current iteration)
+    double xcur = load_x(2), ucur = load_u(2);  // inputs of the vector stage that runs inside iteration k: step k+2
     PrefixL<D> P;
     simt::mbar_wait(bars + 0, 0u);
-    vector_stage(stage0, true);
     {
         Mat E, A, Bm, Ft, G;
-        closed_inverse(E, KF1, YQ, rsq);
-        load_AB(stage0, A, Bm);
-        stage_G(Ft, G, A, Bm, E);
+        closed_inverse(E, KF1, scratch + PS::YQ, V0.rsq);
+        load_AB(stage0, scratch + PS::DU, A, Bm);
+        mma_nt<NT, NT, KB, false>(Ft, A, E);                                   // F_0^T = A_0 E_0
+        mma_nt<NT, NT, KB, false>(G, Ft, A);                                   // (A_0 E_0) A_0^T              (:61)
+        Mat BR;
+        mma_nt<NT, NTM, KBM, false>(BR, Bm, RinvT);                            // B_0 R^-1
+        mma_nt<NT, NT, KBM, true>(G, BR, Bm);                                  // + (B_0 R^-1) B_0^T
         mat_sym(G, L);
         mma_nt<NT, NT, KB, false>(P.fb, E, A);                                 // F_0 = E_0 A_0^T              (:60)
         mat_copy(P.eb, E);
@@ -353,26 +393,36 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
 
     for (int k = 0; k < p.T_max; ++k) {
         const bool last = (k + 1 == p.T_max);
-        simt::sync();                                                           // everyone is done with stage k
-        if (L.lane == 0 && k + 2 <= p.T_max) issue(k + 2);
-        simt::mbar_wait(bars + ((k + 1) & 1), (unsigned)(((k + 1) >> 1) & 1));
-        const double* stg = stage0 + ((k + 1) & 1) * kStage;
-        vector_stage(stg, !last);
-        if (!simt::all(ok)) return bail(k + 2 <= p.T_max ? k + 2 : -1);
+        const int q1 = (k + 1) & 1;                                             // buffers of step k+1
+        const bool do_vec = (k + 2 <= p.T_max);
+        simt::sync();                                                           // everyone is done with stage k and vectors k
+        if (L.lane == 0 && k + 2 < p.T_max) issue(k + 2);
+        const double xnext = load_x(k + 3), unext = load_u(k + 3);              // consumed one iteration from now
         // ---------------- the three independent inversions
         Mat W, Wt;
         {
-            closed_inverse(W, KF1, YQ, rsq);                                   // E_{k+1} = chol_inv(Q_aug[k+1])   (:59)
-            closed_inverse(Wt, KF2, YP, rsp);                                  // X_t = chol_inv(QT_t), t = k+1     (:79)
+            closed_inverse(W, KF1, scratch + PS::YQ + q1 * 16, rsq);            // E_{k+1} = chol_inv(Q_aug[k+1])   (:59)
+            closed_inverse(Wt, KF2, scratch + PS::YP + q1 * 16, rsp);           // X_t = chol_inv(QT_t), t = k+1     (:79)
             HOP_FOR_ELEMS(I, J, s) {
                 const double dg = (I == J && L.row(I) == L.col(J, s) && L.row(I) < D) ? p.jitter : 0.0;
                 W.v[I][J][s] = (W.v[I][J][s] + P.gb.v[I][J][s]) + dg;          // E_{k+1} + Gbar_k (+ eps I)        (:72)
                 Wt.v[I][J][s] = (Wt.v[I][J][s] + P.gb.v[I][J][s]) + dg;        // X_t + Gbar_k (+ eps I)            (:82)
-                if (I >= J) X0.v[I][J][s] += dg;                               // X0_{t-1} + eps I                  (:84)
+                if (I == J) X0.v[I][J][s] += dg;                               // X0_{t-1} + eps I                  (:84)
             }
         }
-        const double piv = gj3<D>(W, Wt, X0, L, ok);
-        if (!simt::all(ok)) return bail(k + 2 <= p.T_max ? k + 2 : -1);
+        Vec V;                                                                  // (past the horizon the inputs are zeros: harmless)
+        double piv = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            if (j == 0) vecA(V, k + 2, xcur, ucur);
+            if (j == 3) vecB(V);
+            if (j == 6) vecC(V, k + 2);
+            if (j == 9) vecD(V, do_vec);
+            gj_pivot<D>(W, j, L, bad);
+            gj_pivot<D>(Wt, j, L, bad);
+            fe_pivot_lower<D>(X0, j, L, bad, piv);
+        }
+        if (simt::ballot(bad) != 0u) return bail(k + 2 < p.T_max ? k + 2 : -1);
         if (k > 0 && L.lane == 0) {                                            // J(t-1) = 0.5 / pivot_n  (z0 = e_n, :85)
             const double Jt = 0.5 / piv;
             p.J_out[(size_t)b * p.T_max + (k - 1)] = Jt;
@@ -382,7 +432,7 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
         {
             Mat T3, acc;
             mma_nt<NT, NT, KB, false>(T3, P.fb, Wt);
-            mma_nt_lower<KB>(acc, T3, P.fb);
+            mma_nt_lower<KB, false>(acc, T3, P.fb);
 #pragma unroll
             for (int I = 0; I < 2; ++I)
 #pragma unroll
@@ -392,11 +442,18 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
         }
         if (last) break;
         // ---------------- prefix step k+1 (:57-75)
+        simt::mbar_wait(bars + q1, (unsigned)(((k + 1) >> 1) & 1));
         {
             Mat E, A, Bm, Ft, G;
-            closed_inverse(E, KF1, YQ, rsq);
-            load_AB(stg, A, Bm);
-            stage_G(Ft, G, A, Bm, E);
+            closed_inverse(E, KF1, scratch + PS::YQ + q1 * 16, rsq);
+            load_AB(stage0 + q1 * kStage, scratch + PS::DU + q1 * 8, A, Bm);
+            mma_nt<NT, NT, KB, false>(Ft, A, E);                               // F_k^T = A_k E_k
+            mma_nt<NT, NT, KB, false>(G, Ft, A);                               // (A_k E_k) A_k^T              (:61)
+            {
+                Mat BR;
+                mma_nt<NT, NTM, KBM, false>(BR, Bm, RinvT);                    // B_k R^-1
+                mma_nt<NT, NT, KBM, true>(G, BR, Bm);                          // + (B_k R^-1) B_k^T
+            }
             Mat T1, acc;
             mma_nt<NT, NT, KB, false>(T1, P.fb, W);                            // Fbar W                       (:73)
             mma_nt<NT, NT, KB, false>(acc, T1, P.fb);                          // (Fbar W) Fbar^T
@@ -405,19 +462,21 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
             mma_nt<NT, NT, KB, false>(acc, T1, Ft);                            // (Fbar W) F_k  -> new Fbar    (:74)
             mma_nt<NT, NT, KB, false>(T1, Ft, W);                              // F_k^T W                      (:75)
             mat_copy(P.fb, acc);
-            mma_nt<NT, NT, KB, false>(acc, T1, Ft);                            // (F_k^T W) F_k
+            mma_nt<NT, NT, KB, false>(acc, T1, Ft);
             mat_sub(P.gb, G, acc);
             mat_sym(P.gb, L);                                                  // Gbar                         (:75)
         }
+        rsq = V.rsq; rsp = V.rsp;
+        xcur = xnext; ucur = unext;
     }
     // ---------------- epilogue: cost of the last horizon
     {
         HOP_FOR_ELEMS(I, J, s)
-            if (I >= J && I == J && L.row(I) == L.col(J, s) && L.row(I) < D) X0.v[I][J][s] += p.jitter;
+            if (I == J && L.row(I) == L.col(J, s) && L.row(I) < D) X0.v[I][J][s] += p.jitter;
         double piv = 0.0;
 #pragma unroll
-        for (int j = 0; j < D; ++j) fe_pivot_lower<D>(X0, j, L, ok, piv);
-        if (!simt::all(ok)) return bail(-1);
+        for (int j = 0; j < D; ++j) fe_pivot_lower<D>(X0, j, L, bad, piv);
+        if (simt::ballot(bad) != 0u) return bail(-1);
         if (L.lane == 0) {
             const double Jt = 0.5 / piv;
             p.J_out[(size_t)b * p.T_max + (p.T_max - 1)] = Jt;

@@ -1,9 +1,11 @@
 #!/bin/bash
 # A/B of the selection-kernel variants on one B200 (run under gpurun).  Output: gpurun_out/ab_*.log
+# usage: gpu_ab.sh [--notest] name:ENV=VAL[,ENV=VAL] ...
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
-for v in "pipe3:HOP_MMA_MINBLOCKS=3" "pipe2:HOP_MMA_MINBLOCKS=2" "pipe4:HOP_MMA_MINBLOCKS=4" "seq3:HOP_FAST_SEQ=1"; do
-  name=${v%%:*}; envs=${v#*:}
+if [ "$1" == "--notest" ]; then shift; else
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log; fi
+for v in "$@"; do
+  name=${v%%:*}; envs=$(echo ${v#*:} | tr ',' ' ')
   env $envs timeout 300 python bench.py --steps 3 --warmup 3 > gpurun_out/ab_$name.log 2> gpurun_out/ab_$name.err
   python - <<PY
 import json
