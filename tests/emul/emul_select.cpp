@@ -72,10 +72,10 @@ void mma_fused_lane(void* a) {
     auto* j = (MmaFusedJob<D, M>*)a;
     hop::mma::select_fused_body<D, M, MODE>(*j->p, j->b, j->scratch, j->cst);
 }
-template <int D, int M>
-void mma_pipe_lane(void* a) {   // mirrors k_select_fused_mma<.., MODE = 2>
+template <int D, int M, bool LOOPED>
+void mma_pipe_lane(void* a) {   // mirrors k_select_fused_mma<.., MODE = 2 | 3>
     auto* j = (MmaFusedJob<D, M>*)a;
-    if (hop::mma::select_fused_pipe_body<D, M>(*j->p, j->b, j->scratch, j->cst)) return;
+    if (hop::mma::select_fused_pipe_body<D, M, LOOPED>(*j->p, j->b, j->scratch, j->cst)) return;
     hop::mma::select_fused_body<D, M, 1>(*j->p, j->b, j->scratch, j->cst);
 }
 template <int D, int M>
@@ -92,10 +92,11 @@ int run_fused_mma(const hop::FusedArgs& p) {
         MmaFusedJob<D, M> j{&p, 0, scratch.data(), cst.data()};
         if (hop::simt::run_warp(mma_fast_const_lane<D, M>, &j)) return -1;
     }
-    if (p.mode == 2) hop::mma::pipe_const_fill<D, M>(cst.data(), 0, 1);
+    if (p.mode >= 2) hop::mma::pipe_const_fill<D, M>(cst.data(), 0, 1);
     for (int b = 0; b < p.B; ++b) {
         MmaFusedJob<D, M> j{&p, b, scratch.data(), cst.data()};
-        auto fn = p.mode == 2 ? mma_pipe_lane<D, M> : (p.mode == 1 ? mma_fused_lane<D, M, 1> : mma_fused_lane<D, M, 0>);
+        auto fn = p.mode == 3 ? mma_pipe_lane<D, M, true> : p.mode == 2 ? mma_pipe_lane<D, M, false>
+                                : (p.mode == 1 ? mma_fused_lane<D, M, 1> : mma_fused_lane<D, M, 0>);
         if (hop::simt::run_warp(fn, &j)) return -1;
     }
     return 0;

@@ -124,6 +124,25 @@ def test_rollout_and_linearize_match_oracle(name):
         assert np.abs(Bm.cpu().numpy()[0] - g[kb]).max() <= 2e-9 * max(1.0, np.abs(g[kb]).max())
 
 
+def test_pipeline_linearisation_with_f0_from_rollout_is_bit_identical():
+    """hop_select_from_x0 lets the quadrotor FD kernel read f0 = F(X_k, U_k) from X[k+1] (consistent rollout) and share
+    the unperturbed sin/cos between lanes; the result must equal the stand-alone linearisation (which evaluates f0)
+    bit for bit, NaN tails included (Euler-singularity instance: F returns NaN from step 1 on)."""
+    case = cases.make_case("Quadrotor", N=128)
+    F, u_ref, N = case[0], case[3], case[8]
+    B = 48
+    x0s = s1_x0(B)
+    x0s[1, 7] = np.pi / 2
+    x0s[2, 7] = 1.2                                         # large pitch: trajectory leaves the small-angle regime
+    sel = api.HorizonSelector(case, B, mode=api.MODE_FAST)
+    sel(_t(x0s))
+    X, A, Bm = sel.views()
+    A2, B2 = api.linearize_batched(F, X, _t(np.tile(u_ref, (N, 1))))
+    assert np.isnan(X[1, 1:].cpu().numpy()).all() and np.isnan(A[1, 1:].cpu().numpy()).all()
+    assert np.array_equal(A.cpu().numpy(), A2.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(Bm.cpu().numpy(), B2.cpu().numpy(), equal_nan=True)
+
+
 def test_rollout_divergence_guard_nan_fills_like_the_reference():
     F = cases.make_case("Quadrotor", N=128)[0]
     x0 = np.zeros((2, 12)); x0[1, 7] = np.pi / 2          # Euler singularity -> F returns NaN (systems.py:179-181)

@@ -13,8 +13,8 @@ int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st);
 int dispatch_rollout(int B, int sys, const double* params_host, int N, const double* x0, const double* U, long ustride,
                      double max_norm, double* X, cudaStream_t st);
 int dispatch_linearize(int B, int sys, const double* params_host, int N, const double* X, const double* U, long ustride,
-                       int central, double epsx, double epsu, double relx, double relu, const int* skip, double* A,
-                       double* Bm, cudaStream_t st);
+                       int central, double epsx, double epsu, double relx, double relu, int f0_from_x, const int* skip,
+                       double* A, double* Bm, cudaStream_t st);
 struct DdpConst {
     const double *xg, *w, *u_ref, *Q, *R, *Qf;
     unsigned wrap_mask;
@@ -136,7 +136,7 @@ int hop_linearize_f64(int B, int sys, const double* params_host, int N, const do
     if (B < 0 || N < 1 || !params_host) { set_last_error("hop_linearize_f64: bad argument"); return HOP_E_BADARG; }
     if (int rc = need_device()) return rc;
     if (B == 0) return 0;
-    return dispatch_linearize(B, sys, params_host, N, X, U, u_batch_stride, central, epsx, epsu, relx, relu, nullptr, A, Bm,
+    return dispatch_linearize(B, sys, params_host, N, X, U, u_batch_stride, central, epsx, epsu, relx, relu, 0, nullptr, A, Bm,
                               (cudaStream_t)stream);
 }
 
@@ -167,8 +167,9 @@ int hop_select_from_x0_f64(int B, int sys, const double* params_host, int N, int
     double* Bm = (double*)((char*)A + align256(sizeof(double) * (size_t)B * N * n * n));
     int rc = hop_rollout_f64(B, sys, params_host, N, x0, U, u_batch_stride, 1e6, X, stream);            // solver.py:42
     if (rc) return rc;
-    rc = hop_linearize_f64(B, sys, params_host, N, X, U, u_batch_stride, central, 1e-5, 1e-5, 1e-6, 1e-6, A, Bm,
-                           stream);                                                                      // linearization.py:177,216
+    // X comes from the rollout above, so F(X_k, U_k) = X[k+1] bit for bit: the linearisation may read f0 from it
+    rc = dispatch_linearize(B, sys, params_host, N, X, U, u_batch_stride, central, 1e-5, 1e-5, 1e-6, 1e-6, 1, nullptr, A, Bm,
+                            (cudaStream_t)stream);                                                       // linearization.py:177,216
     if (rc) return rc;
     // a_resid = NULL: on a trajectory produced by the rollout above F(X_k,U_k) - X_{k+1} is exactly 0
     return hop_select_fused_f64(B, N, n, m, T_min, T_max, A, Bm, nullptr, X, U, u_batch_stride, xg, w, u_ref, Q, R, Qf,
@@ -328,7 +329,7 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T
     else HOP_TRY(launch_tile_u(B, N, m, u_ref, U, st));                                                  // solver.py:480-481
     HOP_TRY(dispatch_rollout(B, sys, params_host, N, x0, U, ustride, 1e6, X, st));                       // :492
     mark(0);
-    HOP_TRY(dispatch_linearize(B, sys, params_host, N, X, U, ustride, central, 1e-5, 1e-5, 1e-6, 1e-6, nullptr, ws.A, ws.Bm, st));
+    HOP_TRY(dispatch_linearize(B, sys, params_host, N, X, U, ustride, central, 1e-5, 1e-5, 1e-6, 1e-6, 1, nullptr, ws.A, ws.Bm, st));
     mark(1);
     HOP_TRY(select(nullptr));                                                                            // :516-522
     HOP_TRY(launch_after_select(B, ws.sel_status, ws.done, status, st));
@@ -344,7 +345,7 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T
     for (int it = 0; it < max_iter; ++it) {                                                              // :564
         ++iters;
         mark(0);
-        HOP_TRY(dispatch_linearize(B, sys, params_host, N, X, U, ustride, central, 1e-5, 1e-5, 1e-6, 1e-6, ws.done, ws.A, ws.Bm, st));
+        HOP_TRY(dispatch_linearize(B, sys, params_host, N, X, U, ustride, central, 1e-5, 1e-5, 1e-6, 1e-6, 1, ws.done, ws.A, ws.Bm, st));
         mark(1);
         HOP_TRY(select(ws.done));                                                                        // :581-590
         HOP_TRY(launch_after_select(B, ws.sel_status, ws.done, status, st));

@@ -65,12 +65,14 @@ HOP_DEVICE void dynamics<3>(const double* p, const double* x, const double* u, d
     const double n2 = wrap_pi(add(th, mul(dt, om))), n3 = add(om, mul(dt, alp));
     xn[0] = n0; xn[1] = n1; xn[2] = n2; xn[3] = n3;
 }
-// systems.py:170-210 (rotm :145-156, Tmat :158-163, guards :175-191)
-template <>
-HOP_DEVICE void dynamics<2>(const double* p, const double* x, const double* u, double* xn) {
-    const double dt = p[0], mass = p[1], g = p[2], Ix = p[3], Iy = p[4], Iz = p[5];
-    const double iIx = p[6], iIy = p[7], iIz = p[8], kv = p[9], kw = p[10];
-    const double cmin = p[11], wmax = p[12], nmax = p[13];
+// systems.py:170-210 (rotm :145-156, Tmat :158-163, guards :175-191), split so that the finite-difference
+// kernel can share the trigonometry of the unperturbed angles between the lanes of a (problem, step) group;
+// dynamics<2> below and k_linearize_quad evaluate exactly the same operation sequence.
+struct QuadTrig { double sph, cph, sth, cth, tth, sps, cps; };
+
+// the guards that do not need trigonometry (systems.py:175-183,188-191)
+HOP_DEVICE bool quad_guard(const double* p, const double* x, const double* u) {
+    const double wmax = p[12], nmax = p[13];
     bool bad = false;
     double ss = 0.0;
 #pragma unroll
@@ -78,18 +80,15 @@ HOP_DEVICE void dynamics<2>(const double* p, const double* x, const double* u, d
 #pragma unroll
     for (int i = 0; i < 4; ++i) bad = bad || !isfinite(u[i]);
     bad = bad || (sqrt(ss) > nmax);
-    const double phi = x[6], th = x[7], psi = x[8], wp = x[9], wq = x[10], wr = x[11];
-    double sth, cth, sph, cph, sps, cps;
-    sincos(th, &sth, &cth);
-    bad = bad || (fabs(cth) < cmin) || (fabs(wp) > wmax) || (fabs(wq) > wmax) || (fabs(wr) > wmax);
-    if (bad) {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) xn[i] = nan("");
-        return;
-    }
-    sincos(phi, &sph, &cph);
-    sincos(psi, &sps, &cps);
-    const double tth = tan(th), sec = 1.0 / cth, thrust = u[0];
+    return bad || (fabs(x[9]) > wmax) || (fabs(x[10]) > wmax) || (fabs(x[11]) > wmax);
+}
+
+HOP_DEVICE void quad_core(const double* p, const double* x, const double* u, const QuadTrig& T, double* xn) {
+    const double dt = p[0], mass = p[1], g = p[2], Ix = p[3], Iy = p[4], Iz = p[5];
+    const double iIx = p[6], iIy = p[7], iIz = p[8], kv = p[9], kw = p[10];
+    const double wp = x[9], wq = x[10], wr = x[11];
+    const double sph = T.sph, cph = T.cph, sth = T.sth, cth = T.cth, sps = T.sps, cps = T.cps;
+    const double tth = T.tth, sec = 1.0 / cth, thrust = u[0];
     const double r02 = add(mul(-sps, -sph), mul(mul(cps, sth), cph));
     const double r12 = add(mul(cps, -sph), mul(mul(sps, sth), cph));
     const double r22 = mul(cth, cph);
@@ -107,6 +106,23 @@ HOP_DEVICE void dynamics<2>(const double* p, const double* x, const double* u, d
     xd[11] = sub(mul(iIz, sub(u[3], sub(mul(wp, h1), mul(wq, h0)))), mul(kw, wr));
 #pragma unroll
     for (int i = 0; i < 12; ++i) xn[i] = add(x[i], mul(dt, xd[i]));
+}
+
+template <>
+HOP_DEVICE void dynamics<2>(const double* p, const double* x, const double* u, double* xn) {
+    bool bad = quad_guard(p, x, u);
+    QuadTrig T;
+    sincos(x[7], &T.sth, &T.cth);
+    bad = bad || (fabs(T.cth) < p[11]);
+    if (bad) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) xn[i] = nan("");
+        return;
+    }
+    sincos(x[6], &T.sph, &T.cph);
+    sincos(x[8], &T.sps, &T.cps);
+    T.tth = tan(x[7]);
+    quad_core(p, x, u, T, xn);
 }
 
 }  // namespace hop

@@ -47,17 +47,16 @@ HOP_DEVICE void mat_sub(Mat& d, const Mat& a, const Mat& b) { HOP_FOR_ELEMS(I, J
 // D (+)= X * Z^T.  NI/NJ: row tiles of X / Z that hold data, KB: number of 4-wide k blocks.
 template <int NI, int NJ, int KB, bool ACC>
 HOP_DEVICE void mma_nt(Mat& D, const Mat& X, const Mat& Z) {
+    if (!ACC) { HOP_FOR_ELEMS(I, J, s) D.v[I][J][s] = 0.0; }
+    // k-block outermost: consecutive DMMAs go to different accumulator tiles, so a dependent pair is NI*NJ
+    // instructions apart (tile-major order serialises on the DMMA latency: ncu r1d, `wait` 83 % in the products)
 #pragma unroll
-    for (int I = 0; I < 2; ++I)
+    for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-        for (int J = 0; J < 2; ++J) {
-            if (!ACC) { D.v[I][J][0] = 0.0; D.v[I][J][1] = 0.0; }
-            if (I < NI && J < NJ) {
+        for (int I = 0; I < NI; ++I)
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb)
-                    simt::dmma(D.v[I][J][0], D.v[I][J][1], X.v[I][kb >> 1][kb & 1], Z.v[J][kb >> 1][kb & 1]);
-            }
-        }
+            for (int J = 0; J < NJ; ++J)
+                simt::dmma(D.v[I][J][0], D.v[I][J][1], X.v[I][kb >> 1][kb & 1], Z.v[J][kb >> 1][kb & 1]);
 }
 
 // T = M^T (layout L -> layout L): 16 double shuffles.

@@ -79,7 +79,8 @@ __device__ __noinline__ void select_fused_seq_cold(const FusedArgs& p, int b, do
     mma::select_fused_body<D, M, 1>(p, b, scratch, cst);
 }
 
-// MODE 0: EXACT, 1: FAST sequential, 2: FAST software-pipelined (hop_select_pipe_body.cuh) with MODE 1 as its cold path
+// MODE 0: EXACT, 1: FAST sequential, 2: FAST software-pipelined (hop_select_pipe_body.cuh) with MODE 1 as its cold path,
+// 3: as 2 with the pivot sweep as run-time loops over groups of four pivots (a quarter of the code)
 template <int D, int M, int MODE, int MINB>
 __global__ void __launch_bounds__(kMmaWarps * 32, MINB) k_select_fused_mma(const FusedArgs p) {
     extern __shared__ __align__(16) double smem[];
@@ -91,15 +92,15 @@ __global__ void __launch_bounds__(kMmaWarps * 32, MINB) k_select_fused_mma(const
         if (warp == 0) mma::fast_const_fill_warp<D, M>(p, cst, smem);
         __syncthreads();
     }
-    if (MODE == 2) {
+    if (MODE >= 2) {
         mma::pipe_const_fill<D, M>(cst, threadIdx.x, blockDim.x);
         __syncthreads();
     }
     const int b = blockIdx.x * kMmaWarps + warp;
     double* scratch = smem + (size_t)warp * mma::kWarpScratch;
-    if (MODE == 2) {
+    if (MODE >= 2) {
         if (b >= p.B || (p.skip && p.skip[b])) return;
-        if (mma::select_fused_pipe_body<D, M>(p, b, scratch, cst)) return;
+        if (mma::select_fused_pipe_body<D, M, MODE == 3>(p, b, scratch, cst)) return;
         select_fused_seq_cold<D, M>(p, b, scratch, cst);
     } else {
         mma::select_fused_body<D, M, MODE>(p, b, scratch, cst);
@@ -155,7 +156,9 @@ int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st) {
     if (n == 12 && m == 4) {
         if (p.mode != HOP_MODE_FAST) return launch_fused_mma<13, 4, 0>(p, st);
         static const bool seq = getenv("HOP_FAST_SEQ") && atoi(getenv("HOP_FAST_SEQ")) != 0;   // A/B switch: old schedule
-        return seq ? launch_fused_mma<13, 4, 1>(p, st) : launch_fused_mma<13, 4, 2>(p, st);
+        static const bool unrolled = getenv("HOP_PIPE_UNROLL") && atoi(getenv("HOP_PIPE_UNROLL")) != 0;   // A/B switch
+        if (seq) return launch_fused_mma<13, 4, 1>(p, st);
+        return unrolled ? launch_fused_mma<13, 4, 2>(p, st) : launch_fused_mma<13, 4, 3>(p, st);
     }
     set_last_error("hop_select_fused_f64: (n, m) not instantiated; supported: (2,1) (4,1) (12,4)");
     return HOP_E_UNSUPPORTED_DIMS;

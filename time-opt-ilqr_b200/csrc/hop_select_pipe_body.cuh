@@ -112,56 +112,56 @@ HOP_DEVICE double wrap_pi_fast(double a) {
 // One pivot of the in-place Gauss-Jordan inversion.  Same values as gj_attempt; the pivot row / column
 // fix-ups are folded into the rank-1 update by zeroing the target and patching f / pr:
 //   row j:  0 - (-1/p) M[j][c] = M[j][c]/p;   column j:  0 - f_i * 1 = -M[i][j]/p;   (j,j):  0 - (-1/p) * 1 = 1/p
-template <int D>
-HOP_DEVICE void gj_pivot(Mat& a, int j, const LaneGeo& L, bool& bad) {
-    const int Ij = j >> 3, gj = rho_inv(j & 7);
-    const int Jj = j >> 3, tj = j & 3, sj = (j & 7) >> 2;
-    const double p = simt::shfl(a.v[Ij][Jj][sj], (gj << 2) | tj, 32);
+// The pivot index is j = 8 GI + 4 GS + tj: (GI, GS) select REGISTERS and must be compile-time, tj only enters
+// lane numbers and predicates and may be a run-time loop variable (looped variant, smaller code).
+template <int D, int GI, int GS>
+HOP_DEVICE void gj_pivot(Mat& a, int tj, const LaneGeo& L, bool& bad) {
+    const int gj = 2 * tj + GS;                                  // rho_inv(4 GS + tj)
+    const double p = simt::shfl(a.v[GI][GI][GS], (gj << 2) | tj, 32);
     bad = bad || pivot_bad(p);
     const double rinv = pivot_rcp3(p);
     double pr[2][2], f[2];
 #pragma unroll
     for (int J = 0; J < 2; ++J)
 #pragma unroll
-        for (int s = 0; s < 2; ++s) pr[J][s] = simt::shfl(a.v[Ij][J][s], (gj << 2) | L.t, 32);
+        for (int s = 0; s < 2; ++s) pr[J][s] = simt::shfl(a.v[GI][J][s], (gj << 2) | L.t, 32);
 #pragma unroll
-    for (int I = 0; I < 2; ++I) f[I] = simt::shfl(a.v[I][Jj][sj], (L.g << 2) | tj, 32) * rinv;
+    for (int I = 0; I < 2; ++I) f[I] = simt::shfl(a.v[I][GI][GS], (L.g << 2) | tj, 32) * rinv;
     const bool isrow = (L.g == gj), iscol = (L.t == tj);
     if (iscol) {
-        a.v[0][Jj][sj] = 0.0;
-        a.v[1][Jj][sj] = 0.0;
-        pr[Jj][sj] = 1.0;
+        a.v[0][GI][GS] = 0.0;
+        a.v[1][GI][GS] = 0.0;
+        pr[GI][GS] = 1.0;
     }
     if (isrow) {
 #pragma unroll
         for (int J = 0; J < 2; ++J)
 #pragma unroll
-            for (int s = 0; s < 2; ++s) a.v[Ij][J][s] = 0.0;
-        f[Ij] = -rinv;
+            for (int s = 0; s < 2; ++s) a.v[GI][J][s] = 0.0;
+        f[GI] = -rinv;
     }
     HOP_FOR_ELEMS(I, J, s) a.v[I][J][s] = fma(-f[I], pr[J][s], a.v[I][J][s]);
 }
 
 // One pivot of the forward elimination of a SYMMETRIC matrix held on its lower tiles (0,0), (1,0), (1,1)
 // (tile (0,1) is never read or written).  Row j is taken from column j.  p receives the pivot.
-template <int D>
-HOP_DEVICE void fe_pivot_lower(Mat& a, int j, const LaneGeo& L, bool& bad, double& p) {
-    const int Ij = j >> 3, gj = rho_inv(j & 7);
-    const int Jj = j >> 3, tj = j & 3, sj = (j & 7) >> 2;
-    p = simt::shfl(a.v[Ij][Jj][sj], (gj << 2) | tj, 32);
+template <int D, int GI, int GS>
+HOP_DEVICE void fe_pivot_lower(Mat& a, int tj, const LaneGeo& L, bool& bad, double& p) {
+    const int gj = 2 * tj + GS;
+    p = simt::shfl(a.v[GI][GI][GS], (gj << 2) | tj, 32);
     bad = bad || pivot_bad(p);
-    if (j == D - 1) return;
+    if (8 * GI + 4 * GS + tj == D - 1) return;
     const double rinv = pivot_rcp3(p);
     double pr[2][2], f[2];
     // rows/cols <= j are dead: once j >= 8 only tile (1,1) is live
 #pragma unroll
-    for (int J = (j >= 8 ? 1 : 0); J < 2; ++J)
+    for (int J = GI; J < 2; ++J)
 #pragma unroll
-        for (int s = 0; s < 2; ++s)   // M[j][8J+t+4s] = M[8J+t+4s][j]: tile (J, Jj), lane (rho_inv(t+4s), tj)
-            pr[J][s] = simt::shfl(a.v[J][Jj][sj], ((2 * L.t + s) << 2) | tj, 32);
+        for (int s = 0; s < 2; ++s)   // M[j][8J+t+4s] = M[8J+t+4s][j]: tile (J, GI), lane (rho_inv(t+4s), tj)
+            pr[J][s] = simt::shfl(a.v[J][GI][GS], ((2 * L.t + s) << 2) | tj, 32);
 #pragma unroll
-    for (int I = (j >= 8 ? 1 : 0); I < 2; ++I) f[I] = simt::shfl(a.v[I][Jj][sj], (L.g << 2) | tj, 32) * rinv;
-    if (j < 8) {
+    for (int I = GI; I < 2; ++I) f[I] = simt::shfl(a.v[I][GI][GS], (L.g << 2) | tj, 32) * rinv;
+    if (GI == 0) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) a.v[0][0][s] = fma(-f[0], pr[0][s], a.v[0][0][s]);
 #pragma unroll
@@ -170,20 +170,49 @@ HOP_DEVICE void fe_pivot_lower(Mat& a, int j, const LaneGeo& L, bool& bad, doubl
 #pragma unroll
     for (int s = 0; s < 2; ++s) a.v[1][1][s] = fma(-f[1], pr[1][s], a.v[1][1][s]);
 }
+// the three interleaved sweeps over the pivots of group (GI, GS); UNROLL = false keeps tj a run-time loop
+template <int D, int GI, int GS, bool UNROLL>
+HOP_DEVICE void gj3_group(Mat& a1, Mat& a2, Mat& x, const LaneGeo& L, bool& bad, double& p) {
+    constexpr int first = 8 * GI + 4 * GS;
+    constexpr int cnt = (D - first) < 4 ? (D - first) : 4;
+#ifdef HOP_EXP_NOGJ     // timing experiment only (wrong results): what do the products cost without the pivot sweeps?
+    HOP_FOR_ELEMS(I, J, s) asm volatile("" : "+d"(a1.v[I][J][s]), "+d"(a2.v[I][J][s]), "+d"(x.v[I][J][s]));
+    p = x.v[1][1][1] + 1.0; return;
+#endif
+    if (UNROLL) {
+#pragma unroll
+        for (int tj = 0; tj < cnt; ++tj) {
+            gj_pivot<D, GI, GS>(a1, tj, L, bad);
+            gj_pivot<D, GI, GS>(a2, tj, L, bad);
+            fe_pivot_lower<D, GI, GS>(x, tj, L, bad, p);
+        }
+    } else {
+#pragma unroll 1
+        for (int tj = 0; tj < cnt; ++tj) {
+            gj_pivot<D, GI, GS>(a1, tj, L, bad);
+            gj_pivot<D, GI, GS>(a2, tj, L, bad);
+            fe_pivot_lower<D, GI, GS>(x, tj, L, bad, p);
+        }
+    }
+}
 static_assert(rho_inv(0) == 0 && rho_inv(1) == 2 && rho_inv(4) == 1 && rho_inv(7) == 7, "rho_inv(t + 4s) == 2t + s");
 
 // D = X * Z^T on the lower tiles (0,0), (1,0), (1,1) only (symmetric result).
 template <int KB, bool ACC>
 HOP_DEVICE void mma_nt_lower(Mat& Dm, const Mat& X, const Mat& Z) {
+    if (!ACC) {
 #pragma unroll
-    for (int I = 0; I < 2; ++I)
+        for (int I = 0; I < 2; ++I)
 #pragma unroll
-        for (int J = 0; J <= I; ++J) {
-            if (!ACC) { Dm.v[I][J][0] = 0.0; Dm.v[I][J][1] = 0.0; }
+            for (int J = 0; J <= I; ++J) { Dm.v[I][J][0] = 0.0; Dm.v[I][J][1] = 0.0; }
+    }
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb)
+    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+        for (int I = 0; I < 2; ++I)
+#pragma unroll
+            for (int J = 0; J <= I; ++J)
                 simt::dmma(Dm.v[I][J][0], Dm.v[I][J][1], X.v[I][kb >> 1][kb & 1], Z.v[J][kb >> 1][kb & 1]);
-        }
 }
 
 // NOTE (numerics): forming Ebar / Gbar from the lower tiles of their products and mirroring was tried and
@@ -192,7 +221,7 @@ HOP_DEVICE void mma_nt_lower(Mat& Dm, const Mat& X, const Mat& Z) {
 // tiles keeps it (error at T* 8e-8 instead of 4e-10 on the S1 goldens).  X0 only feeds pivots and is fine.
 
 // Returns true when the problem was solved by the pipelined sweep; false => caller must run the sequential body.
-template <int D, int M>
+template <int D, int M, bool LOOPED>
 HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratch, const double* cst) {
     using FC = FusedConst<D, M>;
     using XC = FastConst<D, M>;
@@ -412,16 +441,15 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
         }
         Vec V;                                                                  // (past the horizon the inputs are zeros: harmless)
         double piv = 0.0;
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            if (j == 0) vecA(V, k + 2, xcur, ucur);
-            if (j == 3) vecB(V);
-            if (j == 6) vecC(V, k + 2);
-            if (j == 9) vecD(V, do_vec);
-            gj_pivot<D>(W, j, L, bad);
-            gj_pivot<D>(Wt, j, L, bad);
-            fe_pivot_lower<D>(X0, j, L, bad, piv);
-        }
+        static_assert(D > 12, "the phase placement below assumes four pivot groups");
+        vecA(V, k + 2, xcur, ucur);
+        gj3_group<D, 0, 0, !LOOPED>(W, Wt, X0, L, bad, piv);
+        vecB(V);
+        gj3_group<D, 0, 1, !LOOPED>(W, Wt, X0, L, bad, piv);
+        vecC(V, k + 2);
+        gj3_group<D, 1, 0, !LOOPED>(W, Wt, X0, L, bad, piv);
+        vecD(V, do_vec);
+        gj3_group<D, 1, 1, !LOOPED>(W, Wt, X0, L, bad, piv);
         if (simt::ballot(bad) != 0u) return bail(k + 2 < p.T_max ? k + 2 : -1);
         if (k > 0 && L.lane == 0) {                                            // J(t-1) = 0.5 / pivot_n  (z0 = e_n, :85)
             const double Jt = 0.5 / piv;
@@ -474,8 +502,12 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
         HOP_FOR_ELEMS(I, J, s)
             if (I == J && L.row(I) == L.col(J, s) && L.row(I) < D) X0.v[I][J][s] += p.jitter;
         double piv = 0.0;
-#pragma unroll
-        for (int j = 0; j < D; ++j) fe_pivot_lower<D>(X0, j, L, bad, piv);
+        Mat d1, d2;                                                            // dummies: the sweep is shared with the main loop
+        HOP_FOR_ELEMS(I, J, s) d1.v[I][J][s] = d2.v[I][J][s] = (L.row(I) == L.col(J, s)) ? 1.0 : 0.0;
+        gj3_group<D, 0, 0, false>(d1, d2, X0, L, bad, piv);
+        gj3_group<D, 0, 1, false>(d1, d2, X0, L, bad, piv);
+        gj3_group<D, 1, 0, false>(d1, d2, X0, L, bad, piv);
+        gj3_group<D, 1, 1, false>(d1, d2, X0, L, bad, piv);
         if (simt::ballot(bad) != 0u) return bail(-1);
         if (L.lane == 0) {
             const double Jt = 0.5 / piv;

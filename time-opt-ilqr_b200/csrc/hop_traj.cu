@@ -110,6 +110,99 @@ __global__ void k_linearize(int B, DynParams prm, int N, const double* __restric
     }
 }
 
+// Quadrotor forward-difference linearisation (linearization.py:216-262), 16 lanes per (problem, step): lane c
+// perturbs coordinate c of (x, u).  Compared with the generic kernel above:
+//   * every lane evaluates ONE sincos (+ tan for the pitch lanes): lanes 0..2 the unperturbed roll / pitch / yaw,
+//     lanes 6..8 their perturbed angle; the unperturbed values reach the other lanes by shuffles (only an angle
+//     perturbation changes the trigonometry) -- same function values, so A and B are unchanged bit for bit;
+//   * f0 = F(X_k, U_k) is read from X[k+1] when the caller guarantees a consistent rollout (f0_from_x: the
+//     rollout / line-search kernels produced X with this very dynamics function), recomputed otherwise;
+//   * the 12 quotients (fp - f0) / h share one reciprocal: q0 = d * r, q = q0 + fma(-q0, h, d) * r, which is the
+//     correctly rounded quotient for r = RN(1/h) (Markstein), i.e. what the division returns.
+__global__ void __launch_bounds__(128) k_linearize_quad(int B, DynParams prm, int N, const double* __restrict__ X,
+                                                        const double* __restrict__ U, long ustride, double epsx, double epsu,
+                                                        double relx, double relu, int f0_from_x, const int* __restrict__ skip,
+                                                        double* __restrict__ A, double* __restrict__ Bm) {
+    constexpr int n = 12, m = 4, P = 16;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)B * N * P;
+    const bool live = gid < total;
+    const size_t bk = live ? gid / P : 0;         // dead lanes shadow group 0 so that the shuffles stay converged
+    const int c = (int)(threadIdx.x & (P - 1));
+    const int k = (int)(bk % N);
+    const size_t b = bk / N;
+    const bool skipped = skip && skip[b];
+    double x[n], u[m];
+    const double* xs = X + (b * (N + 1) + k) * n;
+    const double* us = U + b * ustride + (size_t)k * m;
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = xs[i];
+#pragma unroll
+    for (int i = 0; i < m; ++i) u[i] = us[i];
+    // f0
+    double f0[n];
+    bool have_f0 = false;
+    if (f0_from_x) {
+        bool fin = true, finx = true;
+#pragma unroll
+        for (int i = 0; i < n; ++i) { f0[i] = xs[n + i]; fin = fin && isfinite(f0[i]); finx = finx && isfinite(x[i]); }
+        // X[k+1] non-finite although X[k] is finite: either F is non-finite there or the rollout cut the trajectory
+        // on its norm test (solver.py:57-59) -- only F itself can tell, so recompute
+        have_f0 = fin || !finx;
+    }
+    if (!have_f0) dynamics<2>(prm.p, x, u, f0);
+    bool nanout = false;
+#pragma unroll
+    for (int i = 0; i < n; ++i) nanout = nanout || !isfinite(f0[i]);      // linearization.py:243-248
+    // h = max(eps, rel * max(1, |v|))  (linearization.py:253,257)
+    double h = 0.0, base = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) if (i == c) { base = x[i]; h = fmax(epsx, mul(relx, fmax(1.0, fabs(x[i])))); }
+#pragma unroll
+    for (int i = 0; i < m; ++i) if (i + n == c) { base = u[i]; h = fmax(epsu, mul(relu, fmax(1.0, fabs(u[i])))); }
+    const double vp = add(base, h);
+    // one angle per lane: lanes 6..8 their perturbed angle, everyone else the unperturbed angle (c mod 3)
+    const int role = (c >= 6 && c <= 8) ? c - 6 : c % 3;
+    const double ang = (c >= 6 && c <= 8) ? vp : (role == 0 ? x[6] : role == 1 ? x[7] : x[8]);
+    double sa, ca, ta = 0.0;
+    sincos(ang, &sa, &ca);
+    if (role == 1) ta = tan(ang);
+    QuadTrig T;
+    T.sph = __shfl_sync(0xffffffffu, sa, 0, P); T.cph = __shfl_sync(0xffffffffu, ca, 0, P);
+    T.sth = __shfl_sync(0xffffffffu, sa, 1, P); T.cth = __shfl_sync(0xffffffffu, ca, 1, P);
+    T.tth = __shfl_sync(0xffffffffu, ta, 1, P);
+    T.sps = __shfl_sync(0xffffffffu, sa, 2, P); T.cps = __shfl_sync(0xffffffffu, ca, 2, P);
+    if (c == 6) { T.sph = sa; T.cph = ca; }
+    if (c == 7) { T.sth = sa; T.cth = ca; T.tth = ta; }
+    if (c == 8) { T.sps = sa; T.cps = ca; }
+    if (!live || skipped) return;
+#pragma unroll
+    for (int i = 0; i < n; ++i) if (i == c) x[i] = vp;
+#pragma unroll
+    for (int i = 0; i < m; ++i) if (i + n == c) u[i] = vp;
+    double fp[n];
+    const bool bad = quad_guard(prm.p, x, u) || (fabs(T.cth) < prm.p[11]);
+    quad_core(prm.p, x, u, T, fp);
+    const double rh = 1.0 / h;
+    double col[n];
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        const double d = sub(fp[i], f0[i]);
+        const double q0 = mul(d, rh);
+        const double q = fma(fma(-q0, h, d), rh, q0);
+        col[i] = (nanout || bad) ? nan("") : q;
+    }
+    if (c < n) {
+        double* Ak = A + bk * n * n;
+#pragma unroll
+        for (int i = 0; i < n; ++i) Ak[i * n + c] = col[i];
+    } else {
+        double* Bk = Bm + bk * n * m;
+#pragma unroll
+        for (int i = 0; i < n; ++i) Bk[i * m + (c - n)] = col[i];
+    }
+}
+
 template <int SYS>
 static int launch_rollout(int B, const DynParams& prm, int N, const double* x0, const double* U, long ustride,
                           double max_norm, double* X, cudaStream_t st) {
@@ -119,12 +212,16 @@ static int launch_rollout(int B, const DynParams& prm, int N, const double* x0, 
 }
 template <int SYS>
 static int launch_linearize(int B, const DynParams& prm, int N, const double* X, const double* U, long ustride,
-                            int central, double epsx, double epsu, double relx, double relu, const int* skip, double* A,
-                            double* Bm, cudaStream_t st) {
+                            int central, double epsx, double epsu, double relx, double relu, int f0_from_x, const int* skip,
+                            double* A, double* Bm, cudaStream_t st) {
     constexpr int P = SysDims<SYS>::n + SysDims<SYS>::m;
     const size_t total = (size_t)B * N * P;
     const int threads = 128;
     const size_t grid = (total + threads - 1) / threads;
+    if (SYS == 2 && !central) {
+        k_linearize_quad<<<(unsigned)grid, threads, 0, st>>>(B, prm, N, X, U, ustride, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm);
+        return check_launch("k_linearize_quad");
+    }
     k_linearize<SYS><<<(unsigned)grid, threads, 0, st>>>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, skip, A, Bm);
     return check_launch("k_linearize");
 }
@@ -144,15 +241,15 @@ int dispatch_rollout(int B, int sys, const double* params_host, int N, const dou
 }
 
 int dispatch_linearize(int B, int sys, const double* params_host, int N, const double* X, const double* U, long ustride,
-                       int central, double epsx, double epsu, double relx, double relu, const int* skip, double* A,
-                       double* Bm, cudaStream_t st) {
+                       int central, double epsx, double epsu, double relx, double relu, int f0_from_x, const int* skip,
+                       double* A, double* Bm, cudaStream_t st) {
     DynParams prm;
     for (int i = 0; i < HOP_NPARAMS; ++i) prm.p[i] = params_host[i];
     switch (sys) {
-        case 0: return launch_linearize<0>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, skip, A, Bm, st);
-        case 1: return launch_linearize<1>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, skip, A, Bm, st);
-        case 2: return launch_linearize<2>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, skip, A, Bm, st);
-        case 3: return launch_linearize<3>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, skip, A, Bm, st);
+        case 0: return launch_linearize<0>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm, st);
+        case 1: return launch_linearize<1>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm, st);
+        case 2: return launch_linearize<2>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm, st);
+        case 3: return launch_linearize<3>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm, st);
     }
     set_last_error("hop_linearize_f64: unknown system id");
     return HOP_E_BADARG;

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhop_b200.so")
+LIB_PATH = os.environ.get("HOP_LIB") or os.path.join(_HERE, "libhop_b200.so")   # HOP_LIB: experiment builds only
 
 _vp, _d, _i, _l, _u, _ull = C.c_void_p, C.c_double, C.c_int, C.c_long, C.c_uint, C.c_ulonglong
 
