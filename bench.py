@@ -248,10 +248,17 @@ def run_hop(args):
     except OSError:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None                                      # dram bytes per launch of the same kernel from the committed ncu capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tr.get("batch") == B and tr.get("mode") == args.mode:
+            traffic = tr["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
     ach_tf = flop_launch / (ms_launch * 1e-3) / 1e12
     ach_gb = byte_launch / (ms_launch * 1e-3) / 1e9
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": ach_tf / tf.value,
-                "traffic": None, "kernel": "k_select_fused_mma<13,4,%d>" % mode,
+                "traffic": traffic, "kernel": "k_select_fused_mma<13,4,%s>" % ("pipelined" if mode else "exact"),
                 "peak_source": "DFMA microbenchmark in this run (hop_probe_fp64_tflops); nominal 37.2 TFLOP/s",
                 "algorithmic_flop_per_solve": f_alg(N_HORIZON, D_AUG, M_CTRL),
                 "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
@@ -266,18 +273,33 @@ def run_hop(args):
     rate = 4 * cores / dtc
     sample = int(max(cores, min(B, round(rate * 12.0 / cores) * cores)))
     dtc, Jc, Tc, stc = cpu_from_x0(case, x0_np[:sample], cores)
-    mism = int(np.count_nonzero(Tc != T_h[:sample]))
+    mism_idx = np.nonzero(Tc != T_h[:sample])[0]
+    mism = int(mism_idx.size)
     relJ = float(np.max(np.abs(J_h[:sample, T_min - 1:] - Jc[:, T_min - 1:]) / np.abs(Jc[:, T_min - 1:])))
+    # every T* mismatch is re-examined with the selection sweep in x87 extended precision ("truth" of the same
+    # jittered algorithm): a near-tie whose winner is decided by fp64 rounding is ill-posed for ANY implementation,
+    # the reference included (SURVEY.md s.9 argmin-gap census)
+    detail = []
+    Uc = np.tile(u_ref, (N, 1))
+    for bb in mism_idx[:8]:
+        Xc = O.rollout(F.hop_sys, F.hop_params, x0_np[bb], Uc)
+        Ac, Bc = O.linearize(F.hop_sys, F.hop_params, Xc, Uc)
+        J80, T80 = O.select_fused(Ac, Bc, Xc, Uc, xg, u_ref, Q, R, alpha, w, T_min, T_max, wrap_idx, f80=True)
+        tg, to = int(T_h[bb]), int(Tc[bb])
+        detail.append({"instance": int(bb), "T_gpu": tg, "T_oracle_fp64": to, "T_fp80": int(T80),
+                       "rel_gap_between_the_two_candidates": float(abs(J80[tg - 1] - J80[to - 1]) / abs(J80[to - 1])),
+                       "rel_noise_fp64_vs_fp80_at_T": float(abs(Jc[bb, to - 1] - J80[to - 1]) / abs(J80[to - 1]))})
     cpu_baseline = {"value": sample / dtc, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"first {sample} instances of rank 0's batch, x0 -> T* pipeline, oracle/hop_oracle.c on {cores} "
                               "pthreads (the Python reference itself measured ~17 solves/s/core in the build container)",
-                    "parity_on_sample": {"T_star_mismatches": mism, "max_rel_J_window": relJ}}
+                    "parity_on_sample": {"T_star_mismatches": mism, "max_rel_J_window": relJ, "mismatch_detail": detail}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": "S1 quadrotor n=12 m=4 d=13 N=128 T in [40,128] (iteration-0 HOP selection)",
-                       "batch_per_gpu": B, "global_batch": world * B, "mode": args.mode + "-sequential",
+                       "batch_per_gpu": B, "global_batch": world * B,
+                       "mode": args.mode + " (sequential in the horizon; software-pipelined pivot sweeps)",
                        "l2": "inputs (A,B,X = %.1f GB per GPU) exceed the 126 MB L2" % (byte_launch / 1e9),
                        "parallelism": f"batch-sharded x{world}, final all_gather of T*/J*" if world > 1 else "single GPU"},
             "clocks": clocks,

@@ -215,6 +215,44 @@ HOP_DEVICE void mma_nt_lower(Mat& Dm, const Mat& X, const Mat& Z) {
                 simt::dmma(Dm.v[I][J][0], Dm.v[I][J][1], X.v[I][kb >> 1][kb & 1], Z.v[J][kb >> 1][kb & 1]);
 }
 
+// ---- the k = D-1 column as a rank-1 DFMA update ----------------------------------------------------------
+// For d = 13 the fourth k-block of every product holds ONE non-zero column (k = 12): four DMMAs (64 pipe clocks)
+// that do the work of a rank-1 update.  The products of the pipelined body therefore run three k-blocks on the
+// tensor pipe and add  x_12 z_12^T  with DFMAs (8 per product, 16 pipe clocks); the two vectors come from the
+// operands' fragments by shuffles (or from shared memory where the column is known in closed form).
+template <int D>
+struct LastCol {
+    static constexpr int k = D - 1, Jk = k >> 3, sk = (k & 7) >> 2, tk = k & 3;   // register [.][Jk][sk], lanes t == tk
+    static constexpr bool split = (D % 4) == 1;                                    // exactly one column in the last k-block
+};
+// M[row(I)][D-1] for the two row tiles of this lane (the X-operand role)
+template <int D>
+HOP_DEVICE void last_col_rows(double (&r)[2], const Mat& M, const LaneGeo& L) {
+    using LC = LastCol<D>;
+#pragma unroll
+    for (int I = 0; I < 2; ++I) r[I] = simt::shfl(M.v[I][LC::Jk][LC::sk], (L.g << 2) | LC::tk, 32);
+}
+// M[col(J,s)][D-1] for the four column slots of this lane (the Z-operand role)
+template <int D>
+HOP_DEVICE void last_col_cols(double (&c)[2][2], const Mat& M, const LaneGeo& L) {
+    using LC = LastCol<D>;
+#pragma unroll
+    for (int J = 0; J < 2; ++J)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) c[J][s] = simt::shfl(M.v[J][LC::Jk][LC::sk], ((2 * L.t + s) << 2) | LC::tk, 32);
+}
+template <bool LOWER>
+HOP_DEVICE void rank1_add(Mat& Dm, const double (&r)[2], const double (&c)[2][2]) {
+#pragma unroll
+    for (int I = 0; I < 2; ++I)
+#pragma unroll
+        for (int J = 0; J < 2; ++J)
+            if (!LOWER || J <= I) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) Dm.v[I][J][s] = fma(r[I], c[J][s], Dm.v[I][J][s]);
+            }
+}
+
 // NOTE (numerics): forming Ebar / Gbar from the lower tiles of their products and mirroring was tried and
 // rejected.  W comes out of the Gauss-Jordan sweep with an antisymmetric rounding component Omega, and
 // Fbar Omega Fbar^T (|Fbar| ~ 1e8) is exactly antisymmetric: 0.5 (M + M^T) removes it, mirroring the lower
@@ -229,6 +267,8 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
     using PS = PipeSlab;
     constexpr int n = D - 1;
     constexpr int NT = (D + 7) / 8, KB = (D + 3) / 4, KBM = (M + 3) / 4, NTM = (M + 7) / 8;
+    constexpr bool R1 = LastCol<D>::split;          // last k-block as a rank-1 DFMA update
+    constexpr int KD = R1 ? KB - 1 : KB;            // k-blocks left on the tensor pipe
     static_assert(D > 8 && D <= 16 && n <= 16 && M <= 4, "one-problem-per-warp mapping: 9 <= d <= 16, m <= 4");
     if (cst[XC::FLAG] != 0.0) return false;      // K / K' needed the ladder: closed forms do not apply
     LaneGeo L;
@@ -457,10 +497,14 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
             if (k >= p.T_min) am.push(Jt, k);
         }
         // ---------------- query products of horizon t = k+1 (:83): X0 = Ebar - (Fbar W_t) Fbar^T, lower tiles
+        double fb_r[2], fb_c[2][2];                                            // column d-1 of Fbar in both operand roles
+        if (R1) { last_col_rows<D>(fb_r, P.fb, L); last_col_cols<D>(fb_c, P.fb, L); }
         {
             Mat T3, acc;
-            mma_nt<NT, NT, KB, false>(T3, P.fb, Wt);
-            mma_nt_lower<KB, false>(acc, T3, P.fb);
+            mma_nt<NT, NT, KD, false>(T3, P.fb, Wt);
+            if (R1) { double c[2][2]; last_col_cols<D>(c, Wt, L); rank1_add<false>(T3, fb_r, c); }
+            mma_nt_lower<KD, false>(acc, T3, P.fb);
+            if (R1) { double r[2]; last_col_rows<D>(r, T3, L); rank1_add<true>(acc, r, fb_c); }
 #pragma unroll
             for (int I = 0; I < 2; ++I)
 #pragma unroll
@@ -475,22 +519,40 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
             Mat E, A, Bm, Ft, G;
             closed_inverse(E, KF1, scratch + PS::YQ + q1 * 16, rsq);
             load_AB(stage0 + q1 * kStage, scratch + PS::DU + q1 * 8, A, Bm);
-            mma_nt<NT, NT, KB, false>(Ft, A, E);                               // F_k^T = A_k E_k
-            mma_nt<NT, NT, KB, false>(G, Ft, A);                               // (A_k E_k) A_k^T              (:61)
+            double ft_r[2], ft_c[2][2], w_c[2][2];
+            mma_nt<NT, NT, KD, false>(Ft, A, E);                               // F_k^T = A_k E_k
+            if (R1) {
+                double r[2], c[2][2];
+                last_col_rows<D>(r, A, L); last_col_cols<D>(c, E, L);
+                rank1_add<false>(Ft, r, c);
+            }
+            mma_nt<NT, NT, KD, false>(G, Ft, A);                               // (A_k E_k) A_k^T              (:61)
+            if (R1) {
+                double c[2][2];
+                last_col_rows<D>(ft_r, Ft, L); last_col_cols<D>(ft_c, Ft, L); last_col_cols<D>(c, A, L);
+                rank1_add<false>(G, ft_r, c);
+            }
             {
                 Mat BR;
                 mma_nt<NT, NTM, KBM, false>(BR, Bm, RinvT);                    // B_k R^-1
                 mma_nt<NT, NT, KBM, true>(G, BR, Bm);                          // + (B_k R^-1) B_k^T
             }
             Mat T1, acc;
-            mma_nt<NT, NT, KB, false>(T1, P.fb, W);                            // Fbar W                       (:73)
-            mma_nt<NT, NT, KB, false>(acc, T1, P.fb);                          // (Fbar W) Fbar^T
+            mma_nt<NT, NT, KD, false>(T1, P.fb, W);                            // Fbar W                       (:73)
+            if (R1) { last_col_cols<D>(w_c, W, L); rank1_add<false>(T1, fb_r, w_c); }
+            double t1_r[2];
+            if (R1) last_col_rows<D>(t1_r, T1, L);
+            mma_nt<NT, NT, KD, false>(acc, T1, P.fb);                          // (Fbar W) Fbar^T
+            if (R1) rank1_add<false>(acc, t1_r, fb_c);
             mat_sub(P.eb, P.eb, acc);
             mat_sym(P.eb, L);                                                  // Ebar                         (:73)
-            mma_nt<NT, NT, KB, false>(acc, T1, Ft);                            // (Fbar W) F_k  -> new Fbar    (:74)
-            mma_nt<NT, NT, KB, false>(T1, Ft, W);                              // F_k^T W                      (:75)
+            mma_nt<NT, NT, KD, false>(acc, T1, Ft);                            // (Fbar W) F_k  -> new Fbar    (:74)
+            if (R1) rank1_add<false>(acc, t1_r, ft_c);
+            mma_nt<NT, NT, KD, false>(T1, Ft, W);                              // F_k^T W                      (:75)
+            if (R1) rank1_add<false>(T1, ft_r, w_c);
             mat_copy(P.fb, acc);
-            mma_nt<NT, NT, KB, false>(acc, T1, Ft);
+            mma_nt<NT, NT, KD, false>(acc, T1, Ft);                            // (F_k^T W) F_k
+            if (R1) { double r[2]; last_col_rows<D>(r, T1, L); rank1_add<false>(acc, r, ft_c); }
             mat_sub(P.gb, G, acc);
             mat_sym(P.gb, L);                                                  // Gbar                         (:75)
         }

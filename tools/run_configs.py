@@ -1,0 +1,236 @@
+#!/usr/bin/env python
+"""Runs the five BASELINE.json configurations on the B200 path at their stated sizes and prints one JSON line each
+(device time, throughput, parity against the CPU oracle on a bounded sample).  These are the parity / scale cases
+around the headline workload that bench.py times; nothing here feeds bench.py.
+
+  python tools/run_configs.py [--configs 1,2,3,4,5] [--small]
+  torchrun --nproc-per-node G ... tools/run_configs.py --configs 4,5     # batch sharded over G GPUs (hop.dist)
+
+The oracle (oracle/, plain-C restatement of the reference) is the checker only; it never computes a reported result.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "time-opt-ilqr_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def f_alg(N, d, m):
+    return N * (5 * d**3 + 2 * d * m * m + 2 * d * d * m) + (N - 1) * (11 * d**3 + 3 * d * d) + N * (7 * d**3 + 4 * d * d)
+
+
+def b_alg(N, d, m):
+    return 8 * (N * (3 * d * d + d * m) + m * m + d) + 8 * N + 4
+
+
+def timed(fn, reps=1):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return out, e0.elapsed_time(e1) * 1e-3 / reps
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def emit(rec):
+    rank, G = world()
+    rec["n_gpus"] = G
+    if rank == 0:
+        print(json.dumps(rec), flush=True)
+
+
+def max_over_ranks(t, dev):
+    rank, G = world()
+    if G == 1:
+        return t
+    x = torch.tensor([t], dtype=torch.float64, device=dev)
+    dist.all_reduce(x, op=dist.ReduceOp.MAX)
+    return float(x.item())
+
+
+def cfg1(args, dev):
+    """DoubleIntegrator HOP-LQR horizon selection, single trial, through the drop-in run_suite CLI."""
+    import subprocess
+    import tempfile
+    import pandas as pd
+    from _common import golden
+    rank, _ = world()
+    if rank != 0:
+        return
+    out = tempfile.mkdtemp()
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "time-opt-ilqr_b200", "dropin"), PYTHONHASHSEED="0")
+    t0 = time.perf_counter()
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "time-opt-ilqr_b200", "dropin", "run_suite.py"), "--cases",
+                           "DoubleIntegrator", "--trials", "1", "--outdir", out], env=env, stdout=subprocess.DEVNULL)
+    wall = time.perf_counter() - t0
+    df = pd.read_csv(os.path.join(out, "summary_all.csv"))
+    g = golden("case_DoubleIntegrator")
+    row = df[df["solver"] == "ourmethod"].iloc[0] if "solver" in df.columns else df.iloc[0]
+    emit({"config": 1, "what": "DoubleIntegrator, run_suite.py --cases DoubleIntegrator --trials 1 (drop-in CLI)",
+          "wall_s_incl_process_start": wall, "T_star": int(row["T_star"]), "J_star": float(row["J_star"]),
+          "reference_T_star": int(g["sol_T_hist"][-1]), "reference_J_star": float(g["sol_J_hist"][-1]),
+          "T_star_equal": int(row["T_star"]) == int(g["sol_T_hist"][-1]),
+          "rel_J_star": abs(float(row["J_star"]) - float(g["sol_J_hist"][-1])) / abs(float(g["sol_J_hist"][-1]))})
+
+
+def _ddp(name, x0s, dev, max_iter, check, label, cfg, N=None, mode=None):
+    import oracle as O
+    from _common import rel
+    from hop import api, cases, dist as hdist
+    case = cases.make_case(name, N=N) if N else cases.make_case(name)
+    F, x0, xg, u_ref, Q, R, alpha, w, Nn, T_min, T_max, wrap_idx, _ = case
+    rank, G = world()
+    lo, hi = hdist.shard_bounds(len(x0s), rank, G)
+    mine = torch.as_tensor(x0s[lo:hi], device=dev)
+    mode = api.MODE_FAST if mode is None else mode
+    run = lambda: api.ilqr_timeopt_batched(case, mine, max_iter=max_iter, use_central_diff=False, mode=mode)  # noqa: E731
+    run()                                                                       # warm-up (allocator, module load)
+    r, dt = timed(run)
+    dt = max_over_ranks(dt, dev)
+    nh = r["n_hist"].cpu().numpy(); Th = r["T_hist"].cpu().numpy(); Jh = r["J_hist"].cpu().numpy()
+    st = r["status"].cpu().numpy()
+    rec = {"config": cfg, "what": label, "instances": len(x0s), "max_iter": max_iter, "device_s": dt,
+           "solves_per_s": len(x0s) / dt, "outer_iterations_run": r["iters"], "crashed": int(((st & 0xFF) != 0).sum()),
+           "phase_seconds_rank0": r["timers"]}
+    if rank == 0 and check > 0:
+        k = min(check, hi - lo)
+        o = O.ilqr_timeopt_batch(F.hop_sys, F.hop_params, Nn, T_min, T_max, x0s[:k], np.tile(u_ref, (Nn, 1)), xg, u_ref, Q, R,
+                                 alpha, w, wrap_idx, max_iter=max_iter, use_central_diff=False, nthreads=os.cpu_count() or 1)
+        # second opinion: the same algorithm with the selection sweep in x87 extended precision.  Where the two CPU runs
+        # disagree the instance is ill-posed (its T_hist is decided by fp64 rounding: the reference itself flips there,
+        # SURVEY.md s.9), and an independent implementation cannot be asked to reproduce it.
+        o80 = O.ilqr_timeopt_batch(F.hop_sys, F.hop_params, Nn, T_min, T_max, x0s[:k], np.tile(u_ref, (Nn, 1)), xg, u_ref, Q, R,
+                                   alpha, w, wrap_idx, max_iter=max_iter, use_central_diff=False, f80_select=True,
+                                   nthreads=os.cpu_count() or 1)
+        well = [np.array_equal(o["T_hist"][b, :o["n_hist"][b]], o80["T_hist"][b, :o80["n_hist"][b]]) for b in range(k)]
+        same_T = [np.array_equal(Th[b, :nh[b]], o["T_hist"][b, :o["n_hist"][b]]) for b in range(k)]
+        relJ = [rel(Jh[b, :nh[b]], o["J_hist"][b, :nh[b]]) for b in range(k) if same_T[b]]
+        rec["parity_vs_oracle"] = {"checked": k, "well_posed": int(sum(well)),
+                                   "T_hist_identical_among_well_posed": int(sum(s_ and w_ for s_, w_ in zip(same_T, well))),
+                                   "T_hist_identical": int(sum(same_T)),
+                                   "max_rel_J_hist_where_T_identical": float(max(relJ)) if relJ else None,
+                                   "T_star_identical": int((r["T_star"].cpu().numpy()[:k] == o["T_star"][:k]).sum())}
+    emit(rec)
+
+
+def cfg2(args, dev):
+    from hop import cases
+    case = cases.make_case("Segway_Balance")
+    rng = np.random.default_rng(0)
+    x0s = case[1][None] + 0.02 * rng.standard_normal((25, 4))                   # run_suite.py:73 sigma_x0 = .02 x 4
+    x0s[0] = case[1]                                                            # trial 0 is the nominal case (run_suite.py:109-111)
+    _ddp("Segway_Balance", x0s, dev, 12, 25, "Segway_Balance HOP-DDP, 25 trials, max-iter 12, one batched device call", 2)
+
+
+def cfg3(args, dev):
+    B = 256 if args.small else 4096
+    rng = np.random.default_rng(0)                                              # the reference's cartpole sigma is 0
+    x0s = np.array([rng.normal(0, .1, B), rng.normal(0, .1, B), rng.normal(0, .2, B), rng.normal(0, .2, B)]).T
+    _ddp("Cartpole_SwingUp", x0s, dev, 12, 32, f"Cartpole swing-up HOP-DDP (augmented homogeneous state), {B} random initial "
+         "states x0 ~ N(0, diag(.1,.1,.2,.2)^2), max-iter 12; T* is ill-posed at the reference's own noise level "
+         "(argmin gap 1.3e-5 < 3e-5, SURVEY.md s.9)", 3)
+
+
+def cfg4(args, dev):
+    from _common import s1_x0
+    B = 1024 if args.small else 16384
+    _ddp("Quadrotor", s1_x0(B, seed=4), dev, 12, 32, f"Quadrotor 12-DOF HOP-DDP, N=128, {B} initial states, max-iter 12, "
+         "batch sharded over the ranks", 4, N=128)
+
+
+def cfg5(args, dev):
+    """Synthetic batched HOP-LQR sweep (LQR-boundary entry point hop_select_f64)."""
+    import oracle as O
+    from _common import rel, s2_batch
+    from hop import api, dist as hdist
+    rank, G = world()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    for d, m in ((4, 2), (12, 4), (13, 4)):
+        for N in (64, 128, 256):
+            per = b_alg(N, d, m)
+            Btot = (1 << 20) if not args.small else (1 << 14)
+            Btot = min(Btot, int(40e9 * G // per))                              # keep each rank's inputs under ~40 GB
+            lo, hi = hdist.shard_bounds(Btot, rank, G)
+            B = hi - lo
+            gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+            A = torch.eye(d, dtype=torch.float64, device=dev).expand(B, N, d, d) + \
+                0.05 / np.sqrt(d) * torch.randn((B, N, d, d), dtype=torch.float64, device=dev, generator=gen)
+            Bm = 0.05 * torch.randn((B, N, d, m), dtype=torch.float64, device=dev, generator=gen)
+            Q = torch.diag_embed(0.5 + 1.5 * torch.rand((B, N, d), dtype=torch.float64, device=dev, generator=gen))
+            QT = (50.0 * torch.eye(d, dtype=torch.float64, device=dev)).expand(B, N, d, d).contiguous()
+            Rd = 0.05 + 0.45 * torch.rand((B, m), dtype=torch.float64, device=dev, generator=gen)
+            Rinv = torch.diag_embed(1.0 / (Rd + 1e-9))                          # chol_inv of a diagonal R (utils.py:79-85)
+            z0 = torch.randn((B, d), dtype=torch.float64, device=dev, generator=gen)
+            w = 0.01 + 0.09 * torch.rand((B,), dtype=torch.float64, device=dev, generator=gen)
+            run = lambda: api.propagator_all_Jt_aug_batched(A, Bm, Q, Rinv, z0, QT, 1, N, w_explicit=w)  # noqa: E731
+            run()
+            sel, dt = timed(run, reps=2)
+            dt = max_over_ranks(dt, dev)
+            rec = {"config": 5, "what": f"synthetic HOP-LQR d={d} m={m} N={N}", "batch": Btot, "device_s": dt,
+                   "solves_per_s": Btot / dt, "algorithmic_TFLOPs": Btot * f_alg(N, d, m) / dt / 1e12,
+                   "algorithmic_GBs_per_gpu": B * per / dt / 1e9, "hbm_frac_per_gpu": B * per / dt / 1e9 / hbm,
+                   "status_nonzero": int((sel.status != 0).sum())}
+            if rank == 0:
+                k = 64
+                Jo, sto = O.propagator_batch(A[:k].cpu().numpy(), Bm[:k].cpu().numpy(), Q[:k].cpu().numpy(), Rinv[:k].cpu().numpy(),
+                                             z0[:k].cpu().numpy(), QT[:k].cpu().numpy(), nthreads=os.cpu_count() or 1)
+                tot = Jo + w[:k].cpu().numpy()[:, None] * np.arange(1, N + 1)
+                rec["parity_vs_oracle"] = {"checked": k, "max_rel_J": rel(sel.J[:k].cpu().numpy(), Jo),
+                                           "T_star_identical": int((sel.T_star[:k].cpu().numpy() == np.argmin(tot, 1) + 1).sum())}
+                # and the reference's own generator (numpy default_rng per instance) on a few instances
+                Ar, Br, Qr, Rr, zr, wr, QTr = s2_batch(range(8), d, m, N)
+                Rir = np.stack([O.chol_inv(r) for r in Rr])
+                s8 = api.propagator_all_Jt_aug_batched(*(torch.as_tensor(x, device=dev) for x in (Ar, Br, Qr, Rir, zr, QTr)), 1, N,
+                                                       w_explicit=torch.as_tensor(wr, device=dev))
+                Jo8, _ = O.propagator_batch(Ar, Br, Qr, Rir, zr, QTr)
+                rec["parity_vs_oracle"]["max_rel_J_reference_generator"] = rel(s8.J.cpu().numpy(), Jo8)
+            emit(rec)
+            del A, Bm, Q, QT, Rinv, z0, w, sel
+            torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,2,3,4,5")
+    ap.add_argument("--small", action="store_true", help="reduced sizes (smoke run)")
+    args = ap.parse_args()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import oracle as O
+    O.build()
+    fns = {1: cfg1, 2: cfg2, 3: cfg3, 4: cfg4, 5: cfg5}
+    for c in (int(x) for x in args.configs.split(",")):
+        fns[c](args, dev)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
