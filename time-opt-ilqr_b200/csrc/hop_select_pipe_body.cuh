@@ -72,19 +72,22 @@ HOP_DEVICE void pipe_const_fill(double* cst, int tid, int nthr) {
 }
 
 // ---- small helpers --------------------------------------------------------------------------------
-// "pivot is not a positive normal number" on the integer pipe (the FP64 pipe is the bottleneck):
-// true for p <= 0, NaN, +inf and p < 2^-1042.  Any hit sends the problem to the sequential body.
-HOP_DEVICE bool pivot_bad(double p) {
+// Pivot positivity on the integer pipe (the FP64 pipe is the bottleneck).  Inside the sweeps only the SIGN of
+// every pivot is accumulated (one LOP3: signs |= hi word); zero, NaN and +inf pivots turn the reciprocal into
+// NaN, which reaches the last pivot of a later X0 and is caught by the once-per-iteration test on that value.
+// Any hit sends the problem to the sequential body, which owns the jitter ladder and the status word.
+HOP_DEVICE int hi_word(double p) {
 #if defined(__CUDA_ARCH__)
-    const int hi = __double2hiint(p);
+    return __double2hiint(p);
 #else
     long long bits;
     static_assert(sizeof(bits) == sizeof(p), "");
     __builtin_memcpy(&bits, &p, 8);
-    const int hi = (int)(bits >> 32);
+    return (int)(bits >> 32);
 #endif
-    return (unsigned)(hi - 1) >= 0x7fefffffu;
 }
+// true for p <= 0, NaN, +inf and p < 2^-1042
+HOP_DEVICE bool pivot_bad(double p) { return (unsigned)(hi_word(p) - 1) >= 0x7fefffffu; }
 
 // 1/p: MUFU.RCP64H seed r0 (rel. error e <= 2^-23) and r0 (1 + e + e^2): three dependent DFMAs, error ~ e^3.
 HOP_DEVICE double pivot_rcp3(double p) {
@@ -115,10 +118,10 @@ HOP_DEVICE double wrap_pi_fast(double a) {
 // The pivot index is j = 8 GI + 4 GS + tj: (GI, GS) select REGISTERS and must be compile-time, tj only enters
 // lane numbers and predicates and may be a run-time loop variable (looped variant, smaller code).
 template <int D, int GI, int GS>
-HOP_DEVICE void gj_pivot(Mat& a, int tj, const LaneGeo& L, bool& bad) {
+HOP_DEVICE void gj_pivot(Mat& a, int tj, const LaneGeo& L, int& signs) {
     const int gj = 2 * tj + GS;                                  // rho_inv(4 GS + tj)
     const double p = simt::shfl(a.v[GI][GI][GS], (gj << 2) | tj, 32);
-    bad = bad || pivot_bad(p);
+    signs |= hi_word(p);
     const double rinv = pivot_rcp3(p);
     double pr[2][2], f[2];
 #pragma unroll
@@ -146,10 +149,10 @@ HOP_DEVICE void gj_pivot(Mat& a, int tj, const LaneGeo& L, bool& bad) {
 // One pivot of the forward elimination of a SYMMETRIC matrix held on its lower tiles (0,0), (1,0), (1,1)
 // (tile (0,1) is never read or written).  Row j is taken from column j.  p receives the pivot.
 template <int D, int GI, int GS>
-HOP_DEVICE void fe_pivot_lower(Mat& a, int tj, const LaneGeo& L, bool& bad, double& p) {
+HOP_DEVICE void fe_pivot_lower(Mat& a, int tj, const LaneGeo& L, int& signs, double& p) {
     const int gj = 2 * tj + GS;
     p = simt::shfl(a.v[GI][GI][GS], (gj << 2) | tj, 32);
-    bad = bad || pivot_bad(p);
+    signs |= hi_word(p);
     if (8 * GI + 4 * GS + tj == D - 1) return;
     const double rinv = pivot_rcp3(p);
     double pr[2][2], f[2];
@@ -172,7 +175,7 @@ HOP_DEVICE void fe_pivot_lower(Mat& a, int tj, const LaneGeo& L, bool& bad, doub
 }
 // the three interleaved sweeps over the pivots of group (GI, GS); UNROLL = false keeps tj a run-time loop
 template <int D, int GI, int GS, bool UNROLL>
-HOP_DEVICE void gj3_group(Mat& a1, Mat& a2, Mat& x, const LaneGeo& L, bool& bad, double& p) {
+HOP_DEVICE void gj3_group(Mat& a1, Mat& a2, Mat& x, const LaneGeo& L, int& signs, double& p) {
     constexpr int first = 8 * GI + 4 * GS;
     constexpr int cnt = (D - first) < 4 ? (D - first) : 4;
 #ifdef HOP_EXP_NOGJ     // timing experiment only (wrong results): what do the products cost without the pivot sweeps?
@@ -182,16 +185,16 @@ HOP_DEVICE void gj3_group(Mat& a1, Mat& a2, Mat& x, const LaneGeo& L, bool& bad,
     if (UNROLL) {
 #pragma unroll
         for (int tj = 0; tj < cnt; ++tj) {
-            gj_pivot<D, GI, GS>(a1, tj, L, bad);
-            gj_pivot<D, GI, GS>(a2, tj, L, bad);
-            fe_pivot_lower<D, GI, GS>(x, tj, L, bad, p);
+            gj_pivot<D, GI, GS>(a1, tj, L, signs);
+            gj_pivot<D, GI, GS>(a2, tj, L, signs);
+            fe_pivot_lower<D, GI, GS>(x, tj, L, signs, p);
         }
     } else {
 #pragma unroll 1
         for (int tj = 0; tj < cnt; ++tj) {
-            gj_pivot<D, GI, GS>(a1, tj, L, bad);
-            gj_pivot<D, GI, GS>(a2, tj, L, bad);
-            fe_pivot_lower<D, GI, GS>(x, tj, L, bad, p);
+            gj_pivot<D, GI, GS>(a1, tj, L, signs);
+            gj_pivot<D, GI, GS>(a2, tj, L, signs);
+            fe_pivot_lower<D, GI, GS>(x, tj, L, signs, p);
         }
     }
 }
@@ -483,13 +486,15 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
         double piv = 0.0;
         static_assert(D > 12, "the phase placement below assumes four pivot groups");
         vecA(V, k + 2, xcur, ucur);
-        gj3_group<D, 0, 0, !LOOPED>(W, Wt, X0, L, bad, piv);
+        int signs = 0;
+        gj3_group<D, 0, 0, !LOOPED>(W, Wt, X0, L, signs, piv);
         vecB(V);
-        gj3_group<D, 0, 1, !LOOPED>(W, Wt, X0, L, bad, piv);
+        gj3_group<D, 0, 1, !LOOPED>(W, Wt, X0, L, signs, piv);
         vecC(V, k + 2);
-        gj3_group<D, 1, 0, !LOOPED>(W, Wt, X0, L, bad, piv);
+        gj3_group<D, 1, 0, !LOOPED>(W, Wt, X0, L, signs, piv);
         vecD(V, do_vec);
-        gj3_group<D, 1, 1, !LOOPED>(W, Wt, X0, L, bad, piv);
+        gj3_group<D, 1, 1, !LOOPED>(W, Wt, X0, L, signs, piv);
+        bad = bad || (signs < 0) || pivot_bad(piv);                             // piv: last pivot of X0_{t-1} (or of I at k = 0)
         if (simt::ballot(bad) != 0u) return bail(k + 2 < p.T_max ? k + 2 : -1);
         if (k > 0 && L.lane == 0) {                                            // J(t-1) = 0.5 / pivot_n  (z0 = e_n, :85)
             const double Jt = 0.5 / piv;
@@ -566,10 +571,12 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
         double piv = 0.0;
         Mat d1, d2;                                                            // dummies: the sweep is shared with the main loop
         HOP_FOR_ELEMS(I, J, s) d1.v[I][J][s] = d2.v[I][J][s] = (L.row(I) == L.col(J, s)) ? 1.0 : 0.0;
-        gj3_group<D, 0, 0, false>(d1, d2, X0, L, bad, piv);
-        gj3_group<D, 0, 1, false>(d1, d2, X0, L, bad, piv);
-        gj3_group<D, 1, 0, false>(d1, d2, X0, L, bad, piv);
-        gj3_group<D, 1, 1, false>(d1, d2, X0, L, bad, piv);
+        int signs = 0;
+        gj3_group<D, 0, 0, false>(d1, d2, X0, L, signs, piv);
+        gj3_group<D, 0, 1, false>(d1, d2, X0, L, signs, piv);
+        gj3_group<D, 1, 0, false>(d1, d2, X0, L, signs, piv);
+        gj3_group<D, 1, 1, false>(d1, d2, X0, L, signs, piv);
+        bad = bad || (signs < 0) || pivot_bad(piv);
         if (simt::ballot(bad) != 0u) return bail(-1);
         if (L.lane == 0) {
             const double Jt = 0.5 / piv;
