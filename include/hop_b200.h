@@ -175,6 +175,10 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double *params_host, int N, int T
                          double *J_hist, int *T_hist, int *n_hist, double *J_curve, int *T_star, int *status,
                          int *iters_run_host, double *timers_host, void *stream);
 
+/* Test hook: selects the quadrotor forward-difference kernel (0 = thread per step [default], 1 = lane per column,
+ * 2 = the generic kernel); returns the previous value.  All three produce identical bits (tests/test_gpu_parity.py). */
+int hop_test_set_linearize_variant(int variant);
+
 /* Measures the FP64 FMA throughput of the current device with a register-resident DFMA chain
  * (8 independent accumulators per thread, 2048 threads per SM), timed with CUDA events.  This is
  * the roofline denominator bench.py reports against (MEASURED_PEAKS.json holds no FP64 figure). */

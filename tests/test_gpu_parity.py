@@ -143,6 +143,40 @@ def test_pipeline_linearisation_with_f0_from_rollout_is_bit_identical():
     assert np.array_equal(Bm.cpu().numpy(), B2.cpu().numpy(), equal_nan=True)
 
 
+def test_quadrotor_fd_kernels_agree_bit_for_bit():
+    """Three implementations of linearize_forward_diff_traj for the quadrotor (thread per step with compile-time
+    sparsity, lane per column with shared trigonometry, generic) must produce identical bits, on hover-like and on
+    aggressive random states, with and without f0 taken from a consistent rollout, guards included."""
+    from hop import _cabi
+    lib = _cabi.require_device()
+    case = cases.make_case("Quadrotor", N=128)
+    F, u_ref, N = case[0], case[3], case[8]
+    rng = np.random.default_rng(11)
+    B = 40
+    x0s = s1_x0(B, seed=9)
+    x0s[:, 3:] += rng.standard_normal((B, 9)) * np.array([1, 1, 1, .6, .6, 2.0, 3, 3, 3])   # velocities, large angles, rates
+    x0s[3, 7] = np.pi / 2 - 1.0005e-3                    # |cos(pitch)| just above cos_pitch_min = 1e-3 (systems.py:166,187)
+    x0s[4, 3:] = 0.0; x0s[4, 9] = 999.9995               # body rate just below omg_abs_max = 1e3: the perturbed point trips it
+    x0s[5, 3:] = 0.0; x0s[5, :3] = [999999.4, 0.0, 0.0]  # norm just below state_norm_max = 1e6: h = 1 trips it for c = 0
+    U = np.tile(u_ref, (N, 1))[None] + 0.5 * rng.standard_normal((B, N, 4))
+    X = api.rollout_batched(F, _t(x0s), _t(U))
+    out = {}
+    try:
+        for variant in (0, 1, 2):
+            lib.hop_test_set_linearize_variant(variant)
+            A, Bm = api.linearize_batched(F, X, _t(U))
+            out[variant] = (A.cpu().numpy(), Bm.cpu().numpy())
+    finally:
+        lib.hop_test_set_linearize_variant(0)
+    assert np.isfinite(out[2][0]).mean() > 0.5
+    for variant in (0, 1):
+        assert np.array_equal(out[variant][0], out[2][0], equal_nan=True), variant
+        assert np.array_equal(out[variant][1], out[2][1], equal_nan=True), variant
+    # a structurally independent entry is an exact zero, as in the reference ((F_i - F_i) / h)
+    fin = np.isfinite(out[0][0][:, :, 0, 0])
+    assert (out[0][0][:, :, 9, 0][fin] == 0.0).all()
+
+
 def test_rollout_divergence_guard_nan_fills_like_the_reference():
     F = cases.make_case("Quadrotor", N=128)[0]
     x0 = np.zeros((2, 12)); x0[1, 7] = np.pi / 2          # Euler singularity -> F returns NaN (systems.py:179-181)

@@ -15,6 +15,7 @@ int dispatch_rollout(int B, int sys, const double* params_host, int N, const dou
 int dispatch_linearize(int B, int sys, const double* params_host, int N, const double* X, const double* U, long ustride,
                        int central, double epsx, double epsu, double relx, double relu, int f0_from_x, const int* skip,
                        double* A, double* Bm, cudaStream_t st);
+extern int g_linearize_variant;
 struct DdpConst {
     const double *xg, *w, *u_ref, *Q, *R, *Qf;
     unsigned wrap_mask;
@@ -386,6 +387,12 @@ __global__ void k_probe_dfma(int iters, double seed, double* sink) {
     }
     const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
     if (r == 12345.678) sink[0] = r;   // never true; keeps the chain alive
+}
+
+int hop_test_set_linearize_variant(int variant) {
+    const int old = g_linearize_variant;
+    if (variant >= 0 && variant <= 2) g_linearize_variant = variant;
+    return old;
 }
 
 int hop_probe_fp64_tflops(int iters, double* tflops_out, double* ms_out) {

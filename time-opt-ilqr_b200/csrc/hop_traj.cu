@@ -4,6 +4,8 @@
 //   k_linearize : linearization.py:216-262 (forward) / :177-211 (central)
 //                 one thread per (problem, step, perturbed coordinate); the n+m threads of a
 //                 (problem, step) pair are adjacent, so each row of A_k / B_k is written coalesced.
+#include <cstdlib>
+
 #include "hop_common.cuh"
 #include "hop_dynamics.cuh"
 #include "../../include/hop_b200.h"
@@ -11,6 +13,9 @@
 namespace hop {
 
 struct DynParams { double p[HOP_NPARAMS]; };
+
+// quadrotor forward-difference kernel: 0 thread-per-step (default), 1 lane-per-column, 2 generic (test / A-B hook)
+int g_linearize_variant = getenv("HOP_LIN_VARIANT") ? atoi(getenv("HOP_LIN_VARIANT")) : 0;
 
 template <int SYS>
 __global__ void k_rollout(int B, DynParams prm, int N, const double* __restrict__ x0, const double* __restrict__ U,
@@ -110,6 +115,11 @@ __global__ void k_linearize(int B, DynParams prm, int N, const double* __restric
     }
 }
 
+// out-of-line copy of the full dynamics for cold paths
+__device__ __noinline__ void quad_dynamics_cold(const double* p, const double* x, const double* u, double* xn) {
+    dynamics<2>(p, x, u, xn);
+}
+
 // Quadrotor forward-difference linearisation (linearization.py:216-262), 16 lanes per (problem, step): lane c
 // perturbs coordinate c of (x, u).  Compared with the generic kernel above:
 //   * every lane evaluates ONE sincos (+ tan for the pitch lanes): lanes 0..2 the unperturbed roll / pitch / yaw,
@@ -203,6 +213,156 @@ __global__ void __launch_bounds__(128) k_linearize_quad(int B, DynParams prm, in
     }
 }
 
+// ---- quadrotor forward differences, ONE THREAD PER (problem, step) -----------------------------------------
+// k_linearize_quad above spends 1584 warp-instructions per 32 lanes (ncu: 80 % of them selects / moves / integer
+// tests that exist only because the perturbed coordinate is a run-time lane index).  Here the 16 perturbations are
+// a compile-time unrolled loop in one thread, so that
+//   * the perturbed evaluations share every sub-expression that does not depend on the perturbed coordinate
+//     (same operations on the same values -> same bits; the compiler's CSE does the sharing),
+//   * entries (i, c) whose output F_i does not depend on coordinate c are written as the exact 0.0 the reference
+//     obtains from (F_i - F_i) / h  (quad_affects below is the dependency structure of systems.py:170-210),
+//   * A_k and B_k are stored as full 32-byte sectors (four columns of a row at a time).
+// f0 = F(X_k, U_k) comes from X[k+1] (consistent rollout) or is evaluated; NaN / guard semantics as above.
+// Bit-identical to k_linearize<2> / k_linearize_quad (tests/test_gpu_parity.py compares them on random states).
+// bit i of quad_affects(c): F_i depends on coordinate c of (x, u)
+__host__ __device__ constexpr unsigned quad_affects(int c) {
+    return c == 0 ? 0x001u : c == 1 ? 0x002u : c == 2 ? 0x004u          // x, y, z        -> their own row
+         : c == 3 ? 0x009u : c == 4 ? 0x012u : c == 5 ? 0x024u          // vx, vy, vz     -> position and velocity rows
+         : c == 6 ? 0x1f8u : c == 7 ? 0x1f8u : c == 8 ? 0x118u          // roll, pitch -> v and Euler-rate rows; yaw -> vx, vy, yaw
+         : c == 9 ? 0xe40u : c == 10 ? 0xfc0u : c == 11 ? 0xfc0u        // wp -> {roll rate, w}; wq, wr -> Euler rates and w
+         : c == 12 ? 0x038u : c == 13 ? 0x200u : c == 14 ? 0x400u : 0x800u;   // thrust -> v rows; torques -> their w row
+}
+
+template <int C>
+__device__ __forceinline__ void quad_fd_column(const double* p, const double* x0v, const double* u0v, const QuadTrig& Tb,
+                                               const double* f0, bool nanout, double ss_sqrt, double epsx, double epsu,
+                                               double relx, double relu, double* col) {
+    constexpr int n = 12, m = 4;
+    constexpr unsigned aff = quad_affects(C);
+    double x[n], u[m];
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = x0v[i];
+#pragma unroll
+    for (int i = 0; i < m; ++i) u[i] = u0v[i];
+    const double base = C < n ? x0v[C < n ? C : 0] : u0v[C >= n ? C - n : 0];
+    const double h = C < n ? fmax(epsx, mul(relx, fmax(1.0, fabs(base)))) : fmax(epsu, mul(relu, fmax(1.0, fabs(base))));
+    const double vp = add(base, h);
+    if (C < n) x[C < n ? C : 0] = vp; else u[C >= n ? C - n : 0] = vp;
+    QuadTrig T = Tb;
+    if (C == 6) sincos(vp, &T.sph, &T.cph);
+    if (C == 7) { sincos(vp, &T.sth, &T.cth); T.tth = tan(vp); }
+    if (C == 8) sincos(vp, &T.sps, &T.cps);
+    // guards (systems.py:175-191).  The norm test can only change if the unperturbed norm is within h of the limit:
+    // ||x + h e_c|| <= ||x|| + h.  Otherwise evaluate it exactly (cold).
+    bool bad = !isfinite(vp);
+    if (C < n) {
+        if (ss_sqrt + 1.0000001 * h + 1e-9 * ss_sqrt >= p[13]) bad = bad || quad_guard(p, x, u);
+        if (C >= 9) bad = bad || (fabs(vp) > p[12]);
+    }
+    if (C == 7) bad = bad || (fabs(T.cth) < p[11]);
+    double fp[n];
+    quad_core(p, x, u, T, fp);
+    const double rh = 1.0 / h;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        double q = 0.0;
+        if ((aff >> i) & 1u) {
+            const double d = sub(fp[i], f0[i]);
+            const double q0 = mul(d, rh);
+            q = fma(fma(-q0, h, d), rh, q0);
+        }
+        col[i] = (nanout || bad) ? nan("") : q;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_linearize_quad_row(int B, DynParams prm, int N, const double* __restrict__ X,
+                                                            const double* __restrict__ U, long ustride, double epsx, double epsu,
+                                                            double relx, double relu, int f0_from_x, const int* __restrict__ skip,
+                                                            double* __restrict__ A, double* __restrict__ Bm) {
+    constexpr int n = 12, m = 4;
+    const size_t total = (size_t)B * N;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = gid < total;
+    const size_t bk = live ? gid : total - 1;     // dead lanes shadow the last step: the pair exchange below needs every lane
+    const int k = (int)(bk % N);
+    const size_t b = bk / N;
+    const bool active = live && !(skip && skip[b]);
+    if (__all_sync(0xffffffffu, !active)) return;
+    double x[n], u[m], f0[n];
+    const double* xs = X + (b * (N + 1) + k) * n;
+    const double* us = U + b * ustride + (size_t)k * m;
+#pragma unroll
+    for (int i = 0; i < n; ++i) x[i] = xs[i];
+#pragma unroll
+    for (int i = 0; i < m; ++i) u[i] = us[i];
+    bool have_f0 = false;
+    if (f0_from_x) {
+        bool fin = true, finx = true;
+#pragma unroll
+        for (int i = 0; i < n; ++i) { f0[i] = xs[n + i]; fin = fin && isfinite(f0[i]); finx = finx && isfinite(x[i]); }
+        have_f0 = fin || !finx;       // see k_linearize_quad
+    }
+    if (!have_f0) {                     // cold; through copies so that x, u, f0 themselves never live in local memory
+        double xc[n], uc[m], fc[n];
+#pragma unroll
+        for (int i = 0; i < n; ++i) xc[i] = x[i];
+#pragma unroll
+        for (int i = 0; i < m; ++i) uc[i] = u[i];
+        quad_dynamics_cold(prm.p, xc, uc, fc);
+#pragma unroll
+        for (int i = 0; i < n; ++i) f0[i] = fc[i];
+    }
+    bool nanout = false;
+#pragma unroll
+    for (int i = 0; i < n; ++i) nanout = nanout || !isfinite(f0[i]);      // linearization.py:243-248
+    // unperturbed trigonometry and norm, shared by all 16 columns
+    QuadTrig T;
+    sincos(x[6], &T.sph, &T.cph);
+    sincos(x[7], &T.sth, &T.cth);
+    sincos(x[8], &T.sps, &T.cps);
+    T.tth = tan(x[7]);
+    double ss = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) ss = add(ss, mul(x[i], x[i]));
+    const double nrm = sqrt(ss);
+    // Stores: a thread owns 32 contiguous bytes per (row, 4-column group).  Two half-sector stores per thread make the
+    // L2 read-fill every sector (ncu: 19 GB written + 6.5 GB read for 12.9 GB of output); instead neighbouring lanes
+    // swap halves so that every store instruction writes FULL 32-byte sectors (lane pair = one sector).
+    const bool odd = (threadIdx.x & 1) != 0;
+    const bool pair_active = __shfl_xor_sync(0xffffffffu, active ? 1 : 0, 1) != 0;
+    char* Aown = reinterpret_cast<char*>(A + bk * n * n);
+    char* Bown = reinterpret_cast<char*>(Bm + bk * n * m);
+    const size_t bk_pair = (size_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)bk, 1);   // (a dead lane shadows total - 1)
+    char* Apair = reinterpret_cast<char*>(A + bk_pair * n * n);
+    char* Bpair = reinterpret_cast<char*>(Bm + bk_pair * n * m);
+#define HOP_FD4(C0, OWN, PAIR, LDB)                                                                                       \
+    {                                                                                                                     \
+        double c0[n], c1[n], c2[n], c3[n];                                                                                \
+        quad_fd_column<C0 + 0>(prm.p, x, u, T, f0, nanout, nrm, epsx, epsu, relx, relu, c0);                              \
+        quad_fd_column<C0 + 1>(prm.p, x, u, T, f0, nanout, nrm, epsx, epsu, relx, relu, c1);                              \
+        quad_fd_column<C0 + 2>(prm.p, x, u, T, f0, nanout, nrm, epsx, epsu, relx, relu, c2);                              \
+        quad_fd_column<C0 + 3>(prm.p, x, u, T, f0, nanout, nrm, epsx, epsu, relx, relu, c3);                              \
+        _Pragma("unroll") for (int i = 0; i < n; ++i) {                                                                   \
+            /* even lane keeps (c0,c1) and sends (c2,c3); odd lane keeps (c2,c3) and sends (c0,c1) */                     \
+            const double s0 = odd ? c0[i] : c2[i], s1 = odd ? c1[i] : c3[i];                                              \
+            const double r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);              \
+            /* sector of the even lane's step: even writes its low half, odd writes the even lane's high half */          \
+            if (odd ? pair_active : active)                                                                               \
+                *reinterpret_cast<double2*>((odd ? (PAIR) : (OWN)) + i * (LDB) + (odd ? 16 : 0)) =                         \
+                    odd ? make_double2(r0, r1) : make_double2(c0[i], c1[i]);                                              \
+            /* sector of the odd lane's step */                                                                           \
+            if (odd ? active : pair_active)                                                                               \
+                *reinterpret_cast<double2*>((odd ? (OWN) : (PAIR)) + i * (LDB) + (odd ? 16 : 0)) =                         \
+                    odd ? make_double2(c2[i], c3[i]) : make_double2(r0, r1);                                              \
+        }                                                                                                                 \
+    }
+    HOP_FD4(0, Aown + 0, Apair + 0, n * 8)
+    HOP_FD4(4, Aown + 32, Apair + 32, n * 8)
+    HOP_FD4(8, Aown + 64, Apair + 64, n * 8)
+    HOP_FD4(12, Bown, Bpair, m * 8)
+#undef HOP_FD4
+}
+
 template <int SYS>
 static int launch_rollout(int B, const DynParams& prm, int N, const double* x0, const double* U, long ustride,
                           double max_norm, double* X, cudaStream_t st) {
@@ -219,8 +379,18 @@ static int launch_linearize(int B, const DynParams& prm, int N, const double* X,
     const int threads = 128;
     const size_t grid = (total + threads - 1) / threads;
     if (SYS == 2 && !central) {
-        k_linearize_quad<<<(unsigned)grid, threads, 0, st>>>(B, prm, N, X, U, ustride, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm);
-        return check_launch("k_linearize_quad");
+        // A/B + test switch: 0 (default) thread-per-step kernel, 1 lane-per-column kernel, 2 generic kernel
+        const int variant = g_linearize_variant;
+        if (variant == 0) {
+            const size_t rows = (size_t)B * N;
+            k_linearize_quad_row<<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(
+                B, prm, N, X, U, ustride, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm);
+            return check_launch("k_linearize_quad_row");
+        }
+        if (variant == 1) {
+            k_linearize_quad<<<(unsigned)grid, threads, 0, st>>>(B, prm, N, X, U, ustride, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm);
+            return check_launch("k_linearize_quad");
+        }
     }
     k_linearize<SYS><<<(unsigned)grid, threads, 0, st>>>(B, prm, N, X, U, ustride, central, epsx, epsu, relx, relu, skip, A, Bm);
     return check_launch("k_linearize");
