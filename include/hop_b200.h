@@ -39,8 +39,12 @@ enum { HOP_ST_OK = 0, HOP_ST_NONFINITE = 1, HOP_ST_LINALG = 2, HOP_ST_ERRMASK = 
  *   EXACT: every augmented block is materialised and inverted through the generic chol_inv, in the
  *          reference's operation order.
  *   FAST : fused entry points only (ignored elsewhere): closed-form block inverses for E_k and X_t,
- *          pivot-only evaluation of J(t) = 0.5 / pivot_n(X0), _sym only on the carried state. */
-enum { HOP_MODE_EXACT = 0, HOP_MODE_FAST = 1 };
+ *          pivot-only evaluation of J(t) = 0.5 / pivot_n(X0), _sym only on the carried state.
+ *   SCAN : hop_select_f64 only, (d, m) = (12,4) / (13,4): the prefix composition as a chunked parallel scan over the
+ *          horizon (one CTA of 8 warps per problem; latency 2T/8 + 7 instead of T steps for ~2x the prefix work) --
+ *          for SMALL batches.  Re-association changes the rounding (<= 1e-9 on well-conditioned problems; unsafe on
+ *          ill-conditioned ones such as the cartpole embedding), so it is opt-in. */
+enum { HOP_MODE_EXACT = 0, HOP_MODE_FAST = 1, HOP_MODE_SCAN = 2 };
 
 /* device dynamics registry (systems.py closures cannot run on the GPU) */
 enum { HOP_SYS_DOUBLE_INTEGRATOR = 0, /* systems.py:28-50   params [dt]                               */

@@ -6,6 +6,7 @@
 #include "hop_select_body.cuh"
 #include "hop_select_mma_body.cuh"
 #include "hop_select_pipe_body.cuh"
+#include "hop_select_scan_body.cuh"
 
 namespace {
 template <int D, int M, int G>
@@ -128,6 +129,31 @@ extern "C" int emul_chol_inv_mma(int d, const double* A, double* X, int* status)
     if (d == 13) return hop::simt::run_warp(inv_lane<13>, &j);
     if (d == 12) return hop::simt::run_warp(inv_lane<12>, &j);
     if (d == 4) return hop::simt::run_warp(inv_lane<4>, &j);
+    return -2;
+}
+
+// ---- HOP_MODE_SCAN: the CTA's warps run one after the other; the two __syncthreads() are the phase boundaries
+namespace {
+struct ScanJob { const hop::SelectArgs* p; int b, c; double* smem; };
+template <int D, int M>
+void scan_p1_lane(void* a) { auto* j = (ScanJob*)a; hop::mma::scan_phase1<D, M>(*j->p, j->b, j->c, hop::mma::kScanWarps, j->smem); }
+template <int D, int M>
+void scan_p23_lane(void* a) { auto* j = (ScanJob*)a; hop::mma::scan_phase23<D, M>(*j->p, j->b, j->c, hop::mma::kScanWarps, j->smem); }
+template <int D, int M>
+int run_generic_scan(const hop::SelectArgs& p) {
+    constexpr int C = hop::mma::kScanWarps;
+    std::vector<double> smem(hop::mma::ScanSmem::size(C), -7.0);
+    for (int b = 0; b < p.B; ++b) {
+        for (int c = 0; c < C; ++c) { ScanJob j{&p, b, c, smem.data()}; if (hop::simt::run_warp(scan_p1_lane<D, M>, &j)) return -1; }
+        for (int c = 0; c < C; ++c) { ScanJob j{&p, b, c, smem.data()}; if (hop::simt::run_warp(scan_p23_lane<D, M>, &j)) return -1; }
+        hop::mma::scan_finish(p, b, C, smem.data());
+    }
+    return 0;
+}
+}  // namespace
+extern "C" int emul_select_generic_scan(int d, int m, const hop::SelectArgs* p) {
+    if (d == 12 && m == 4) return run_generic_scan<12, 4>(*p);
+    if (d == 13 && m == 4) return run_generic_scan<13, 4>(*p);
     return -2;
 }
 

@@ -11,6 +11,7 @@
 
 #define HOP_DEVICE inline
 #define HOP_DEVICE_NOINLINE inline
+#define HOP_HD
 
 using std::isfinite;
 

@@ -68,6 +68,34 @@ def test_select_fused_matches_reference_golden(name, traj, mode):
         assert rel(J[T_min - 1:T_max], Jr[T_min - 1:T_max]) <= tol_win
 
 
+@pytest.mark.parametrize("d,m,N,T_max", [(12, 4, 128, 128), (13, 4, 128, 128), (13, 4, 64, 61), (13, 4, 16, 5)])
+def test_scan_mode_matches_sequential_sweep_and_oracle(d, m, N, T_max):
+    """HOP_MODE_SCAN: chunked parallel scan over the horizon (one CTA of 8 warps per problem).  Chunk 0 is bit-identical to
+    the sequential sweep; later chunks differ by re-association only (well-conditioned S2: 1e-9, the north-star tolerance)."""
+    A, Bm, Q, R, z0, w, QT = s2_batch(range(7), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    args = (_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, T_max)
+    seq = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w))
+    scan = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w), mode=api.MODE_SCAN)
+    Js, Jp = seq.J.cpu().numpy(), scan.J.cpu().numpy()
+    Lc = -(-T_max // 8)
+    assert not scan.status.cpu().numpy().any()
+    assert np.array_equal(Jp[:, :Lc], Js[:, :Lc])
+    assert rel(Jp, Js) <= 1e-9
+    assert torch.equal(scan.T_star, seq.T_star)
+    Jo, _ = O.propagator_batch(A, Bm, Q, Rinv, z0, QT, T_use=T_max)
+    assert rel(Jp, Jo) <= 1e-9
+    assert np.array_equal(scan.T_star.cpu().numpy(), np.argmin(Jo + w[:, None] * np.arange(1, T_max + 1), axis=1) + 1)
+
+
+def test_scan_mode_is_refused_where_it_is_not_instantiated():
+    from hop import _cabi
+    A, Bm, Q, R, z0, w, QT = s2_batch(range(2), 4, 2, 8)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    with pytest.raises(_cabi.HopError):
+        api.propagator_all_Jt_aug_batched(_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, 8, mode=api.MODE_SCAN)
+
+
 def test_generic_and_fused_agree_bitwise_in_T_and_closely_in_J():
     """The fused kernel builds the augmented blocks itself; feeding the oracle-built blocks to the
     generic kernel must give the same selection."""

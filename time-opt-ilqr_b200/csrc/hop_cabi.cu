@@ -8,7 +8,7 @@
 #include "../../include/hop_b200.h"
 
 namespace hop {
-int dispatch_select_generic(int d, int m, const SelectArgs& p, cudaStream_t st);
+int dispatch_select_generic(int d, int m, int mode, const SelectArgs& p, cudaStream_t st);
 int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st);
 int dispatch_rollout(int B, int sys, const double* params_host, int N, const double* x0, const double* U, long ustride,
                      double max_norm, double* X, cudaStream_t st);
@@ -94,7 +94,8 @@ int hop_select_f64(int B, int N, int d, int m, int T_min, int T_max, const doubl
                    const double* Q_aug, const double* R_inv, long rinv_step_stride, const double* z0, const double* QT,
                    const double* w_explicit, int mode, double* J_out, int* Tstar_out, double* Jstar_out, int* status,
                    void* stream) {
-    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || (mode != HOP_MODE_EXACT && mode != HOP_MODE_FAST) ||
+    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N ||
+        (mode != HOP_MODE_EXACT && mode != HOP_MODE_FAST && mode != HOP_MODE_SCAN) ||
         (rinv_step_stride != 0 && rinv_step_stride != (long)m * m)) {
         set_last_error("hop_select_f64: bad argument (need 1 <= T_min <= T_max <= N, rinv_step_stride in {0, m*m})");
         return HOP_E_BADARG;
@@ -103,7 +104,7 @@ int hop_select_f64(int B, int N, int d, int m, int T_min, int T_max, const doubl
     if (B == 0) return 0;
     SelectArgs p{B, N, T_min, T_max, kJitter, kMaxTries, A_aug, B_aug, Q_aug, R_inv, z0, QT, rinv_step_stride, w_explicit,
                  J_out, Tstar_out, Jstar_out, status};
-    return dispatch_select_generic(d, m, p, (cudaStream_t)stream);
+    return dispatch_select_generic(d, m, mode, p, (cudaStream_t)stream);
 }
 
 int hop_select_fused_f64(int B, int N, int n, int m, int T_min, int T_max, const double* A, const double* Bm,

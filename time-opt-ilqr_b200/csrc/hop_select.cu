@@ -10,6 +10,7 @@
 #include "hop_select_body.cuh"
 #include "hop_select_mma_body.cuh"
 #include "hop_select_pipe_body.cuh"
+#include "hop_select_scan_body.cuh"
 #include "../../include/hop_b200.h"
 
 namespace hop {
@@ -107,6 +108,26 @@ __global__ void __launch_bounds__(kMmaWarps * 32, MINB) k_select_fused_mma(const
     }
 }
 
+// HOP_MODE_SCAN: one CTA (kScanWarps warps) per problem, chunked parallel scan over the horizon
+template <int D, int M>
+__global__ void __launch_bounds__(mma::kScanWarps * 32) k_select_generic_scan(const SelectArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, b = blockIdx.x;
+    mma::scan_phase1<D, M>(p, b, warp, mma::kScanWarps, smem);
+    __syncthreads();
+    mma::scan_phase23<D, M>(p, b, warp, mma::kScanWarps, smem);
+    __syncthreads();
+    if (threadIdx.x == 0) mma::scan_finish(p, b, mma::kScanWarps, smem);
+}
+template <int D, int M>
+static int launch_generic_scan(const SelectArgs& p, cudaStream_t st) {
+    const size_t smem = sizeof(double) * (size_t)mma::ScanSmem::size(mma::kScanWarps);
+    cudaError_t e = cudaFuncSetAttribute(k_select_generic_scan<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return report_cuda(e, "cudaFuncSetAttribute(k_select_generic_scan)");
+    k_select_generic_scan<D, M><<<p.B, mma::kScanWarps * 32, smem, st>>>(p);
+    return check_launch("k_select_generic_scan");
+}
+
 template <int D, int M>
 static int launch_generic_mma(const SelectArgs& p, cudaStream_t st) {
     const size_t smem = sizeof(double) * (size_t)kMmaWarps * mma::kWarpScratch;
@@ -140,7 +161,13 @@ static int launch_fused_mma(const FusedArgs& p, cudaStream_t st) {
     }
 }
 
-int dispatch_select_generic(int d, int m, const SelectArgs& p, cudaStream_t st) {
+int dispatch_select_generic(int d, int m, int mode, const SelectArgs& p, cudaStream_t st) {
+    if (mode == HOP_MODE_SCAN) {
+        if (d == 12 && m == 4) return launch_generic_scan<12, 4>(p, st);
+        if (d == 13 && m == 4) return launch_generic_scan<13, 4>(p, st);
+        set_last_error("hop_select_f64: HOP_MODE_SCAN is instantiated for (d, m) = (12,4) and (13,4) only");
+        return HOP_E_UNSUPPORTED_DIMS;
+    }
     if (d == 3 && m == 1) return launch_generic<3, 1, 4>(p, st);
     if (d == 4 && m == 2) return launch_generic<4, 2, 4>(p, st);
     if (d == 5 && m == 1) return launch_generic<5, 1, 8>(p, st);

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #define HOP_DEVICE __device__ __forceinline__
 #define HOP_DEVICE_NOINLINE __device__ __noinline__
+#define HOP_HD __host__ __device__
 namespace hop { namespace simt {
 HOP_DEVICE int lane_id() { return (int)(threadIdx.x & 31u); }
 HOP_DEVICE void sync() { __syncwarp(); }

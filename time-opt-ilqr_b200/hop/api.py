@@ -24,6 +24,7 @@ from .cases import NPARAMS, SYS_DIMS
 
 MODE_EXACT = 0   # reference operation order, every block through the generic chol_inv
 MODE_FAST = 1    # fused entry points: closed-form block inverses + pivot-only J(t) (same function)
+MODE_SCAN = 2    # propagator_all_Jt_aug_batched only, d in {12, 13}: chunked parallel scan over the horizon (small batches)
 
 
 @dataclass
