@@ -34,6 +34,8 @@ os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
 import numpy as np  # noqa: E402
 
 METRIC = "horizon-selection solves/sec (batched HOP-LQR, quadrotor n=12, N=128)"
+WORKLOAD = ("S1 quadrotor n=12 m=4 d=13 N=128 T in [40,128]: iteration-0 HOP horizon selection per initial state "
+            "(rollout + forward-FD linearisation -> augmented embedding + LFT stage/prefix/query sweep + argmin)")
 UNIT = "solves/s"
 N_HORIZON, D_AUG, M_CTRL = 128, 13, 4
 
@@ -128,9 +130,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "S1 quadrotor n=12 m=4 d=13 N=128 T in [40,128], x0 -> T* (rollout + forward-FD "
-                                   "linearisation + augmented embedding + LFT sweep + argmin)",
-                       "batch_per_step": sample, "threads": cores},
+            "config": {"workload": WORKLOAD, "batch_per_step": sample, "threads": cores,
+                       "timed": "whole x0 -> T* pipeline on the host cores (the e2e definition of the hop arm)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{sample} instances per step, pthread fan-out of oracle/hop_oracle.c over {cores} host "
                                        "threads (the reference is pure Python/numpy and is not installable on the box; "
@@ -297,7 +298,8 @@ def run_hop(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "S1 quadrotor n=12 m=4 d=13 N=128 T in [40,128] (iteration-0 HOP selection)",
+            "config": {"workload": WORKLOAD,
+                       "timed": "value: fused selection kernel on HBM-resident linearisation; e2e: whole x0 -> T* pipeline from pinned host buffers",
                        "batch_per_gpu": B, "global_batch": world * B,
                        "mode": args.mode + " (sequential in the horizon; software-pipelined pivot sweeps)",
                        "l2": "inputs (A,B,X = %.1f GB per GPU) exceed the 126 MB L2" % (byte_launch / 1e9),

@@ -357,9 +357,6 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch
                 YV[L.lane] = y;
             }
             const double sigma = (corner + p.jitter) - warp_sum(isx ? qe * y : 0.0);
-#ifdef HOP_DEBUG_PIPE
-            if (L.lane==0) printf("seq k=%d eQe=%.17g corner=%.17g sigq=%.17g\n", k, eQe, corner, sigma);
-#endif
             simt::sync();
             if (simt::all(sigma > 0.0)) {
                 const double rs = 1.0 / sigma;
@@ -453,9 +450,6 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* scratch
                 YV[L.lane] = y;
             }
             const double sigma = (p.rho_reg + p.jitter) + p.jitter * warp_sum(isx ? y * et : 0.0);
-#ifdef HOP_DEBUG_PIPE
-            if (L.lane==0) printf("seq k=%d sigp=%.17g\n", k, sigma);
-#endif
             simt::sync();
             if (simt::all(sigma > 0.0)) {
                 const double rs = 1.0 / sigma;

@@ -178,10 +178,6 @@ template <int D, int GI, int GS, bool UNROLL>
 HOP_DEVICE void gj3_group(Mat& a1, Mat& a2, Mat& x, const LaneGeo& L, int& signs, double& p) {
     constexpr int first = 8 * GI + 4 * GS;
     constexpr int cnt = (D - first) < 4 ? (D - first) : 4;
-#ifdef HOP_EXP_NOGJ     // timing experiment only (wrong results): what do the products cost without the pivot sweeps?
-    HOP_FOR_ELEMS(I, J, s) asm volatile("" : "+d"(a1.v[I][J][s]), "+d"(a2.v[I][J][s]), "+d"(x.v[I][J][s]));
-    p = x.v[1][1][1] + 1.0; return;
-#endif
     if (UNROLL) {
 #pragma unroll
         for (int tj = 0; tj < cnt; ++tj) {

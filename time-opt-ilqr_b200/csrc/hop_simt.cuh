@@ -24,9 +24,6 @@ HOP_DEVICE bool all(bool p) { return __all_sync(0xffffffffu, p) != 0; }
 // D(8x8) += A(8x4) * B(4x8) in fp64 on the tensor pipe (SASS: DMMA.8x8x4).  Fragments (g = lane>>2,
 // t = lane&3): a = A[g][t], b = B[t][g], c0/c1 = C[g][2t], C[g][2t+1].
 HOP_DEVICE void dmma(double& c0, double& c1, double a, double b) {
-#ifdef HOP_EXP_NODMMA   // timing experiment only (wrong results): what does the sweep cost without the tensor work?
-    asm volatile("" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b)); return;
-#endif
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
