@@ -182,6 +182,8 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double *params_host, int N, int T
 /* Test hook: selects the quadrotor forward-difference kernel (0 = thread per step [default], 1 = lane per column,
  * 2 = the generic kernel); returns the previous value.  All three produce identical bits (tests/test_gpu_parity.py). */
 int hop_test_set_linearize_variant(int variant);
+/* Test hook: backward-pass kernel, 0 = one warp per problem [default], 1 = one thread per problem; identical bits. */
+int hop_test_set_backward_variant(int variant);
 
 /* Measures the FP64 FMA throughput of the current device with a register-resident DFMA chain
  * (8 independent accumulators per thread, 2048 threads per SM), timed with CUDA events.  This is

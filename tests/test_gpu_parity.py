@@ -317,6 +317,27 @@ def test_batched_hop_ddp_solve_matches_reference_golden(name, mode):
     assert torch.equal(r["T_hist"][0], r["T_hist"][2]) and torch.equal(r["J_hist"][0, :nh], r["J_hist"][2, :nh])
 
 
+@pytest.mark.parametrize("name", ["Quadrotor", "Segway_Balance", "DoubleIntegrator"])
+def test_warp_and_thread_backward_kernels_agree_bit_for_bit(name):
+    """backward_pass_truncated has two device mappings (one warp per problem, elements of every product spread over the
+    lanes; one thread per problem).  Same operation order per element => identical gains, flags and solves."""
+    from hop import _cabi
+    lib = _cabi.require_device()
+    case = cases.make_case(name, N=128) if name == "Quadrotor" else cases.make_case(name)
+    n = case[1].size
+    rng = np.random.default_rng(2)
+    x0s = case[1][None] + 0.05 * rng.standard_normal((37, n))
+    out = {}
+    try:
+        for variant in (0, 1):
+            lib.hop_test_set_backward_variant(variant)
+            out[variant] = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=4, use_central_diff=False, mode=api.MODE_FAST)
+    finally:
+        lib.hop_test_set_backward_variant(0)
+    for key in ("X", "U", "J_hist", "T_hist", "n_hist", "T_star", "status"):
+        assert torch.equal(torch.nan_to_num(out[0][key].double(), nan=-1.0), torch.nan_to_num(out[1][key].double(), nan=-1.0)), key
+
+
 def test_batched_hop_ddp_matches_oracle_on_sampled_quadrotor_instances():
     """Config 4 (scaled down): quadrotor N=128, sampled x0; every instance runs its own state machine."""
     case = cases.make_case("Quadrotor", N=128)

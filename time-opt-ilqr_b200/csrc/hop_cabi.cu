@@ -16,6 +16,7 @@ int dispatch_linearize(int B, int sys, const double* params_host, int N, const d
                        int central, double epsx, double epsu, double relx, double relu, int f0_from_x, const int* skip,
                        double* A, double* Bm, cudaStream_t st);
 extern int g_linearize_variant;
+extern int g_backward_variant;
 struct DdpConst {
     const double *xg, *w, *u_ref, *Q, *R, *Qf;
     unsigned wrap_mask;
@@ -388,6 +389,12 @@ __global__ void k_probe_dfma(int iters, double seed, double* sink) {
     }
     const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
     if (r == 12345.678) sink[0] = r;   // never true; keeps the chain alive
+}
+
+int hop_test_set_backward_variant(int variant) {
+    const int old = g_backward_variant;
+    if (variant == 0 || variant == 1) g_backward_variant = variant;
+    return old;
 }
 
 int hop_test_set_linearize_variant(int variant) {

@@ -9,6 +9,8 @@
 // Every kernel takes the per-instance `done` word and skips finished instances, so a batch whose
 // members stop at different iterations needs no host-side control flow.
 #include "hop_common.cuh"
+#include <cstdlib>
+
 #include "hop_ddp_core.cuh"
 #include "../../include/hop_b200.h"
 
@@ -53,6 +55,31 @@ __global__ void k_backward(int B, int N, const double* A, const double* Bm, cons
                                             K_out + (size_t)b * N * m * n, &okb);
     ok[b] = (rc == 0) ? okb : 0;
     if (err) err[b] = rc;
+}
+
+// backward-pass kernel: 0 warp per problem (default), 1 thread per problem (test / A-B hook; identical bits)
+int g_backward_variant = getenv("HOP_BW_THREAD") ? atoi(getenv("HOP_BW_THREAD")) : 0;
+
+// one warp per problem (backward_pass_warp), kBwWarps problems per CTA
+constexpr int kBwWarps = 4;
+template <int n, int m>
+__global__ void __launch_bounds__(kBwWarps * 32) k_backward_warp(int B, int N, const double* A, const double* Bm, const double* X,
+                                                                 const double* U, DdpConst c, const int* T, const double* lm,
+                                                                 const int* done, double* k_out, double* K_out, int* ok, int* err) {
+    __shared__ __align__(16) double smem[kBwWarps * ddp::BwSmem<n, m>::SIZE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kBwWarps + warp;
+    if (b >= B) return;
+    if (done && done[b]) { if (lane == 0) ok[b] = 0; return; }
+    const ddp::CostConst cc = cost_const<n>(c, b);
+    int okb = 0;
+    const int rc = ddp::backward_pass_warp<n, m>(A + (size_t)b * N * n * n, Bm + (size_t)b * N * n * m, X + (size_t)b * (N + 1) * n,
+                                                 U + (size_t)b * N * m, cc, T[b], lm[b], k_out + (size_t)b * N * m,
+                                                 K_out + (size_t)b * N * m * n, &okb, smem + (size_t)warp * ddp::BwSmem<n, m>::SIZE, lane);
+    if (lane == 0) {
+        ok[b] = (rc == 0) ? okb : 0;
+        if (err) err[b] = rc;
+    }
 }
 
 template <int SYS>
@@ -175,7 +202,10 @@ static int ddp_backward_linesearch(int B, const DynParams2& prm, int N, const do
                                    cudaEvent_t mid, cudaStream_t st) {
     constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
     const int threads = 64;
-    k_backward<n, m><<<grid1(B, threads), threads, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
+    // A/B + test switch: HOP_BW_THREAD=1 selects the thread-per-problem kernel (bit-identical results)
+    const bool per_thread = g_backward_variant != 0;
+    if (per_thread) k_backward<n, m><<<grid1(B, threads), threads, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
+    else k_backward_warp<n, m><<<grid1(B, kBwWarps), kBwWarps * 32, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
     if (int rc = check_launch("k_backward")) return rc;
     if (mid) cudaEventRecord(mid, st);
     k_linesearch<SYS><<<grid1(B, threads), threads, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, done, Xn, Un, Jn, acc);

@@ -227,6 +227,207 @@ HOP_DEVICE int backward_pass(const double* A, const double* Bm, const double* X,
     return DDP_OK;
 }
 
+// ---- warp-cooperative backward pass ------------------------------------------------------------------------
+// Same recursion as backward_pass above, ONE WARP per problem: every matrix lives in per-warp shared memory and each
+// output ELEMENT is produced by one lane with exactly the operation sequence of the thread-per-problem version
+// (ordered 12-term sums, unfused mul/add), so the gains, Vx/Vxx and the ok/err flags are bit-identical -- only the
+// elements of a product are spread over the lanes.  The thread-per-problem kernel needs >= 3e5 problems to fill a
+// B200 (11 KB of local memory per thread); at 16 384 problems it ran 3.5 warps per SM (13 ms per pass).
+template <int n, int m>
+struct BwSmem {   // doubles per warp
+    static constexpr int VXX = 0, AK = VXX + n * n, BK = AK + n * n, ATV = BK + n * m, TT = ATV + n * n, QXX = TT + n * n,
+                         BTV = QXX + n * n, QUX = BTV + m * n, KK = QUX + m * n, KTQ = KK + m * n, QUU = KTQ + n * m,
+                         VX = QUU + m * m, QX = VX + n, VXN = QX + n, EV = VXN + n, QU = EV + n, KAP = QU + m, DU = KAP + m,
+                         SIZE = (DU + m + 1) & ~1;
+};
+
+// chol_solve (utils.py:96-120) with the right-hand-side columns spread over the lanes: every lane factors the d x d
+// matrix redundantly (same bits everywhere), lane j < c substitutes column j; the ladder decision (all X finite) is a vote.
+template <int d, int c>
+HOP_DEVICE int chol_solve_warp(const double* A, const double* Bm, double* X, double jitter, int max_tries, int lane) {
+    double S[d * d], M[d * d], Lo[d * d];
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) S[i * d + j] = 0.5 * add(A[i * d + j], A[j * d + i]);
+    bool fin = all_finite<d * d>(S);
+    for (int i = lane; i < d * c; i += 32) fin = fin && isfinite(Bm[i]);
+    if (!simt::all(fin)) return DDP_NONFINITE;
+    double eps = jitter;
+    for (int t = 0; t < max_tries; ++t) {
+        for (int i = 0; i < d * d; ++i) M[i] = S[i];
+        for (int i = 0; i < d; ++i) M[i * d + i] = add(S[i * d + i], eps);
+        if (cholesky_lower<d>(M, Lo)) {
+            bool okc = true;
+            double Y[d], Xc[d];
+            if (lane < c) {
+                const int col = lane;
+                for (int i = 0; i < d; ++i) {
+                    double s = Bm[i * c + col];
+                    for (int p = 0; p < i; ++p) s = sub(s, mul(Lo[i * d + p], Y[p]));
+                    Y[i] = s / Lo[i * d + i];
+                }
+                for (int i = d - 1; i >= 0; --i) {
+                    double s = Y[i];
+                    for (int p = i + 1; p < d; ++p) s = sub(s, mul(Lo[p * d + i], Xc[p]));
+                    Xc[i] = s / Lo[i * d + i];
+                }
+                okc = all_finite<d>(Xc);
+            }
+            if (simt::all(okc)) {
+                if (lane < c)
+                    for (int i = 0; i < d; ++i) X[i * c + lane] = Xc[i];
+                return DDP_OK;
+            }
+        }
+        eps *= 10.0;
+    }
+    return DDP_LINALG;
+}
+
+template <int n, int m>
+HOP_DEVICE int backward_pass_warp(const double* A, const double* Bm, const double* X, const double* U, const CostConst& c,
+                                  int T, double lm, double* k_out, double* K_out, int* ok, double* sm, int lane) {
+    using S = BwSmem<n, m>;
+    static_assert(n + m <= 32 && m * m <= 32, "lane roles below assume n + m <= 32");
+    double *Vxx = sm + S::VXX, *Ak = sm + S::AK, *Bk = sm + S::BK, *AtV = sm + S::ATV, *t = sm + S::TT, *Qxx = sm + S::QXX;
+    double *BtV = sm + S::BTV, *Qux = sm + S::QUX, *Kk = sm + S::KK, *KtQuu = sm + S::KTQ, *Quu = sm + S::QUU;
+    double *Vx = sm + S::VX, *Qx = sm + S::QX, *Vxn = sm + S::VXN, *e = sm + S::EV, *Qu = sm + S::QU, *kap = sm + S::KAP, *du = sm + S::DU;
+    *ok = 0;
+    if (T <= 0) return DDP_OK;
+    bool fin = true;
+    if (lane < n) {
+        double v = sub(X[(size_t)T * n + lane], c.xg[lane]);
+        if ((c.wrap_mask >> lane) & 1u) v = wrap_pi(v);
+        e[lane] = v;
+        fin = isfinite(v);
+    }
+    if (!simt::all(fin)) return DDP_OK;
+    simt::sync();
+    if (lane < n) {
+        double s = 0.0;
+        for (int j = 0; j < n; ++j) s = add(s, mul(c.Qf[lane * n + j], e[j]));
+        Vx[lane] = s;
+    }
+    for (int q = lane; q < n * n; q += 32) {
+        const int i = q / n, j = q % n;
+        Vxx[q] = 0.5 * add(c.Qf[i * n + j], c.Qf[j * n + i]);
+    }
+    for (int k = T - 1; k >= 0; --k) {
+        simt::sync();
+        for (int q = lane; q < n * n; q += 32) Ak[q] = A[(size_t)k * n * n + q];
+        for (int q = lane; q < n * m; q += 32) Bk[q] = Bm[(size_t)k * n * m + q];
+        fin = true;
+        if (lane < n) {
+            double v = sub(X[(size_t)k * n + lane], c.xg[lane]);
+            if ((c.wrap_mask >> lane) & 1u) v = wrap_pi(v);
+            e[lane] = v;
+            fin = isfinite(v);
+        } else if (lane < n + m) {
+            const double v = sub(U[(size_t)k * m + (lane - n)], c.u_ref[lane - n]);
+            du[lane - n] = v;
+            fin = isfinite(v);
+        }
+        if (!simt::all(fin)) return DDP_OK;
+        simt::sync();
+        // ---- Qx, Qu, A^T Vxx, B^T Vxx
+        if (lane < n) {
+            const int i = lane;
+            double lx = 0.0, s = 0.0;
+            for (int j = 0; j < n; ++j) lx = add(lx, mul(c.Q[i * n + j], e[j]));
+            for (int l = 0; l < n; ++l) s = add(s, mul(Ak[l * n + i], Vx[l]));
+            Qx[i] = add(lx, s);
+        } else if (lane < n + m) {
+            const int i = lane - n;
+            double lu = 0.0, s = 0.0;
+            for (int j = 0; j < m; ++j) lu = add(lu, mul(c.R[i * m + j], du[j]));
+            for (int l = 0; l < n; ++l) s = add(s, mul(Bk[l * m + i], Vx[l]));
+            Qu[i] = add(lu, s);
+        }
+        for (int q = lane; q < n * n; q += 32) {                                // mm_tn<n, n, n>(Ak, Vxx, AtV)
+            const int i = q / n, j = q % n;
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = add(s, mul(Ak[l * n + i], Vxx[l * n + j]));
+            AtV[q] = s;
+        }
+        for (int q = lane; q < m * n; q += 32) {                                // mm_tn<m, n, n>(Bk, Vxx, BtV)
+            const int i = q / n, j = q % n;
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = add(s, mul(Bk[l * m + i], Vxx[l * n + j]));
+            BtV[q] = s;
+        }
+        simt::sync();
+        // ---- Qxx = Q + (A^T Vxx) A, Quu = R + (B^T Vxx) B, Qux = (B^T Vxx) A
+        for (int q = lane; q < n * n; q += 32) {
+            const int i = q / n, j = q % n;
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = add(s, mul(AtV[i * n + l], Ak[l * n + j]));
+            Qxx[q] = add(c.Q[q], s);
+        }
+        for (int q = lane; q < m * m; q += 32) {
+            const int i = q / m, j = q % m;
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = add(s, mul(BtV[i * n + l], Bk[l * m + j]));
+            Quu[q] = add(c.R[q], s);
+        }
+        for (int q = lane; q < m * n; q += 32) {
+            const int i = q / n, j = q % n;
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = add(s, mul(BtV[i * n + l], Ak[l * n + j]));
+            Qux[q] = s;
+        }
+        simt::sync();
+        // ---- gains (every lane holds Quu_reg; the right-hand sides are spread over the lanes)
+        double Qreg[m * m], Ltmp[m * m];
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) Qreg[i * m + j] = add(0.5 * add(Quu[i * m + j], Quu[j * m + i]), (i == j) ? lm : 0.0);
+        if (!cholesky_lower<m>(Qreg, Ltmp)) return DDP_OK;                    // solver.py:213-216
+        int rc = chol_solve_warp<m, 1>(Qreg, Qu, kap, 1e-9, 8, lane);
+        if (rc) return rc;
+        rc = chol_solve_warp<m, n>(Qreg, Qux, Kk, 1e-9, 8, lane);
+        if (rc) return rc;
+        simt::sync();
+        if (lane < m) kap[lane] = -kap[lane];
+        for (int q = lane; q < m * n; q += 32) Kk[q] = -Kk[q];
+        simt::sync();
+        if (lane < m) k_out[(size_t)k * m + lane] = kap[lane];
+        for (int q = lane; q < m * n; q += 32) K_out[(size_t)k * m * n + q] = Kk[q];
+        for (int q = lane; q < n * m; q += 32) {                                // mm_tn<n, m, m>(Kk, Quu, KtQuu)
+            const int i = q / m, j = q % m;
+            double s = 0.0;
+            for (int l = 0; l < m; ++l) s = add(s, mul(Kk[l * n + i], Quu[l * m + j]));
+            KtQuu[q] = s;
+        }
+        simt::sync();
+        if (lane < n) {
+            const int i = lane;
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int l = 0; l < m; ++l) s1 = add(s1, mul(Kk[l * n + i], Qu[l]));
+            for (int l = 0; l < m; ++l) s2 = add(s2, mul(Qux[l * n + i], kap[l]));
+            for (int l = 0; l < m; ++l) s3 = add(s3, mul(KtQuu[i * m + l], kap[l]));
+            Vxn[i] = add(add(add(Qx[i], s1), s2), s3);                         // solver.py:224
+        }
+        for (int q = lane; q < n * n; q += 32) {
+            const int i = q / n, j = q % n;
+            double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+            for (int l = 0; l < m; ++l) t1 = add(t1, mul(Kk[l * n + i], Qux[l * n + j]));
+            for (int l = 0; l < m; ++l) t2 = add(t2, mul(Qux[l * n + i], Kk[l * n + j]));
+            for (int l = 0; l < m; ++l) t3 = add(t3, mul(KtQuu[i * m + l], Kk[l * n + j]));
+            t[q] = add(add(add(Qxx[q], t1), t2), t3);
+        }
+        simt::sync();
+        fin = true;
+        for (int q = lane; q < n * n; q += 32) {
+            const int i = q / n, j = q % n;
+            const double v = 0.5 * add(t[i * n + j], t[j * n + i]);             // solver.py:225
+            Vxx[q] = v;
+            fin = fin && isfinite(v);
+        }
+        if (lane < n) { Vx[lane] = Vxn[lane]; fin = fin && isfinite(Vxn[lane]); }
+        if (!simt::all(fin)) return DDP_OK;
+    }
+    *ok = 1;
+    return DDP_OK;
+}
+
 // solver.py:233-286, alphas = (1, .5, .25, .1, .05).  Writes the accepted candidate (or a copy of the
 // nominal when nothing improved) into X_new / U_new.
 template <int SYS>

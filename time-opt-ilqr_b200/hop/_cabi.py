@@ -42,6 +42,7 @@ SIGNATURES = {
     "hop_ilqr_timeopt_f64": (_i, [_i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u, _i, _d, _i, _i, _vp,
                                   _ull, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hop_test_set_linearize_variant": (_i, [_i]),
+    "hop_test_set_backward_variant": (_i, [_i]),
     "hop_probe_fp64_tflops": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
