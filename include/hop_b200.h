@@ -144,6 +144,15 @@ int hop_cost_f64(int B, int N, int n, int m, const double *X, const double *U, c
                  const double *u_ref, const double *Q, const double *R, const double *Qf, unsigned wrap_mask,
                  const int *T_star, double *J_out, void *stream);
 
+/* solver.py:293-358 bruteforce_all_Jt_backward_expansion, batched: J_out [B][T_max], J_out[b][T-1] = V0[0] of a full
+ * Riccati sweep T -> 0 (it already contains w T).  One warp per (instance, T): O(T_max^2 n^3) per instance -- the
+ * reference's baseline-1 curve, kept as an independent on-device check of the propagator.  status [B]: 0, or the
+ * chol_solve failure of some horizon (1 FloatingPointError, 2 LinAlgError; that horizon's J is NaN). */
+int hop_bruteforce_jt_f64(int B, int N, int n, int m, int T_max, const double *A, const double *Bm, const double *X,
+                          const double *U, long u_batch_stride, const double *xg, const double *w, const double *u_ref,
+                          const double *Q, const double *R, const double *Qf, unsigned wrap_mask, double lm_lambda,
+                          double *J_out, int *status, void *stream);
+
 /* solver.py:156-230 backward_pass_truncated followed by solver.py:233-286 forward_linesearch_fixedT, batched,
  * at per-instance horizons T_star[b] and Levenberg-Marquardt weights lm[b].
  *   k_out [B][N][m], K_out [B][N][m][n] (rows >= T_star[b] untouched), ok_out [B] (0 = the reference's

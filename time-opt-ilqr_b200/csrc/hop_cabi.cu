@@ -25,6 +25,8 @@ int dispatch_backward_linesearch(int sys, int B, const double* params_host, int 
                                  const double* X, const double* U, const DdpConst& c, const int* T, const double* lm,
                                  const int* done, double* kl, double* Kl, int* ok, int* bw_err, double* Xn, double* Un,
                                  double* Jn, int* acc, cudaEvent_t mid, cudaStream_t st);
+int dispatch_bruteforce(int n, int m, int B, int N, int T_max, const double* A, const double* Bm, const double* X, const double* U,
+                        long ustride, const DdpConst& c, double lm, double* J_out, int* status, cudaStream_t st);
 int dispatch_cost(int n, int m, int B, int N, const double* X, const double* U, const DdpConst& c, const int* T, double* J,
                   cudaStream_t st);
 int dispatch_linesearch(int sys, int B, const double* params_host, int N, const double* X, const double* U, const DdpConst& c,
@@ -225,6 +227,17 @@ int hop_cost_f64(int B, int N, int n, int m, const double* X, const double* U, c
     if (B <= 0) return B == 0 ? 0 : HOP_E_BADARG;
     DdpConst c{xg, w, u_ref, Q, R, Qf, wrap_mask};
     return dispatch_cost(n, m, B, N, X, U, c, T_star, J_out, (cudaStream_t)stream);
+}
+
+int hop_bruteforce_jt_f64(int B, int N, int n, int m, int T_max, const double* A, const double* Bm, const double* X,
+                          const double* U, long u_batch_stride, const double* xg, const double* w, const double* u_ref,
+                          const double* Q, const double* R, const double* Qf, unsigned wrap_mask, double lm_lambda,
+                          double* J_out, int* status, void* stream) {
+    if (B < 0 || N < 1 || T_max < 1 || T_max > N) { set_last_error("hop_bruteforce_jt_f64: need 1 <= T_max <= N"); return HOP_E_BADARG; }
+    if (int rc = need_device()) return rc;
+    if (B == 0) return 0;
+    DdpConst c{xg, w, u_ref, Q, R, Qf, wrap_mask};
+    return dispatch_bruteforce(n, m, B, N, T_max, A, Bm, X, U, u_batch_stride, c, lm_lambda, J_out, status, (cudaStream_t)stream);
 }
 
 int hop_backward_linesearch_f64(int B, int sys, const double* params_host, int N, const double* A, const double* Bm,

@@ -82,6 +82,39 @@ __global__ void __launch_bounds__(kBwWarps * 32) k_backward_warp(int B, int N, c
     }
 }
 
+// solver.py:293-358: one warp per (problem, T); J_out [B][T_max], status [B] (DDP_* code of the first failing horizon)
+template <int n, int m>
+__global__ void __launch_bounds__(kBwWarps * 32) k_bruteforce(int B, int N, int T_max, const double* A, const double* Bm,
+                                                              const double* X, const double* U, long ustride, DdpConst c,
+                                                              double lm, double* J_out, int* status) {
+    __shared__ __align__(16) double smem[kBwWarps * ddp::BwSmem<n, m>::SIZE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t id = (size_t)blockIdx.x * kBwWarps + warp;
+    if (id >= (size_t)B * T_max) return;
+    const int b = (int)(id / T_max), T = T_max - (int)(id % T_max);          // long horizons first
+    const ddp::CostConst cc = cost_const<n>(c, b);
+    double V0 = 0.0;
+    const int rc = ddp::bruteforce_one_T_warp<n, m>(A + (size_t)b * N * n * n, Bm + (size_t)b * N * n * m,
+                                                    X + (size_t)b * (N + 1) * n, U + (size_t)b * ustride, cc, T, lm, &V0,
+                                                    smem + (size_t)warp * ddp::BwSmem<n, m>::SIZE, lane);
+    if (lane == 0) {
+        J_out[(size_t)b * T_max + (T - 1)] = rc ? nan("") : V0;
+        if (rc) atomicMax(status + b, rc);
+    }
+}
+
+int dispatch_bruteforce(int n, int m, int B, int N, int T_max, const double* A, const double* Bm, const double* X, const double* U,
+                        long ustride, const DdpConst& c, double lm, double* J_out, int* status, cudaStream_t st) {
+    if (int rc = report_cuda(cudaMemsetAsync(status, 0, sizeof(int) * (size_t)B, st), "memset(status)")) return rc;
+    const size_t warps = (size_t)B * T_max;
+    const unsigned grid = (unsigned)((warps + kBwWarps - 1) / kBwWarps);
+    if (n == 2 && m == 1) k_bruteforce<2, 1><<<grid, kBwWarps * 32, 0, st>>>(B, N, T_max, A, Bm, X, U, ustride, c, lm, J_out, status);
+    else if (n == 4 && m == 1) k_bruteforce<4, 1><<<grid, kBwWarps * 32, 0, st>>>(B, N, T_max, A, Bm, X, U, ustride, c, lm, J_out, status);
+    else if (n == 12 && m == 4) k_bruteforce<12, 4><<<grid, kBwWarps * 32, 0, st>>>(B, N, T_max, A, Bm, X, U, ustride, c, lm, J_out, status);
+    else { set_last_error("hop_bruteforce_jt_f64: (n, m) not instantiated; supported: (2,1) (4,1) (12,4)"); return HOP_E_UNSUPPORTED_DIMS; }
+    return check_launch("k_bruteforce");
+}
+
 template <int SYS>
 __global__ void k_linesearch(int B, DynParams2 prm, int N, const double* X, const double* U, DdpConst c, const int* T,
                              const double* k_list, const double* K_list, const int* ok, const int* done, double* Xn,

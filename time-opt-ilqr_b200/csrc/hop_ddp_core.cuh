@@ -428,6 +428,143 @@ HOP_DEVICE int backward_pass_warp(const double* A, const double* Bm, const doubl
     return DDP_OK;
 }
 
+// ---- brute-force J(T) comparator ---------------------------------------------------------------------------
+// solver.py:293-358 bruteforce_all_Jt_backward_expansion for ONE horizon T: a full Riccati sweep T -> 0 that also
+// carries the constant term V0; J(T) = V0[0] (it already contains w T).  One warp per (problem, T), same shared-memory
+// layout and element-per-lane products as backward_pass_warp.  It is the reference's baseline-1 *method*, kept here as
+// an independent on-device check of the propagator curve (O(T^2 n^3) per problem against the propagator's O(T n^3)).
+template <int n, int m>
+HOP_DEVICE int bruteforce_one_T_warp(const double* A, const double* Bm, const double* X, const double* U, const CostConst& c,
+                                     int T, double lm, double* V0_out, double* sm, int lane) {
+    using S = BwSmem<n, m>;
+    double *Vxx = sm + S::VXX, *Ak = sm + S::AK, *Bk = sm + S::BK, *AtV = sm + S::ATV, *t = sm + S::TT, *Qxx = sm + S::QXX;
+    double *BtV = sm + S::BTV, *Qux = sm + S::QUX, *iQux = sm + S::KK, *Quu = sm + S::QUU;
+    double *Vx = sm + S::VX, *Qx = sm + S::QX, *Vxn = sm + S::VXN, *e = sm + S::EV, *Qu = sm + S::QU, *iQu = sm + S::KAP, *du = sm + S::DU;
+    double *lx = sm + S::KTQ, *lu = sm + S::KTQ + n;                            // (KtQuu is not needed here)
+    if (lane < n) {
+        double v = sub(X[(size_t)T * n + lane], c.xg[lane]);
+        if ((c.wrap_mask >> lane) & 1u) v = wrap_pi(v);
+        e[lane] = v;
+    }
+    simt::sync();
+    if (lane < n) {
+        double s = 0.0;
+        for (int j = 0; j < n; ++j) s = add(s, mul(c.Qf[lane * n + j], e[j]));
+        Vx[lane] = s;                                                           // Vx[T] = Qf e_T
+    }
+    for (int q = lane; q < n * n; q += 32) {
+        const int i = q / n, j = q % n;
+        Vxx[q] = 0.5 * add(c.Qf[i * n + j], c.Qf[j * n + i]);                   // Vxx[T] = sym(Qf)
+    }
+    simt::sync();
+    double V0 = 0.0;
+    if (lane == 0) {
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) acc = add(acc, mul(e[i], Vx[i]));           // e_T . (Qf e_T)
+        V0 = mul(0.5, acc);
+    }
+    for (int k = T - 1; k >= 0; --k) {
+        simt::sync();
+        for (int q = lane; q < n * n; q += 32) Ak[q] = A[(size_t)k * n * n + q];
+        for (int q = lane; q < n * m; q += 32) Bk[q] = Bm[(size_t)k * n * m + q];
+        if (lane < n) {
+            double v = sub(X[(size_t)k * n + lane], c.xg[lane]);
+            if ((c.wrap_mask >> lane) & 1u) v = wrap_pi(v);
+            e[lane] = v;
+        } else if (lane < n + m) {
+            du[lane - n] = sub(U[(size_t)k * m + (lane - n)], c.u_ref[lane - n]);
+        }
+        simt::sync();
+        if (lane < n) {
+            const int i = lane;
+            double a = 0.0, s = 0.0;
+            for (int j = 0; j < n; ++j) a = add(a, mul(c.Q[i * n + j], e[j]));  // lx = Q e
+            for (int l = 0; l < n; ++l) s = add(s, mul(Ak[l * n + i], Vx[l]));
+            lx[i] = a;
+            Qx[i] = add(a, s);
+        } else if (lane < n + m) {
+            const int i = lane - n;
+            double a = 0.0, s = 0.0;
+            for (int j = 0; j < m; ++j) a = add(a, mul(c.R[i * m + j], du[j])); // lu = R du
+            for (int l = 0; l < n; ++l) s = add(s, mul(Bk[l * m + i], Vx[l]));
+            lu[i] = a;
+            Qu[i] = add(a, s);
+        }
+        for (int q = lane; q < n * n; q += 32) {
+            const int i = q / n, j = q % n;
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = add(s, mul(Ak[l * n + i], Vxx[l * n + j]));
+            AtV[q] = s;
+        }
+        for (int q = lane; q < m * n; q += 32) {
+            const int i = q / n, j = q % n;
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = add(s, mul(Bk[l * m + i], Vxx[l * n + j]));
+            BtV[q] = s;
+        }
+        simt::sync();
+        for (int q = lane; q < n * n; q += 32) {
+            const int i = q / n, j = q % n;
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = add(s, mul(AtV[i * n + l], Ak[l * n + j]));
+            Qxx[q] = add(c.Q[q], s);
+        }
+        for (int q = lane; q < m * m; q += 32) {
+            const int i = q / m, j = q % m;
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = add(s, mul(BtV[i * n + l], Bk[l * m + j]));
+            Quu[q] = add(c.R[q], s);
+        }
+        for (int q = lane; q < m * n; q += 32) {
+            const int i = q / n, j = q % n;
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = add(s, mul(BtV[i * n + l], Ak[l * n + j]));
+            Qux[q] = s;
+        }
+        double l0 = 0.0;
+        if (lane == 0) {                                                        // 0.5 e.(Q e) + 0.5 du.(R du) + w
+            double a = 0.0, b = 0.0;
+            for (int i = 0; i < n; ++i) a = add(a, mul(e[i], lx[i]));
+            for (int i = 0; i < m; ++i) b = add(b, mul(du[i], lu[i]));
+            l0 = add(add(mul(0.5, a), mul(0.5, b)), c.w);
+        }
+        simt::sync();
+        double Qreg[m * m];
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) Qreg[i * m + j] = add(0.5 * add(Quu[i * m + j], Quu[j * m + i]), (i == j) ? lm : 0.0);
+        int rc = chol_solve_warp<m, 1>(Qreg, Qu, iQu, 1e-9, 8, lane);
+        if (rc) return rc;
+        rc = chol_solve_warp<m, n>(Qreg, Qux, iQux, 1e-9, 8, lane);
+        if (rc) return rc;
+        simt::sync();
+        if (lane < n) {
+            const int i = lane;
+            double s = 0.0;
+            for (int l = 0; l < m; ++l) s = add(s, mul(Qux[l * n + i], iQu[l]));
+            Vxn[i] = sub(Qx[i], s);                                             // Vx = Qx - Qux^T invQuuQu
+        }
+        for (int q = lane; q < n * n; q += 32) {
+            const int i = q / n, j = q % n;
+            double s = 0.0;
+            for (int l = 0; l < m; ++l) s = add(s, mul(Qux[l * n + i], iQux[l * n + j]));
+            t[q] = sub(Qxx[q], s);
+        }
+        if (lane == 0) {
+            double qq = 0.0;
+            for (int l = 0; l < m; ++l) qq = add(qq, mul(Qu[l], iQu[l]));
+            V0 = sub(add(l0, V0), mul(0.5, qq));                                // V0 = l0 + V0 - 0.5 Qu.invQuuQu
+        }
+        simt::sync();
+        for (int q = lane; q < n * n; q += 32) {
+            const int i = q / n, j = q % n;
+            Vxx[q] = 0.5 * add(t[i * n + j], t[j * n + i]);
+        }
+        if (lane < n) Vx[lane] = Vxn[lane];
+    }
+    if (lane == 0) *V0_out = V0;
+    return DDP_OK;
+}
+
 // solver.py:233-286, alphas = (1, .5, .25, .1, .05).  Writes the accepted candidate (or a copy of the
 // nominal when nothing improved) into X_new / U_new.
 template <int SYS>

@@ -125,8 +125,21 @@ def forward_linesearch_fixedT(F, X, U, xg, u_ref, Q, R, alpha, w: float, T_star:
     return Xn[0].cpu().numpy(), Un[0].cpu().numpy(), float(Jn[0]), True
 
 
-def bruteforce_all_Jt_backward_expansion(*_a, **_k):
-    raise NotImplementedError("brute-force J(T) (baseline1) is the CPU comparator, not part of the B200 hot path")
+def bruteforce_all_Jt_backward_expansion(A_list, B_list, X, U, xg, u_ref, Q, R, alpha, w: float, T_max: int, *,
+                                         lm_lambda: float = 1e-6, wrap_idx: Optional[List[int]] = None,
+                                         extra_stage_cost=None) -> np.ndarray:
+    """Exact J(T) curve under the iLQR quadratic model (solver.py:293-358), one warp per horizon on the device.
+    The baseline-1 *solver* (method="bruteforce") stays out of scope; this curve is kept as an independent check."""
+    if extra_stage_cost is not None:
+        raise NotImplementedError("extra_stage_cost is not supported on the B200 path")
+    X, U = np.asarray(X, float), np.asarray(U, float).reshape(len(U), -1)
+    case = list(_cost_case(X, U, xg, u_ref, Q, R, alpha, w))
+    case[11] = list(wrap_idx or [])
+    N = len(A_list)
+    J, st = api.bruteforce_all_Jt_batched(tuple(case), dev(stack(A_list)[None]), dev(stack(B_list)[None]), dev(X[None, :N + 1]),
+                                          dev(U[None, :N]), T_max=int(T_max), lm_lambda=lm_lambda)
+    raise_status(int(st[0]), "chol_solve(A)")
+    return J[0].cpu().numpy()
 
 
 def ilqr_timeopt(F, x0, xg, u_ref, Q, R, alpha, w: float, N: int, T_min: int, T_max: int, *, U_init=None,

@@ -34,6 +34,7 @@ SIGNATURES = {
                                      _vp, _vp]),
     "hop_build_terminal_f64": (_i, [_i, _i, _i, _vp, _vp, _vp, _u, _d, _vp, _vp]),
     "hop_cost_f64": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u, _vp, _vp, _vp]),
+    "hop_bruteforce_jt_f64": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _u, _d, _vp, _vp, _vp]),
     "hop_backward_linesearch_f64": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u, _vp, _vp,
                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hop_linesearch_f64": (_i, [_i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -346,6 +346,28 @@ def cost_timeopt_true_batched(case, X, U, T_star, xg=None, w=None) -> torch.Tens
     return J
 
 
+def bruteforce_all_Jt_batched(case, A, Bm, X, U, T_max: Optional[int] = None, lm_lambda: float = 1e-6, xg=None, w=None):
+    """solver.bruteforce_all_Jt_backward_expansion over a batch: (J [B, T_max] with J[b, T-1] = V0[0] of a Riccati sweep
+    T -> 0, status [B]).  O(T_max^2 n^3) per instance: a comparator / cross-check, not the selection path."""
+    lib = _cabi.require_device()
+    X = _dev(X)
+    dev = X.device
+    A, Bm, U = _dev(A, dev), _dev(Bm, dev), _dev(U, dev)
+    Bsz = X.shape[0]
+    c = _case_consts(case, Bsz, dev, xg, w)
+    N = A.shape[1]
+    T_max = N if T_max is None else int(T_max)
+    ustride = 0 if U.dim() == 2 else N * c["m"]
+    J = torch.empty((Bsz, T_max), dtype=torch.float64, device=dev)
+    st = torch.empty(Bsz, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.hop_bruteforce_jt_f64(Bsz, N, c["n"], c["m"], T_max, _ptr(A), _ptr(Bm), _ptr(X), _ptr(U), ustride, _ptr(c["xg"]),
+                                       _ptr(c["w"]), _ptr(c["u_ref"]), _ptr(c["Q"]), _ptr(c["R"]), _ptr(c["Qf"]), c["wrap"],
+                                       float(lm_lambda), _ptr(J), _ptr(st), _stream(dev))
+    _cabi.check(rc, "hop_bruteforce_jt_f64")
+    return J, st
+
+
 def backward_linesearch_batched(case, A, Bm, X, U, T_star, lm, xg=None, w=None):
     """solver.backward_pass_truncated + forward_linesearch_fixedT over a batch.
     Returns dict(k, K, ok, err, X_new, U_new, J_new, accepted)."""
