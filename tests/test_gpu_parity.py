@@ -173,8 +173,8 @@ def test_pipeline_linearisation_with_f0_from_rollout_is_bit_identical():
 
 def test_quadrotor_fd_kernels_agree_bit_for_bit():
     """Three implementations of linearize_forward_diff_traj for the quadrotor (thread per step with compile-time
-    sparsity, lane per column with shared trigonometry, generic) must produce identical bits, on hover-like and on
-    aggressive random states, with and without f0 taken from a consistent rollout, guards included."""
+    sparsity, lane per column with shared trigonometry, generic) and two of linearize_central_diff_traj must produce
+    identical bits, on hover-like and on aggressive random states, guards included."""
     from hop import _cabi
     lib = _cabi.require_device()
     case = cases.make_case("Quadrotor", N=128)
@@ -193,13 +193,14 @@ def test_quadrotor_fd_kernels_agree_bit_for_bit():
         for variant in (0, 1, 2):
             lib.hop_test_set_linearize_variant(variant)
             A, Bm = api.linearize_batched(F, X, _t(U))
-            out[variant] = (A.cpu().numpy(), Bm.cpu().numpy())
+            Ac, Bc = api.linearize_batched(F, X, _t(U), central=True)      # (variant 1 has no central form: generic kernel)
+            out[variant] = (A.cpu().numpy(), Bm.cpu().numpy(), Ac.cpu().numpy(), Bc.cpu().numpy())
     finally:
         lib.hop_test_set_linearize_variant(0)
-    assert np.isfinite(out[2][0]).mean() > 0.5
+    assert np.isfinite(out[2][0]).mean() > 0.5 and np.isfinite(out[2][2]).mean() > 0.5
     for variant in (0, 1):
-        assert np.array_equal(out[variant][0], out[2][0], equal_nan=True), variant
-        assert np.array_equal(out[variant][1], out[2][1], equal_nan=True), variant
+        for q in range(4):
+            assert np.array_equal(out[variant][q], out[2][q], equal_nan=True), (variant, q)
     # a structurally independent entry is an exact zero, as in the reference ((F_i - F_i) / h)
     fin = np.isfinite(out[0][0][:, :, 0, 0])
     assert (out[0][0][:, :, 9, 0][fin] == 0.0).all()

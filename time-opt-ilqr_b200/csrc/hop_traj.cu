@@ -233,48 +233,59 @@ __host__ __device__ constexpr unsigned quad_affects(int c) {
          : c == 12 ? 0x038u : c == 13 ? 0x200u : c == 14 ? 0x400u : 0x800u;   // thrust -> v rows; torques -> their w row
 }
 
+// one perturbed evaluation F(x + dv e_C, u) (or u + dv e_{C-n}); *bad = the reference's guards returned NaN(12)
 template <int C>
-__device__ __forceinline__ void quad_fd_column(const double* p, const double* x0v, const double* u0v, const QuadTrig& Tb,
-                                               const double* f0, bool nanout, double ss_sqrt, double epsx, double epsu,
-                                               double relx, double relu, double* col) {
+__device__ __forceinline__ void quad_fd_eval(const double* p, const double* x0v, const double* u0v, const QuadTrig& Tb, double vp,
+                                             double dist, double ss_sqrt, double* fp, bool* bad_out) {
     constexpr int n = 12, m = 4;
-    constexpr unsigned aff = quad_affects(C);
     double x[n], u[m];
 #pragma unroll
     for (int i = 0; i < n; ++i) x[i] = x0v[i];
 #pragma unroll
     for (int i = 0; i < m; ++i) u[i] = u0v[i];
-    const double base = C < n ? x0v[C < n ? C : 0] : u0v[C >= n ? C - n : 0];
-    const double h = C < n ? fmax(epsx, mul(relx, fmax(1.0, fabs(base)))) : fmax(epsu, mul(relu, fmax(1.0, fabs(base))));
-    const double vp = add(base, h);
     if (C < n) x[C < n ? C : 0] = vp; else u[C >= n ? C - n : 0] = vp;
     QuadTrig T = Tb;
     if (C == 6) sincos(vp, &T.sph, &T.cph);
     if (C == 7) { sincos(vp, &T.sth, &T.cth); T.tth = tan(vp); }
     if (C == 8) sincos(vp, &T.sps, &T.cps);
-    // guards (systems.py:175-191).  The norm test can only change if the unperturbed norm is within h of the limit:
-    // ||x + h e_c|| <= ||x|| + h.  Otherwise evaluate it exactly (cold).
+    // guards (systems.py:175-191).  The norm test can only change if the unperturbed norm is within |dv| of the limit:
+    // ||x + dv e_c|| <= ||x|| + |dv|.  Otherwise evaluate it exactly (cold).
     bool bad = !isfinite(vp);
-    if (C < n) {
-        if (ss_sqrt + 1.0000001 * h + 1e-9 * ss_sqrt >= p[13]) bad = bad || quad_guard(p, x, u);
-        if (C >= 9) bad = bad || (fabs(vp) > p[12]);
-    }
-    if (C == 7) bad = bad || (fabs(T.cth) < p[11]);
-    double fp[n];
+    if (C < n && ss_sqrt + 1.0000001 * dist + 1e-9 * ss_sqrt >= p[13]) bad = bad || quad_guard(p, x, u);
+    bad = bad || (fabs(T.cth) < p[11]);                                        // nominal pitch unless C == 7
+    bad = bad || (fabs(x[9]) > p[12]) || (fabs(x[10]) > p[12]) || (fabs(x[11]) > p[12]);   // nominal rates except coordinate C
     quad_core(p, x, u, T, fp);
-    const double rh = 1.0 / h;
+    *bad_out = bad;
+}
+
+// column C of [A_k | B_k]: forward (fp - f0) / h or central (fp - fm) / (2 h) differences (linearization.py:177-262)
+template <int C, bool CENTRAL>
+__device__ __forceinline__ void quad_fd_column(const double* p, const double* x0v, const double* u0v, const QuadTrig& Tb,
+                                               const double* f0, bool nanout, double ss_sqrt, double epsx, double epsu,
+                                               double relx, double relu, double* col) {
+    constexpr int n = 12;
+    constexpr unsigned aff = quad_affects(C);
+    const double base = C < n ? x0v[C < n ? C : 0] : u0v[C >= n ? C - n : 0];
+    const double h = C < n ? fmax(epsx, mul(relx, fmax(1.0, fabs(base)))) : fmax(epsu, mul(relu, fmax(1.0, fabs(base))));
+    double fp[n], fm[n];
+    bool bad = false, badm = false;
+    quad_fd_eval<C>(p, x0v, u0v, Tb, add(base, h), h, ss_sqrt, fp, &bad);
+    if (CENTRAL) quad_fd_eval<C>(p, x0v, u0v, Tb, sub(base, h), h, ss_sqrt, fm, &badm);
+    const double den = CENTRAL ? mul(2.0, h) : h;
+    const double rh = 1.0 / den;
 #pragma unroll
     for (int i = 0; i < n; ++i) {
         double q = 0.0;
         if ((aff >> i) & 1u) {
-            const double d = sub(fp[i], f0[i]);
+            const double d = sub(fp[i], CENTRAL ? fm[i] : f0[i]);
             const double q0 = mul(d, rh);
-            q = fma(fma(-q0, h, d), rh, q0);
+            q = fma(fma(-q0, den, d), rh, q0);
         }
-        col[i] = (nanout || bad) ? nan("") : q;
+        col[i] = (nanout || bad || badm) ? nan("") : q;
     }
 }
 
+template <bool CENTRAL>
 __global__ void __launch_bounds__(128) k_linearize_quad_row(int B, DynParams prm, int N, const double* __restrict__ X,
                                                             const double* __restrict__ U, long ustride, double epsx, double epsu,
                                                             double relx, double relu, int f0_from_x, const int* __restrict__ skip,
@@ -295,26 +306,34 @@ __global__ void __launch_bounds__(128) k_linearize_quad_row(int B, DynParams prm
     for (int i = 0; i < n; ++i) x[i] = xs[i];
 #pragma unroll
     for (int i = 0; i < m; ++i) u[i] = us[i];
-    bool have_f0 = false;
-    if (f0_from_x) {
-        bool fin = true, finx = true;
-#pragma unroll
-        for (int i = 0; i < n; ++i) { f0[i] = xs[n + i]; fin = fin && isfinite(f0[i]); finx = finx && isfinite(x[i]); }
-        have_f0 = fin || !finx;       // see k_linearize_quad
-    }
-    if (!have_f0) {                     // cold; through copies so that x, u, f0 themselves never live in local memory
-        double xc[n], uc[m], fc[n];
-#pragma unroll
-        for (int i = 0; i < n; ++i) xc[i] = x[i];
-#pragma unroll
-        for (int i = 0; i < m; ++i) uc[i] = u[i];
-        quad_dynamics_cold(prm.p, xc, uc, fc);
-#pragma unroll
-        for (int i = 0; i < n; ++i) f0[i] = fc[i];
-    }
     bool nanout = false;
+    if (!CENTRAL) {
+        bool have_f0 = false;
+        if (f0_from_x) {
+            bool fin = true, finx = true;
 #pragma unroll
-    for (int i = 0; i < n; ++i) nanout = nanout || !isfinite(f0[i]);      // linearization.py:243-248
+            for (int i = 0; i < n; ++i) { f0[i] = xs[n + i]; fin = fin && isfinite(f0[i]); finx = finx && isfinite(x[i]); }
+            have_f0 = fin || !finx;       // see k_linearize_quad
+        }
+        if (!have_f0) {                     // cold; through copies so that x, u, f0 themselves never live in local memory
+            double xc[n], uc[m], fc[n];
+#pragma unroll
+            for (int i = 0; i < n; ++i) xc[i] = x[i];
+#pragma unroll
+            for (int i = 0; i < m; ++i) uc[i] = u[i];
+            quad_dynamics_cold(prm.p, xc, uc, fc);
+#pragma unroll
+            for (int i = 0; i < n; ++i) f0[i] = fc[i];
+        }
+#pragma unroll
+        for (int i = 0; i < n; ++i) nanout = nanout || !isfinite(f0[i]);      // linearization.py:243-248
+    } else {
+        // central differences never evaluate F at the nominal point; a non-finite nominal makes every evaluation NaN
+#pragma unroll
+        for (int i = 0; i < n; ++i) { f0[i] = 0.0; nanout = nanout || !isfinite(x[i]); }
+#pragma unroll
+        for (int i = 0; i < m; ++i) nanout = nanout || !isfinite(u[i]);
+    }
     // unperturbed trigonometry and norm, shared by all 16 columns
     QuadTrig T;
     sincos(x[6], &T.sph, &T.cph);
@@ -338,10 +357,10 @@ __global__ void __launch_bounds__(128) k_linearize_quad_row(int B, DynParams prm
 #define HOP_FD4(C0, OWN, PAIR, LDB)                                                                                       \
     {                                                                                                                     \
         double c0[n], c1[n], c2[n], c3[n];                                                                                \
-        quad_fd_column<C0 + 0>(prm.p, x, u, T, f0, nanout, nrm, epsx, epsu, relx, relu, c0);                              \
-        quad_fd_column<C0 + 1>(prm.p, x, u, T, f0, nanout, nrm, epsx, epsu, relx, relu, c1);                              \
-        quad_fd_column<C0 + 2>(prm.p, x, u, T, f0, nanout, nrm, epsx, epsu, relx, relu, c2);                              \
-        quad_fd_column<C0 + 3>(prm.p, x, u, T, f0, nanout, nrm, epsx, epsu, relx, relu, c3);                              \
+        quad_fd_column<C0 + 0, CENTRAL>(prm.p, x, u, T, f0, nanout, nrm, epsx, epsu, relx, relu, c0);                              \
+        quad_fd_column<C0 + 1, CENTRAL>(prm.p, x, u, T, f0, nanout, nrm, epsx, epsu, relx, relu, c1);                              \
+        quad_fd_column<C0 + 2, CENTRAL>(prm.p, x, u, T, f0, nanout, nrm, epsx, epsu, relx, relu, c2);                              \
+        quad_fd_column<C0 + 3, CENTRAL>(prm.p, x, u, T, f0, nanout, nrm, epsx, epsu, relx, relu, c3);                              \
         _Pragma("unroll") for (int i = 0; i < n; ++i) {                                                                   \
             /* even lane keeps (c0,c1) and sends (c2,c3); odd lane keeps (c2,c3) and sends (c0,c1) */                     \
             const double s0 = odd ? c0[i] : c2[i], s1 = odd ? c1[i] : c3[i];                                              \
@@ -378,16 +397,17 @@ static int launch_linearize(int B, const DynParams& prm, int N, const double* X,
     const size_t total = (size_t)B * N * P;
     const int threads = 128;
     const size_t grid = (total + threads - 1) / threads;
-    if (SYS == 2 && !central) {
-        // A/B + test switch: 0 (default) thread-per-step kernel, 1 lane-per-column kernel, 2 generic kernel
+    if (SYS == 2) {
+        // A/B + test switch: 0 (default) thread-per-step kernel, 1 lane-per-column kernel (forward only), 2 generic kernel
         const int variant = g_linearize_variant;
         if (variant == 0) {
             const size_t rows = (size_t)B * N;
-            k_linearize_quad_row<<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(
-                B, prm, N, X, U, ustride, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm);
+            const unsigned g = (unsigned)((rows + threads - 1) / threads);
+            if (central) k_linearize_quad_row<true><<<g, threads, 0, st>>>(B, prm, N, X, U, ustride, epsx, epsu, relx, relu, 0, skip, A, Bm);
+            else k_linearize_quad_row<false><<<g, threads, 0, st>>>(B, prm, N, X, U, ustride, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm);
             return check_launch("k_linearize_quad_row");
         }
-        if (variant == 1) {
+        if (variant == 1 && !central) {
             k_linearize_quad<<<(unsigned)grid, threads, 0, st>>>(B, prm, N, X, U, ustride, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm);
             return check_launch("k_linearize_quad");
         }
