@@ -7,6 +7,7 @@
 #include "hop_select_mma_body.cuh"
 #include "hop_select_pipe_body.cuh"
 #include "hop_select_scan_body.cuh"
+#include "hop_select_gpipe_body.cuh"
 
 namespace {
 template <int D, int M, int G>
@@ -154,6 +155,30 @@ int run_generic_scan(const hop::SelectArgs& p) {
 extern "C" int emul_select_generic_scan(int d, int m, const hop::SelectArgs* p) {
     if (d == 12 && m == 4) return run_generic_scan<12, 4>(*p);
     if (d == 13 && m == 4) return run_generic_scan<13, 4>(*p);
+    return -2;
+}
+
+// ---- pipelined LQR-boundary body (mirrors k_select_generic_pipe: pipelined sweep, sequential body as cold path)
+namespace {
+template <int D, int M>
+void gpipe_lane(void* a) {
+    auto* j = (MmaGenericJob<D, M>*)a;
+    if (hop::mma::select_generic_pipe_body<D, M>(*j->p, j->b, j->scratch)) return;
+    hop::mma::select_generic_body<D, M>(*j->p, j->b, j->scratch);
+}
+template <int D, int M>
+int run_generic_pipe(const hop::SelectArgs& p) {
+    std::vector<double> slab(hop::mma::GpipeSlab<D, M>::SIZE, -7.0);
+    for (int b = 0; b < p.B; ++b) {
+        MmaGenericJob<D, M> j{&p, b, slab.data()};
+        if (hop::simt::run_warp(gpipe_lane<D, M>, &j)) return -1;
+    }
+    return 0;
+}
+}  // namespace
+extern "C" int emul_select_generic_pipe(int d, int m, const hop::SelectArgs* p) {
+    if (d == 12 && m == 4) return run_generic_pipe<12, 4>(*p);
+    if (d == 13 && m == 4) return run_generic_pipe<13, 4>(*p);
     return -2;
 }
 

@@ -36,4 +36,9 @@ inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long l
     for (unsigned i = 0; i < bytes; ++i) d[i] = s[i];
 }
 inline void mbar_wait(unsigned long long*, unsigned) {}
+// cp.async stand-ins: the copy completes at issue time
+inline void cp_async8(void* dst, const void* src) { *(double*)dst = *(const double*)src; }
+inline void cp_async_commit() {}
+template <int N_>
+inline void cp_async_wait() {}
 }}  // namespace hop::simt

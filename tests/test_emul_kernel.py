@@ -125,3 +125,22 @@ def test_emulated_scan_mode_matches_sequential_sweep(d, m, N, T_max):
     assert np.array_equal(Tp, Ts) and np.allclose(Jsp, Jss, rtol=1e-9)
     Jo, _ = O.propagator_batch(A, B, Q, Rinv, z0, QT, T_use=T_max)
     assert rel(Jp, Jo) <= 1e-9
+
+
+@pytest.mark.parametrize("d,m,N", [(12, 4, 12), (13, 4, 16)])
+def test_emulated_pipelined_generic_kernel_matches_oracle_and_falls_back(d, m, N):
+    """Software-pipelined LQR-boundary body (hop_select_gpipe_body.cuh): three interleaved sweeps + a dual sweep per
+    step, elimination with right-hand side z0, cp.async staging.  Instance 1 needs the jitter ladder and the LU
+    fallback, instance 2 has a non-finite input: both must come out of the sequential cold path with its status word."""
+    A, B, Q, R, z0, w, QT = s2_batch(range(3), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    Q[1, 3] = np.diag(np.r_[np.ones(d - 1), -1e-4])       # ladder
+    QT[1, 5] = -np.eye(d)                                  # LU fallback
+    A[2, 4, 1, 1] = np.nan
+    J, T, Js, st = emul.select_generic(A, B, Q, Rinv, z0, QT, 1, N, w_explicit=w, pipe=True)
+    Jq, Tq, Jsq, stq = emul.select_generic(A, B, Q, Rinv, z0, QT, 1, N, w_explicit=w, mma=True)
+    Jo, sto = O.propagator_batch(A, B, Q, Rinv, z0, QT)
+    assert st[0] == 0 and st[1] == 0x300 and (st[2] & 0xFF) == 1 and sto[2] == 1
+    assert np.array_equal(st, stq)
+    assert rel(J[:2], Jo[:2]) <= 1e-9 and np.array_equal(J[1:], Jq[1:], equal_nan=True)
+    assert np.array_equal(T[:2], np.argmin(Jo[:2] + w[:2, None] * np.arange(1, N + 1), axis=1) + 1)

@@ -70,8 +70,10 @@ def test_select_fused_matches_reference_golden(name, traj, mode):
 
 @pytest.mark.parametrize("d,m,N,T_max", [(12, 4, 128, 128), (13, 4, 128, 128), (13, 4, 64, 61), (13, 4, 16, 5)])
 def test_scan_mode_matches_sequential_sweep_and_oracle(d, m, N, T_max):
-    """HOP_MODE_SCAN: chunked parallel scan over the horizon (one CTA of 8 warps per problem).  Chunk 0 is bit-identical to
-    the sequential sweep; later chunks differ by re-association only (well-conditioned S2: 1e-9, the north-star tolerance)."""
+    """HOP_MODE_SCAN: chunked parallel scan over the horizon (one CTA of 8 warps per problem).  Chunk 0 follows the sequential
+    sweep (bit-identical to the sequential body: tests/test_emul_kernel.py; the default kernel here is the pipelined one, whose
+    cost evaluation is an elimination instead of an inverse); later chunks differ by re-association only (well-conditioned
+    S2: 1e-9, the north-star tolerance)."""
     A, Bm, Q, R, z0, w, QT = s2_batch(range(7), d, m, N)
     Rinv = np.stack([O.chol_inv(r) for r in R])
     args = (_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, T_max)
@@ -80,7 +82,7 @@ def test_scan_mode_matches_sequential_sweep_and_oracle(d, m, N, T_max):
     Js, Jp = seq.J.cpu().numpy(), scan.J.cpu().numpy()
     Lc = -(-T_max // 8)
     assert not scan.status.cpu().numpy().any()
-    assert np.array_equal(Jp[:, :Lc], Js[:, :Lc])
+    assert rel(Jp[:, :Lc], Js[:, :Lc]) <= 1e-12
     assert rel(Jp, Js) <= 1e-9
     assert torch.equal(scan.T_star, seq.T_star)
     Jo, _ = O.propagator_batch(A, Bm, Q, Rinv, z0, QT, T_use=T_max)

@@ -11,6 +11,7 @@
 #include "hop_select_mma_body.cuh"
 #include "hop_select_pipe_body.cuh"
 #include "hop_select_scan_body.cuh"
+#include "hop_select_gpipe_body.cuh"
 #include "../../include/hop_b200.h"
 
 namespace hop {
@@ -128,6 +129,31 @@ static int launch_generic_scan(const SelectArgs& p, cudaStream_t st) {
     return check_launch("k_select_generic_scan");
 }
 
+// LQR-boundary form, software-pipelined (hop_select_gpipe_body.cuh); the sequential body is its cold path
+template <int D, int M>
+__device__ __noinline__ void select_generic_seq_cold(const SelectArgs& p, int b, double* scratch) {
+    mma::select_generic_body<D, M>(p, b, scratch);
+}
+template <int D, int M>
+__global__ void __launch_bounds__(kMmaWarps * 32, 2) k_select_generic_pipe(const SelectArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * kMmaWarps + warp;
+    if (b >= p.B) return;
+    double* slab = smem + (size_t)warp * mma::GpipeSlab<D, M>::SIZE;
+    if (mma::select_generic_pipe_body<D, M>(p, b, slab)) return;
+    select_generic_seq_cold<D, M>(p, b, slab);
+}
+template <int D, int M>
+static int launch_generic_pipe(const SelectArgs& p, cudaStream_t st) {
+    const size_t smem = sizeof(double) * (size_t)kMmaWarps * mma::GpipeSlab<D, M>::SIZE;
+    cudaError_t e = cudaFuncSetAttribute(k_select_generic_pipe<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return report_cuda(e, "cudaFuncSetAttribute(k_select_generic_pipe)");
+    const int grid = (p.B + kMmaWarps - 1) / kMmaWarps;
+    k_select_generic_pipe<D, M><<<grid, kMmaWarps * 32, smem, st>>>(p);
+    return check_launch("k_select_generic_pipe");
+}
+
 template <int D, int M>
 static int launch_generic_mma(const SelectArgs& p, cudaStream_t st) {
     const size_t smem = sizeof(double) * (size_t)kMmaWarps * mma::kWarpScratch;
@@ -171,8 +197,9 @@ int dispatch_select_generic(int d, int m, int mode, const SelectArgs& p, cudaStr
     if (d == 3 && m == 1) return launch_generic<3, 1, 4>(p, st);
     if (d == 4 && m == 2) return launch_generic<4, 2, 4>(p, st);
     if (d == 5 && m == 1) return launch_generic<5, 1, 8>(p, st);
-    if (d == 12 && m == 4) return launch_generic_mma<12, 4>(p, st);
-    if (d == 13 && m == 4) return launch_generic_mma<13, 4>(p, st);
+    static const bool gseq = getenv("HOP_GENERIC_SEQ") && atoi(getenv("HOP_GENERIC_SEQ")) != 0;   // A/B switch: sequential sweep
+    if (d == 12 && m == 4) return gseq ? launch_generic_mma<12, 4>(p, st) : launch_generic_pipe<12, 4>(p, st);
+    if (d == 13 && m == 4) return gseq ? launch_generic_mma<13, 4>(p, st) : launch_generic_pipe<13, 4>(p, st);
     set_last_error("hop_select_f64: (d, m) not instantiated; supported: (3,1) (4,2) (5,1) (12,4) (13,4)");
     return HOP_E_UNSUPPORTED_DIMS;
 }

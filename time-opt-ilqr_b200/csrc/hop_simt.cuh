@@ -44,6 +44,13 @@ HOP_DEVICE void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned lo
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
+// ---- cp.async (LDGSTS) in 8-byte granules: global -> shared without a register round trip, any 8-byte alignment
+HOP_DEVICE void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+HOP_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+HOP_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 HOP_DEVICE void mbar_wait(unsigned long long* bar, unsigned parity) {
     unsigned done;
     do {
