@@ -135,7 +135,7 @@ __device__ __noinline__ void select_generic_seq_cold(const SelectArgs& p, int b,
     mma::select_generic_body<D, M>(p, b, scratch);
 }
 template <int D, int M>
-__global__ void __launch_bounds__(kMmaWarps * 32, 2) k_select_generic_pipe(const SelectArgs p) {
+__global__ void __launch_bounds__(kMmaWarps * 32, 3) k_select_generic_pipe(const SelectArgs p) {
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5;
     const int b = blockIdx.x * kMmaWarps + warp;
