@@ -74,8 +74,8 @@ void mma_fused_lane(void* a) {
     auto* j = (MmaFusedJob<D, M>*)a;
     hop::mma::select_fused_body<D, M, MODE>(*j->p, j->b, j->scratch, j->cst);
 }
-template <int D, int M, bool LOOPED>
-void mma_pipe_lane(void* a) {   // mirrors k_select_fused_mma<.., MODE = 2 | 3>
+template <int D, int M, int LOOPED>
+void mma_pipe_lane(void* a) {   // mirrors k_select_fused_mma<.., MODE = 2 | 3 | 4> (SCHED 0 | 1 | 2)
     auto* j = (MmaFusedJob<D, M>*)a;
     if (hop::mma::select_fused_pipe_body<D, M, LOOPED>(*j->p, j->b, j->scratch, j->cst)) return;
     hop::mma::select_fused_body<D, M, 1>(*j->p, j->b, j->scratch, j->cst);
@@ -97,7 +97,7 @@ int run_fused_mma(const hop::FusedArgs& p) {
     if (p.mode >= 2) hop::mma::pipe_const_fill<D, M>(cst.data(), 0, 1);
     for (int b = 0; b < p.B; ++b) {
         MmaFusedJob<D, M> j{&p, b, scratch.data(), cst.data()};
-        auto fn = p.mode == 3 ? mma_pipe_lane<D, M, true> : p.mode == 2 ? mma_pipe_lane<D, M, false>
+        auto fn = p.mode == 4 ? mma_pipe_lane<D, M, 2> : p.mode == 3 ? mma_pipe_lane<D, M, 1> : p.mode == 2 ? mma_pipe_lane<D, M, 0>
                                 : (p.mode == 1 ? mma_fused_lane<D, M, 1> : mma_fused_lane<D, M, 0>);
         if (hop::simt::run_warp(fn, &j)) return -1;
     }

@@ -48,7 +48,8 @@ struct PipeSlab {
     static constexpr int EV = 0, QE = 16, PE = 32, YQ = 48, YP = 80, DU = 112;
     static constexpr int STAGE = 128;             // 2 x kStage staging buffers
     static constexpr int BARS = STAGE + 2 * kStage;
-    static constexpr int SIZE = BARS + 2;
+    static constexpr int ROWB = (BARS + 2 + 1) & ~1;   // pivot row / column exchange: [2 parities][3 matrices][16]
+    static constexpr int SIZE = ROWB + 2 * 3 * 16;
 };
 static_assert(PipeSlab::SIZE <= kWarpScratch, "the pipelined body reuses the sequential body's per-warp slab");
 
@@ -173,6 +174,115 @@ HOP_DEVICE void fe_pivot_lower(Mat& a, int tj, const LaneGeo& L, int& signs, dou
 #pragma unroll
     for (int s = 0; s < 2; ++s) a.v[1][1][s] = fma(-f[1], pr[1][s], a.v[1][1][s]);
 }
+// ---- pivot exchange through shared memory -----------------------------------------------------------------
+// The shuffle exchange costs 14 SHFL.32 per pivot and matrix (7 doubles); the sweeps are issue bound (ncu r1e), so the
+// exchange goes through a 16-double row buffer instead: the 4 lanes that own pivot row j store it (2 x STS.128), one
+// __syncwarp per pivot ROUND (three matrices), and every lane fetches its 4 column values (2 x LDS.128), its 2 row
+// values (1 x LDS.128) and the pivot (1 x LDS.64): 18 shared-memory instructions per round instead of 39 shuffles.
+// Buffer position of column c:  pos(c) = 4 (c & 3) + 2 ((c >> 2) & 1) + (c >> 3), so that a lane's own four columns
+// {t, t+4, t+8, t+12} and its own two rows {rho(g), rho(g)+8} are contiguous, 16-byte aligned runs (4t.., 2g..).
+// To take the column from the ROW the sweep must keep the matrix symmetric: this is the symmetric sweep operator
+// (row AND column scaled by +1/p, pivot -> -1/p), which turns A into -A^-1; it is applied to -S, whose pivots are
+// negative, and returns S^-1.  Same rank-1 update and same folded fix-ups as gj_pivot (pr' = -1 instead of +1).
+HOP_DEVICE void st2(double* p, double a, double b) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<double2*>(p) = make_double2(a, b);
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
+HOP_DEVICE void ld2(const double* p, double& a, double& b) {
+#if defined(__CUDA_ARCH__)
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    a = v.x; b = v.y;
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+template <int GI>
+HOP_DEVICE void gjs_store(const Mat& a, double* buf, bool isrow, int t) {      // pivot row: lanes g == gj
+    if (isrow) {
+        st2(buf + 4 * t, a.v[GI][0][0], a.v[GI][1][0]);
+        st2(buf + 4 * t + 2, a.v[GI][0][1], a.v[GI][1][1]);
+    }
+}
+template <int GI, int GS>
+HOP_DEVICE void fes_store(const Mat& a, double* buf, bool iscol, int g) {      // pivot COLUMN (lower tiles): lanes t == tj
+    if (iscol) st2(buf + 2 * g, a.v[0][GI][GS], a.v[1][GI][GS]);
+}
+template <int D, int GI, int GS>
+HOP_DEVICE void gjs_apply(Mat& a, int tj, const LaneGeo& L, int& signs, const double* buf, bool isrow, bool iscol) {
+    double pr[2][2], f[2];
+    ld2(buf + 4 * L.t, pr[0][0], pr[1][0]);
+    ld2(buf + 4 * L.t + 2, pr[0][1], pr[1][1]);
+    ld2(buf + 2 * L.g, f[0], f[1]);
+    const double p = buf[4 * tj + 2 * GS + GI];
+    signs |= ~hi_word(p);                                        // pivots of -S must be negative
+    const double rinv = pivot_rcp3(p);
+    f[0] *= rinv;
+    f[1] *= rinv;
+    if (iscol) {
+        a.v[0][GI][GS] = 0.0;
+        a.v[1][GI][GS] = 0.0;
+        pr[GI][GS] = -1.0;
+    }
+    if (isrow) {
+#pragma unroll
+        for (int J = 0; J < 2; ++J)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) a.v[GI][J][s] = 0.0;
+        f[GI] = -rinv;
+    }
+    HOP_FOR_ELEMS(I, J, s) a.v[I][J][s] = fma(-f[I], pr[J][s], a.v[I][J][s]);
+}
+template <int D, int GI, int GS>
+HOP_DEVICE void fes_apply(Mat& a, int tj, const LaneGeo& L, int& signs, double& p, const double* buf) {
+    p = buf[4 * tj + 2 * GS + GI];
+    signs |= hi_word(p);
+    if (8 * GI + 4 * GS + tj == D - 1) return;
+    const double rinv = pivot_rcp3(p);
+    double pr[2][2], f[2];
+    ld2(buf + 4 * L.t, pr[0][0], pr[1][0]);
+    ld2(buf + 4 * L.t + 2, pr[0][1], pr[1][1]);
+    ld2(buf + 2 * L.g, f[0], f[1]);
+    f[0] *= rinv;
+    f[1] *= rinv;
+    if (GI == 0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) a.v[0][0][s] = fma(-f[0], pr[0][s], a.v[0][0][s]);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) a.v[1][0][s] = fma(-f[1], pr[0][s], a.v[1][0][s]);
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) a.v[1][1][s] = fma(-f[1], pr[1][s], a.v[1][1][s]);
+}
+// one pivot round of the three sweeps; a1, a2 hold NEGATED matrices (see above), x the lower tiles of X0 + eps I
+template <int D, int GI, int GS>
+HOP_DEVICE void gj3s_round(Mat& a1, Mat& a2, Mat& x, int tj, const LaneGeo& L, int& signs, double& p, double* rowb) {
+    const int gj = 2 * tj + GS;
+    const bool isrow = (L.g == gj), iscol = (L.t == tj);
+    double* buf = rowb + (tj & 1) * 48;
+    gjs_store<GI>(a1, buf, isrow, L.t);
+    gjs_store<GI>(a2, buf + 16, isrow, L.t);
+    fes_store<GI, GS>(x, buf + 32, iscol, L.g);
+    simt::sync();
+    gjs_apply<D, GI, GS>(a1, tj, L, signs, buf, isrow, iscol);
+    gjs_apply<D, GI, GS>(a2, tj, L, signs, buf + 16, isrow, iscol);
+    fes_apply<D, GI, GS>(x, tj, L, signs, p, buf + 32);
+}
+template <int D, int GI, int GS, bool UNROLL>
+HOP_DEVICE void gj3s_group(Mat& a1, Mat& a2, Mat& x, const LaneGeo& L, int& signs, double& p, double* rowb) {
+    constexpr int first = 8 * GI + 4 * GS;
+    constexpr int cnt = (D - first) < 4 ? (D - first) : 4;
+    if (UNROLL) {
+#pragma unroll
+        for (int tj = 0; tj < cnt; ++tj) gj3s_round<D, GI, GS>(a1, a2, x, tj, L, signs, p, rowb);
+    } else {
+#pragma unroll 1
+        for (int tj = 0; tj < cnt; ++tj) gj3s_round<D, GI, GS>(a1, a2, x, tj, L, signs, p, rowb);
+    }
+}
+
 // the three interleaved sweeps over the pivots of group (GI, GS); UNROLL = false keeps tj a run-time loop
 template <int D, int GI, int GS, bool UNROLL>
 HOP_DEVICE void gj3_group(Mat& a1, Mat& a2, Mat& x, const LaneGeo& L, int& signs, double& p) {
@@ -258,7 +368,8 @@ HOP_DEVICE void rank1_add(Mat& Dm, const double (&r)[2], const double (&c)[2][2]
 // tiles keeps it (error at T* 8e-8 instead of 4e-10 on the S1 goldens).  X0 only feeds pivots and is fine.
 
 // Returns true when the problem was solved by the pipelined sweep; false => caller must run the sequential body.
-template <int D, int M, bool LOOPED>
+// SCHED 0: unrolled sweep, shuffle exchange; 1: looped sweep, shuffle exchange; 2: looped sweep, shared-memory exchange
+template <int D, int M, int SCHED>
 HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratch, const double* cst) {
     using FC = FusedConst<D, M>;
     using XC = FastConst<D, M>;
@@ -266,6 +377,8 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
     using PS = PipeSlab;
     constexpr int n = D - 1;
     constexpr int NT = (D + 7) / 8, KB = (D + 3) / 4, KBM = (M + 3) / 4, NTM = (M + 7) / 8;
+    constexpr bool LOOPED = (SCHED != 0), SMX = (SCHED == 2);
+    double* rowb = scratch + PipeSlab::ROWB;
     constexpr bool R1 = LastCol<D>::split;          // last k-block as a rank-1 DFMA update
     constexpr int KD = R1 ? KB - 1 : KB;            // k-blocks left on the tensor pipe
     static_assert(D > 8 && D <= 16 && n <= 16 && M <= 4, "one-problem-per-warp mapping: 9 <= d <= 16, m <= 4");
@@ -473,8 +586,10 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
             closed_inverse(Wt, KF2, scratch + PS::YP + q1 * 16, rsp);           // X_t = chol_inv(QT_t), t = k+1     (:79)
             HOP_FOR_ELEMS(I, J, s) {
                 const double dg = (I == J && L.row(I) == L.col(J, s) && L.row(I) < D) ? p.jitter : 0.0;
-                W.v[I][J][s] = (W.v[I][J][s] + P.gb.v[I][J][s]) + dg;          // E_{k+1} + Gbar_k (+ eps I)        (:72)
-                Wt.v[I][J][s] = (Wt.v[I][J][s] + P.gb.v[I][J][s]) + dg;        // X_t + Gbar_k (+ eps I)            (:82)
+                const double s1 = (W.v[I][J][s] + P.gb.v[I][J][s]) + dg;       // E_{k+1} + Gbar_k (+ eps I)        (:72)
+                const double s2 = (Wt.v[I][J][s] + P.gb.v[I][J][s]) + dg;      // X_t + Gbar_k (+ eps I)            (:82)
+                W.v[I][J][s] = SMX ? -s1 : s1;                                 // (the symmetric sweep inverts -S)
+                Wt.v[I][J][s] = SMX ? -s2 : s2;
                 if (I == J) X0.v[I][J][s] += dg;                               // X0_{t-1} + eps I                  (:84)
             }
         }
@@ -483,13 +598,23 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
         static_assert(D > 12, "the phase placement below assumes four pivot groups");
         vecA(V, k + 2, xcur, ucur);
         int signs = 0;
-        gj3_group<D, 0, 0, !LOOPED>(W, Wt, X0, L, signs, piv);
-        vecB(V);
-        gj3_group<D, 0, 1, !LOOPED>(W, Wt, X0, L, signs, piv);
-        vecC(V, k + 2);
-        gj3_group<D, 1, 0, !LOOPED>(W, Wt, X0, L, signs, piv);
-        vecD(V, do_vec);
-        gj3_group<D, 1, 1, !LOOPED>(W, Wt, X0, L, signs, piv);
+        if (SMX) {
+            gj3s_group<D, 0, 0, false>(W, Wt, X0, L, signs, piv, rowb);
+            vecB(V);
+            gj3s_group<D, 0, 1, false>(W, Wt, X0, L, signs, piv, rowb);
+            vecC(V, k + 2);
+            gj3s_group<D, 1, 0, false>(W, Wt, X0, L, signs, piv, rowb);
+            vecD(V, do_vec);
+            gj3s_group<D, 1, 1, false>(W, Wt, X0, L, signs, piv, rowb);
+        } else {
+            gj3_group<D, 0, 0, !LOOPED>(W, Wt, X0, L, signs, piv);
+            vecB(V);
+            gj3_group<D, 0, 1, !LOOPED>(W, Wt, X0, L, signs, piv);
+            vecC(V, k + 2);
+            gj3_group<D, 1, 0, !LOOPED>(W, Wt, X0, L, signs, piv);
+            vecD(V, do_vec);
+            gj3_group<D, 1, 1, !LOOPED>(W, Wt, X0, L, signs, piv);
+        }
         bad = bad || (signs < 0) || pivot_bad(piv);                             // piv: last pivot of X0_{t-1} (or of I at k = 0)
         if (simt::ballot(bad) != 0u) return bail(k + 2 < p.T_max ? k + 2 : -1);
         if (k > 0 && L.lane == 0) {                                            // J(t-1) = 0.5 / pivot_n  (z0 = e_n, :85)
@@ -566,12 +691,20 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
             if (I == J && L.row(I) == L.col(J, s) && L.row(I) < D) X0.v[I][J][s] += p.jitter;
         double piv = 0.0;
         Mat d1, d2;                                                            // dummies: the sweep is shared with the main loop
-        HOP_FOR_ELEMS(I, J, s) d1.v[I][J][s] = d2.v[I][J][s] = (L.row(I) == L.col(J, s)) ? 1.0 : 0.0;
+        HOP_FOR_ELEMS(I, J, s) d1.v[I][J][s] = d2.v[I][J][s] = (L.row(I) == L.col(J, s)) ? (SMX ? -1.0 : 1.0) : 0.0;
         int signs = 0;
-        gj3_group<D, 0, 0, false>(d1, d2, X0, L, signs, piv);
-        gj3_group<D, 0, 1, false>(d1, d2, X0, L, signs, piv);
-        gj3_group<D, 1, 0, false>(d1, d2, X0, L, signs, piv);
-        gj3_group<D, 1, 1, false>(d1, d2, X0, L, signs, piv);
+        if (SMX) {
+            simt::sync();
+            gj3s_group<D, 0, 0, false>(d1, d2, X0, L, signs, piv, rowb);
+            gj3s_group<D, 0, 1, false>(d1, d2, X0, L, signs, piv, rowb);
+            gj3s_group<D, 1, 0, false>(d1, d2, X0, L, signs, piv, rowb);
+            gj3s_group<D, 1, 1, false>(d1, d2, X0, L, signs, piv, rowb);
+        } else {
+            gj3_group<D, 0, 0, false>(d1, d2, X0, L, signs, piv);
+            gj3_group<D, 0, 1, false>(d1, d2, X0, L, signs, piv);
+            gj3_group<D, 1, 0, false>(d1, d2, X0, L, signs, piv);
+            gj3_group<D, 1, 1, false>(d1, d2, X0, L, signs, piv);
+        }
         bad = bad || (signs < 0) || pivot_bad(piv);
         if (simt::ballot(bad) != 0u) return bail(-1);
         if (L.lane == 0) {
