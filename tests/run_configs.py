@@ -3,8 +3,8 @@
 (device time, throughput, parity against the CPU oracle on a bounded sample).  These are the parity / scale cases
 around the headline workload that bench.py times; nothing here feeds bench.py.
 
-  python tools/run_configs.py [--configs 1,2,3,4,5] [--small]
-  torchrun --nproc-per-node G ... tools/run_configs.py --configs 4,5     # batch sharded over G GPUs (hop.dist)
+  python tests/run_configs.py [--configs 1,2,3,4,5] [--small]
+  torchrun --nproc-per-node G ... tests/run_configs.py --configs 4,5     # batch sharded over G GPUs (hop.dist)
 
 The oracle (oracle/, plain-C restatement of the reference) is the checker only; it never computes a reported result.
 """
@@ -16,7 +16,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this file lives in tests/: it uses the oracle as a checker)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "time-opt-ilqr_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
