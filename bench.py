@@ -214,7 +214,9 @@ def run_hop(args):
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ---- end-to-end through the public host-buffer API
-    T_h = np.empty(B, dtype=np.int32); Js_h = np.empty(B); st_h = np.empty(B, dtype=np.int32)
+    T_h = torch.empty(B, dtype=torch.int32).pin_memory().numpy()
+    Js_h = torch.empty(B, dtype=torch.float64).pin_memory().numpy()
+    st_h = torch.empty(B, dtype=torch.int32).pin_memory().numpy()
     J_h = torch.empty((B, T_max), dtype=torch.float64).pin_memory().numpy()
     x0_np = x0_host.numpy()
     for _ in range(max(args.warmup, 3)):

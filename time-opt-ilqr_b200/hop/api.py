@@ -274,6 +274,27 @@ def select_horizon_batched(case, x0, xg=None, w=None, central: bool = False, mod
     return sel(x0, xg, w)
 
 
+_HOST_BCAST = {}   # (kind, value bytes, B) -> pinned, already broadcast host array (case defaults are re-used across calls)
+
+
+def _pinned_broadcast(kind: str, value, shape):
+    """Broadcast a case default (goal state / weight) to the batch ONCE into pinned host memory: a fresh pageable
+    array per call costs an allocation, a fill and a staged (synchronous) host-to-device copy of 6.8 MB at B = 65 536."""
+    v = np.ascontiguousarray(value, dtype=np.float64)
+    key = (kind, v.tobytes(), tuple(shape))
+    buf = _HOST_BCAST.get(key)
+    if buf is None:
+        if len(_HOST_BCAST) > 16:
+            _HOST_BCAST.clear()
+        t = torch.empty(tuple(shape), dtype=torch.float64)
+        if torch.cuda.is_available():
+            t = t.pin_memory()
+        buf = t.numpy()
+        buf[...] = np.broadcast_to(v, shape)
+        _HOST_BCAST[key] = buf
+    return buf
+
+
 def select_horizon_host(case, x0: np.ndarray, xg: Optional[np.ndarray] = None, w: Optional[np.ndarray] = None,
                         central: bool = False, mode: int = MODE_EXACT, want_curve: bool = True, out=None):
     """HOST-buffer entry (numpy in, numpy out): the library copies x0/xg/w to the device, runs
@@ -288,8 +309,10 @@ def select_horizon_host(case, x0: np.ndarray, xg: Optional[np.ndarray] = None, w
     T_max = int(min(T_max, N))
     x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1, n)
     Bsz = x0.shape[0]
-    xg = np.ascontiguousarray(np.broadcast_to(np.asarray(xg0 if xg is None else xg, dtype=np.float64), (Bsz, n)))
-    w = np.ascontiguousarray(np.broadcast_to(np.asarray(w0 if w is None else w, dtype=np.float64), (Bsz,)))
+    xg = _pinned_broadcast("xg", xg0, (Bsz, n)) if xg is None else \
+        np.ascontiguousarray(np.broadcast_to(np.asarray(xg, dtype=np.float64), (Bsz, n)))
+    w = _pinned_broadcast("w", w0, (Bsz,)) if w is None else \
+        np.ascontiguousarray(np.broadcast_to(np.asarray(w, dtype=np.float64), (Bsz,)))
     U = np.ascontiguousarray(np.tile(np.asarray(u_ref, dtype=np.float64).reshape(1, -1), (N, 1)))
     u_ref = np.ascontiguousarray(u_ref, dtype=np.float64)
     Q = np.ascontiguousarray(Q, dtype=np.float64)
