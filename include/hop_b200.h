@@ -191,6 +191,11 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double *params_host, int N, int T
 /* Test hook: selects the quadrotor forward-difference kernel (0 = thread per step [default], 1 = lane per column,
  * 2 = the generic kernel); returns the previous value.  All three produce identical bits (tests/test_gpu_parity.py). */
 int hop_test_set_linearize_variant(int variant);
+/* Test hook: smallest batch hop_select_f64 routes to the thread-per-problem kernel (d <= 5).  -1 = the built-in defaults
+ * (d <= 4: every batch; d = 5: B >= 16384), >= 0 = that threshold for every d (0 = always; also $HOP_TPP_MIN_BATCH),
+ * < -1 = query only.  Below the threshold the lane-group kernel runs; the two produce identical bits.  Returns the
+ * previous value. */
+long hop_test_set_tpp_min_batch(long min_batch);
 /* Test hook: backward-pass kernel, 0 = one warp per problem [default], 1 = one thread per problem; identical bits. */
 int hop_test_set_backward_variant(int variant);
 

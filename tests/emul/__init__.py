@@ -29,7 +29,7 @@ class FusedArgs(C.Structure):
 def build(force=False):
     srcs = [os.path.join(_HERE, f) for f in ("simt_emul.cpp", "simt_emul.h", "emul_select.cpp")]
     srcs += [os.path.join(_CSRC, f) for f in ("hop_select_core.cuh", "hop_select_body.cuh", "hop_simt.cuh", "hop_mma.cuh",
-                                              "hop_select_mma_body.cuh", "hop_select_pipe_body.cuh", "hop_select_scan_body.cuh", "hop_select_gpipe_body.cuh")]
+                                              "hop_select_mma_body.cuh", "hop_select_pipe_body.cuh", "hop_select_scan_body.cuh", "hop_select_gpipe_body.cuh", "hop_select_tpp_body.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-DHOP_HOST_EMUL", "-Wno-unknown-pragmas", "-I" + _HERE, "-I" + _CSRC, "-fPIC",
                                "-shared", "-o", _SO, os.path.join(_HERE, "simt_emul.cpp"),
@@ -56,7 +56,7 @@ def _p(a):
 
 
 def select_generic(A_aug, B_aug, Q_aug, R_inv, z0, QT, T_min, T_max, w_explicit=None, jitter=1e-9, max_tries=8,
-                   mma=False, scan=False, pipe=False):
+                   mma=False, scan=False, pipe=False, tpp=False):
     A_aug, B_aug, Q_aug, R_inv, z0, QT = map(_d, (A_aug, B_aug, Q_aug, R_inv, z0, QT))
     Bsz, N, d = A_aug.shape[:3]
     m = B_aug.shape[3]
@@ -64,7 +64,7 @@ def select_generic(A_aug, B_aug, Q_aug, R_inv, z0, QT, T_min, T_max, w_explicit=
     J = np.full((Bsz, T_max), np.nan); T = np.zeros(Bsz, np.int32); Js = np.zeros(Bsz); st = np.zeros(Bsz, np.int32)
     a = SelectArgs(Bsz, N, T_min, T_max, jitter, max_tries, _p(A_aug), _p(B_aug), _p(Q_aug), _p(R_inv), _p(z0), _p(QT),
                    (m * m if R_inv.ndim == 4 else 0), _p(wexp), _p(J), T.ctypes.data_as(_ip), _p(Js), st.ctypes.data_as(_ip))
-    fn = lib().emul_select_generic_pipe if pipe else lib().emul_select_generic_scan if scan else (lib().emul_select_generic_mma if mma else lib().emul_select_generic)
+    fn = lib().emul_select_generic_tpp if tpp else lib().emul_select_generic_pipe if pipe else lib().emul_select_generic_scan if scan else (lib().emul_select_generic_mma if mma else lib().emul_select_generic)
     rc = fn(d, m, C.byref(a))
     assert rc == 0, f"emulated kernel failed rc={rc}"
     return J, T, Js, st

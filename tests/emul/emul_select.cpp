@@ -8,6 +8,7 @@
 #include "hop_select_pipe_body.cuh"
 #include "hop_select_scan_body.cuh"
 #include "hop_select_gpipe_body.cuh"
+#include "hop_select_tpp_body.cuh"
 
 namespace {
 template <int D, int M, int G>
@@ -204,5 +205,24 @@ extern "C" int emul_select_fused(int n, int m, const hop::FusedArgs* p) {
     if (n == 2 && m == 1) return run_fused<3, 1, 4>(*p);
     if (n == 4 && m == 1) return run_fused<5, 1, 8>(*p);
     if (n == 12 && m == 4) return run_fused<13, 4, 16>(*p);
+    return -2;
+}
+
+// ---- thread-per-problem LQR-boundary body (hop_select_tpp_body.cuh): no cross-lane traffic, so a plain loop
+namespace {
+template <int D, int M>
+int run_generic_tpp(const hop::SelectArgs& p) {
+    for (int b = 0; b < p.B; ++b) {
+        hop::tpp::GlobalFeed<D, M> feed;
+        feed.init(p, b);
+        hop::tpp::select_generic_tpp_body<D, M>(p, b, true, feed);
+    }
+    return 0;
+}
+}  // namespace
+extern "C" int emul_select_generic_tpp(int d, int m, const hop::SelectArgs* p) {
+    if (d == 3 && m == 1) return run_generic_tpp<3, 1>(*p);
+    if (d == 4 && m == 2) return run_generic_tpp<4, 2>(*p);
+    if (d == 5 && m == 1) return run_generic_tpp<5, 1>(*p);
     return -2;
 }

@@ -144,3 +144,22 @@ def test_emulated_pipelined_generic_kernel_matches_oracle_and_falls_back(d, m, N
     assert np.array_equal(st, stq)
     assert rel(J[:2], Jo[:2]) <= 1e-9 and np.array_equal(J[1:], Jq[1:], equal_nan=True)
     assert np.array_equal(T[:2], np.argmin(Jo[:2] + w[:2, None] * np.arange(1, N + 1), axis=1) + 1)
+
+
+@pytest.mark.parametrize("d,m,N", [(3, 1, 32), (4, 2, 64), (5, 1, 48)])
+def test_emulated_thread_per_problem_kernel_is_bit_identical_to_the_lane_group_kernel(d, m, N):
+    """hop_select_tpp_body.cuh (one problem per thread, blocks in registers) performs, element for element, the IEEE
+    operations of the lane-group kernel: J, T*, J* and status must be identical bit for bit -- also through the jitter
+    ladder, the LU fallback and a non-finite input (utils.py:75,81-93)."""
+    A, B, Q, R, z0, w, QT = s2_batch(range(5), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    Q[1, 3] = np.diag(np.r_[np.ones(d - 1), -1e-4])       # ladder
+    QT[2, 5] = -np.eye(d)                                  # LU fallback
+    A[3, 7, 1, 1] = np.nan                                 # FloatingPointError in the reference
+    Jg, Tg, Jsg, stg = emul.select_generic(A, B, Q, Rinv, z0, QT, 2, N - 1, w_explicit=w)
+    Jt, Tt, Jst, stt = emul.select_generic(A, B, Q, Rinv, z0, QT, 2, N - 1, w_explicit=w, tpp=True)
+    assert stg[1] == 0x100 and stg[2] == 0x300 and (stg[3] & 0xFF) == 1 and stg[0] == 0 and stg[4] == 0
+    assert np.array_equal(stt, stg) and np.array_equal(Tt, Tg)
+    assert np.array_equal(Jt, Jg, equal_nan=True) and np.array_equal(Jst, Jsg, equal_nan=True)
+    Jo, _ = O.propagator_batch(A[:1], B[:1], Q[:1], Rinv[:1], z0[:1], QT[:1], T_use=N - 1)
+    assert rel(Jt[:1], Jo) <= 1e-12

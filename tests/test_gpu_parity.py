@@ -131,6 +131,37 @@ def test_ladder_fallback_and_nonfinite_status_on_gpu():
         sel.raise_for_status()
 
 
+@pytest.mark.parametrize("d,m,N,B", [(3, 1, 32, 70), (4, 2, 64, 97), (5, 1, 48, 33)])
+def test_thread_per_problem_and_lane_group_kernels_agree_bit_for_bit(d, m, N, B):
+    """hop_select_f64 routes large batches of small blocks (d <= 5) to the thread-per-problem kernel
+    (hop_select_tpp_body.cuh); it performs the same IEEE operations per element as the lane-group kernel, so J, T*, J*
+    and status are identical -- ragged last warp, T_min > 1, T_max < N, jitter ladder, LU fallback and a NaN included."""
+    from hop import _cabi
+    lib = _cabi.require_device()
+    A, Bm, Q, R, z0, w, QT = s2_batch(range(B), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    Q[1, 3] = np.diag(np.r_[np.ones(d - 1), -1e-4])       # ladder
+    QT[2, 5] = -np.eye(d)                                  # LU fallback
+    A[B - 1, 7, 1, 1] = np.nan                             # FloatingPointError in the reference
+    args = (_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 2, N - 1)
+    out = {}
+    old = lib.hop_test_set_tpp_min_batch(-2)
+    try:
+        for name, thr in (("lanes", 1 << 40), ("threads", 0)):
+            lib.hop_test_set_tpp_min_batch(thr)
+            sel = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w))
+            out[name] = tuple(x.cpu().numpy() for x in (sel.J, sel.T_star, sel.J_star, sel.status))
+    finally:
+        lib.hop_test_set_tpp_min_batch(old)
+    st = out["lanes"][3]
+    assert st[1] == 0x100 and st[2] == 0x300 and (st[B - 1] & 0xFF) == 1 and st[0] == 0
+    for a, b in zip(out["threads"], out["lanes"]):
+        assert np.array_equal(a, b, equal_nan=True)
+    ok = [i for i in range(B) if i != B - 1]
+    Jo, _ = O.propagator_batch(A[ok], Bm[ok], Q[ok], Rinv[ok], z0[ok], QT[ok], T_use=N - 1)
+    assert rel(out["threads"][0][ok], Jo) <= 1e-9
+
+
 @pytest.mark.parametrize("name", CASE_NAMES)
 def test_rollout_and_linearize_match_oracle(name):
     g = golden("case_" + name)

@@ -9,6 +9,7 @@
 
 namespace hop {
 int dispatch_select_generic(int d, int m, int mode, const SelectArgs& p, cudaStream_t st);
+long tpp_min_batch(long set_to);
 int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st);
 int dispatch_rollout(int B, int sys, const double* params_host, int N, const double* x0, const double* U, long ustride,
                      double max_norm, double* X, cudaStream_t st);
@@ -409,6 +410,8 @@ int hop_test_set_backward_variant(int variant) {
     if (variant == 0 || variant == 1) g_backward_variant = variant;
     return old;
 }
+
+long hop_test_set_tpp_min_batch(long min_batch) { return hop::tpp_min_batch(min_batch); }
 
 int hop_test_set_linearize_variant(int variant) {
     const int old = g_linearize_variant;

@@ -4,6 +4,7 @@
 // independent (warp-synchronous code, no CTA barrier inside the sweep), so the hardware scheduler
 // load-balances warps across the 148 SMs.  Dynamic shared memory = per-group slab (Geo::SLAB
 // doubles) [+ the CTA-wide case constants for the fused form].
+#include <cstdint>
 #include <cstdlib>
 
 #include "hop_common.cuh"
@@ -188,12 +189,21 @@ static int launch_fused_mma(const FusedArgs& p, cudaStream_t st) {
     }
 }
 
+
+// one problem per THREAD (d <= 5, large batches): hop_select_tpp.cu.  Returns HOP_E_UNSUPPORTED_DIMS without touching the
+// error string when (d, m, p) is not for that kernel.
+int dispatch_select_generic_tpp(int d, int m, const SelectArgs& p, cudaStream_t st);
+
 int dispatch_select_generic(int d, int m, int mode, const SelectArgs& p, cudaStream_t st) {
     if (mode == HOP_MODE_SCAN) {
         if (d == 12 && m == 4) return launch_generic_scan<12, 4>(p, st);
         if (d == 13 && m == 4) return launch_generic_scan<13, 4>(p, st);
         set_last_error("hop_select_f64: HOP_MODE_SCAN is instantiated for (d, m) = (12,4) and (13,4) only");
         return HOP_E_UNSUPPORTED_DIMS;
+    }
+    if (d <= 5) {
+        const int rc = dispatch_select_generic_tpp(d, m, p, st);
+        if (rc != HOP_E_UNSUPPORTED_DIMS) return rc;
     }
     if (d == 3 && m == 1) return launch_generic<3, 1, 4>(p, st);
     if (d == 4 && m == 2) return launch_generic<4, 2, 4>(p, st);

@@ -115,7 +115,7 @@ HOP_DEVICE void select_generic_body(const SelectArgs& p, int b_raw, double* sm) 
         if (r == 0 && valid) {
             p.J_out[(size_t)b * p.T_max + k] = J;
             const int t = k + 1;
-            if (t >= p.T_min) am.push(J + wexp * (double)t, t);
+            if (t >= p.T_min) am.push(simt::add_rn(J, simt::mul_rn(wexp, (double)t)), t);   // J + w t as numpy: two roundings
         }
     }
     if (r == 0 && valid) {

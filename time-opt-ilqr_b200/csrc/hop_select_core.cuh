@@ -393,7 +393,7 @@ HOP_DEVICE double query_step(const Prefix<D>& P, const double (&qt)[D], double* 
     double dot = 0.0;
 #pragma unroll
     for (int j = 0; j < D; ++j) dot = fma(p0[j], z0[j], dot);
-    const double part = act ? z0[r] * dot : 0.0;
+    const double part = act ? simt::mul_rn(z0[r], dot) : 0.0;   // (never fused with the first add of the tree)
     return 0.5 * group_sum<G>(part);
 }
 

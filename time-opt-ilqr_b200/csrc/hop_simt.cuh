@@ -9,6 +9,11 @@
 
 #ifdef HOP_HOST_EMUL
 #include "simt_emul.h"   // defines hop::simt::{lane_id, sync, shfl, shfl_xor, ballot, all} + HOP_DEVICE
+namespace hop { namespace simt {
+// (g++ on x86-64 without -mfma never contracts a * b + c)
+inline double mul_rn(double a, double b) { return a * b; }
+inline double add_rn(double a, double b) { return a + b; }
+}}  // namespace hop::simt
 #else
 #include <cuda_runtime.h>
 #define HOP_DEVICE __device__ __forceinline__
@@ -21,6 +26,9 @@ HOP_DEVICE double shfl(double v, int src_in_group, int width) { return __shfl_sy
 HOP_DEVICE double shfl_xor(double v, int mask, int width) { return __shfl_xor_sync(0xffffffffu, v, mask, width); }
 HOP_DEVICE unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 HOP_DEVICE bool all(bool p) { return __all_sync(0xffffffffu, p) != 0; }
+// a product / a sum that must NOT be contracted into an FMA with its neighbours (numpy evaluates them separately)
+HOP_DEVICE double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+HOP_DEVICE double add_rn(double a, double b) { return __dadd_rn(a, b); }
 // D(8x8) += A(8x4) * B(4x8) in fp64 on the tensor pipe (SASS: DMMA.8x8x4).  Fragments (g = lane>>2,
 // t = lane&3): a = A[g][t], b = B[t][g], c0/c1 = C[g][2t], C[g][2t+1].
 HOP_DEVICE void dmma(double& c0, double& c1, double a, double b) {
@@ -47,6 +55,9 @@ HOP_DEVICE void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned lo
 // ---- cp.async (LDGSTS) in 8-byte granules: global -> shared without a register round trip, any 8-byte alignment
 HOP_DEVICE void cp_async8(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+HOP_DEVICE void cp_async16(void* dst, const void* src) {   // dst and src 16-byte aligned
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
 HOP_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_>
