@@ -291,6 +291,24 @@ def test_full_size_properties_without_oracle():
     assert torch.equal(Jw.argmin(dim=1).int() + 40, T1)
 
 
+def test_chunked_host_path_equals_the_device_path_on_ragged_chunks():
+    """hop_select_from_x0_host_f64 cuts large batches into chunks that alternate between two streams (uploads, kernels and
+    the J(T) download of neighbouring chunks overlap).  Chunking must not change a bit: B = 40 003 gives three ragged
+    chunks; per-instance xg / w and per-instance controls exercise every offset computation."""
+    case = cases.make_case("Quadrotor", N=128)
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = case
+    B = 40003
+    rng = np.random.default_rng(5)
+    x0s = s1_x0(B, seed=3)
+    xgs = xg[None] + 0.05 * rng.standard_normal((B, 12)) * np.r_[np.ones(3), np.zeros(9)]
+    ws = w * (0.5 + rng.random(B))
+    dev = api.select_horizon_batched(case, _t(x0s), xg=_t(xgs), w=_t(ws), mode=api.MODE_FAST)
+    Jh, Th, Jsh, sth = api.select_horizon_host(case, x0s, xg=xgs, w=ws, mode=api.MODE_FAST)
+    assert np.array_equal(Th, dev.T_star.cpu().numpy()) and np.array_equal(Jh, dev.J.cpu().numpy())
+    assert np.array_equal(Jsh, dev.J_star.cpu().numpy()) and np.array_equal(sth, dev.status.cpu().numpy())
+    assert len(np.unique(Th)) > 3
+
+
 def test_fast_and_exact_modes_agree_on_4096_instances():
     """MODE_FAST restructures the block inverses algebraically; on the headline workload it must select
     the same horizon as MODE_EXACT except on near-ties, and agree on J to the fp64 noise floor."""

@@ -448,15 +448,22 @@ int hop_probe_fp64_tflops(int iters, double* tflops_out, double* ms_out) {
 }
 
 // ---- host-buffer variant ------------------------------------------------------------------------
+// The batch is cut into up to four chunks that alternate between two streams: while chunk c runs its three kernels,
+// the J(T) block of chunk c-1 (the bulk of the device -> host traffic, 8 T_max bytes per instance) drains over PCIe
+// and the inputs of chunk c+1 arrive, so only the first upload and the last download are exposed.  It also bounds
+// the linearisation workspace (A, B: 1.7 KB per instance and step) to two chunks instead of the whole batch.
 namespace {
 struct HostCtx {
     std::mutex mu;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t consts_ready = nullptr;
     void* buf = nullptr;
     size_t cap = 0;
     int device = -1;
 };
 HostCtx g_host;
+constexpr int kHostChunkMin = 16384;   // instances: below this a chunk no longer fills the machine for several waves
+constexpr int kHostChunksMax = 4;
 }  // namespace
 
 int hop_select_from_x0_host_f64(int B, int sys, const double* params_host, int N, int T_min, int T_max,
@@ -473,19 +480,27 @@ int hop_select_from_x0_host_f64(int B, int sys, const double* params_host, int N
     cudaGetDevice(&dev);
     if (g_host.device != dev) {   // one cached arena per process; re-created when the current device changes
         if (g_host.buf) cudaFree(g_host.buf);
-        if (g_host.stream) cudaStreamDestroy(g_host.stream);
-        g_host.buf = nullptr; g_host.cap = 0; g_host.stream = nullptr; g_host.device = dev;
+        for (auto& st : g_host.stream) { if (st) cudaStreamDestroy(st); st = nullptr; }
+        if (g_host.consts_ready) cudaEventDestroy(g_host.consts_ready);
+        g_host.buf = nullptr; g_host.cap = 0; g_host.consts_ready = nullptr; g_host.device = dev;
     }
-    if (!g_host.stream) {
-        if (int rc = report_cuda(cudaStreamCreateWithFlags(&g_host.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return rc;
+    for (auto& st : g_host.stream)
+        if (!st) { if (int rc = report_cuda(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate")) return rc; }
+    if (!g_host.consts_ready) {
+        if (int rc = report_cuda(cudaEventCreateWithFlags(&g_host.consts_ready, cudaEventDisableTiming), "cudaEventCreate")) return rc;
     }
-    const size_t nU = (u_batch_stride == 0) ? (size_t)N * m : (size_t)B * N * m;
+    int chunks = (B + kHostChunkMin - 1) / kHostChunkMin;
+    chunks = chunks < 1 ? 1 : (chunks > kHostChunksMax ? kHostChunksMax : chunks);
+    const int per = (((B + chunks - 1) / chunks) + 3) & ~3;       // whole CTAs of the selection kernel
+    const int lanes = chunks > 1 ? 2 : 1;                         // workspaces (= streams) in use
+    const bool shared_U = (u_batch_stride == 0);
+    const size_t nU = shared_U ? (size_t)N * m : (size_t)B * N * m;
     const size_t s_x0 = align256(sizeof(double) * (size_t)B * n), s_xg = s_x0, s_w = align256(sizeof(double) * (size_t)B);
     const size_t s_U = align256(sizeof(double) * nU), s_c = align256(sizeof(double) * (size_t)(m + 2 * n * n + m * m));
     const size_t s_J = align256(sizeof(double) * (size_t)B * T_max), s_T = align256(sizeof(int) * (size_t)B);
     const size_t s_Js = align256(sizeof(double) * (size_t)B);
-    const size_t s_ws = (size_t)hop_select_from_x0_workspace_bytes(B, N, n, m);
-    const size_t total = s_x0 + s_xg + s_w + s_U + s_c + s_J + 2 * s_T + s_Js + s_ws;
+    const size_t s_ws = align256((size_t)hop_select_from_x0_workspace_bytes(per, N, n, m));
+    const size_t total = s_x0 + s_xg + s_w + s_U + s_c + s_J + 2 * s_T + s_Js + lanes * s_ws;
     if (total > g_host.cap) {
         if (g_host.buf) cudaFree(g_host.buf);
         g_host.buf = nullptr; g_host.cap = 0;
@@ -502,25 +517,43 @@ int hop_select_from_x0_host_f64(int B, int sys, const double* params_host, int N
     int* d_T = (int*)q; q += s_T;
     int* d_st = (int*)q; q += s_T;
     double* d_Js = (double*)q; q += s_Js;
-    void* d_ws = q;
-    cudaStream_t st = g_host.stream;
+    char* d_ws = q;
     double* d_uref = d_c; double* d_Q = d_uref + m; double* d_R = d_Q + n * n; double* d_Qf = d_R + m * m;
-    cudaMemcpyAsync(d_x0, x0, sizeof(double) * (size_t)B * n, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d_xg, xg, sizeof(double) * (size_t)B * n, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d_w, w, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d_U, U, sizeof(double) * nU, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d_uref, u_ref, sizeof(double) * m, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d_Q, Q, sizeof(double) * n * n, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d_R, R, sizeof(double) * m * m, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d_Qf, Qf, sizeof(double) * n * n, cudaMemcpyHostToDevice, st);
-    int rc = hop_select_from_x0_f64(B, sys, params_host, N, T_min, T_max, d_x0, d_U, u_batch_stride, d_xg, d_w, d_uref,
-                                    d_Q, d_R, d_Qf, wrap_mask, central, mode, d_ws, s_ws, d_J, d_T, d_Js, d_st, st);
+    cudaStream_t s0 = g_host.stream[0];
+    cudaMemcpyAsync(d_uref, u_ref, sizeof(double) * m, cudaMemcpyHostToDevice, s0);
+    cudaMemcpyAsync(d_Q, Q, sizeof(double) * n * n, cudaMemcpyHostToDevice, s0);
+    cudaMemcpyAsync(d_R, R, sizeof(double) * m * m, cudaMemcpyHostToDevice, s0);
+    cudaMemcpyAsync(d_Qf, Qf, sizeof(double) * n * n, cudaMemcpyHostToDevice, s0);
+    if (shared_U) cudaMemcpyAsync(d_U, U, sizeof(double) * nU, cudaMemcpyHostToDevice, s0);
+    cudaEventRecord(g_host.consts_ready, s0);
+    if (lanes > 1) cudaStreamWaitEvent(g_host.stream[1], g_host.consts_ready, 0);
+    int rc = 0;
+    for (int c = 0; c < chunks && rc == 0; ++c) {
+        const int b0 = c * per, cb = (B - b0) < per ? (B - b0) : per;
+        if (cb <= 0) break;
+        cudaStream_t st = g_host.stream[c % lanes];
+        const size_t o = (size_t)b0;
+        cudaMemcpyAsync(d_x0 + o * n, x0 + o * n, sizeof(double) * (size_t)cb * n, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_xg + o * n, xg + o * n, sizeof(double) * (size_t)cb * n, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_w + o, w + o, sizeof(double) * (size_t)cb, cudaMemcpyHostToDevice, st);
+        const double* dU = d_U;
+        if (!shared_U) {
+            cudaMemcpyAsync(d_U + o * N * m, U + o * N * m, sizeof(double) * (size_t)cb * N * m, cudaMemcpyHostToDevice, st);
+            dU = d_U + o * N * m;
+        }
+        rc = hop_select_from_x0_f64(cb, sys, params_host, N, T_min, T_max, d_x0 + o * n, dU, u_batch_stride, d_xg + o * n,
+                                    d_w + o, d_uref, d_Q, d_R, d_Qf, wrap_mask, central, mode, d_ws + (c % lanes) * s_ws, s_ws,
+                                    d_J + o * T_max, d_T + o, d_Js + o, d_st + o, st);
+        if (rc) break;
+        if (J_out) cudaMemcpyAsync(J_out + o * T_max, d_J + o * T_max, sizeof(double) * (size_t)cb * T_max, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(Tstar_out + o, d_T + o, sizeof(int) * (size_t)cb, cudaMemcpyDeviceToHost, st);
+        if (Jstar_out) cudaMemcpyAsync(Jstar_out + o, d_Js + o, sizeof(double) * (size_t)cb, cudaMemcpyDeviceToHost, st);
+        if (status) cudaMemcpyAsync(status + o, d_st + o, sizeof(int) * (size_t)cb, cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e0 = cudaStreamSynchronize(g_host.stream[0]);
+    cudaError_t e1 = lanes > 1 ? cudaStreamSynchronize(g_host.stream[1]) : cudaSuccess;
     if (rc) return rc;
-    if (J_out) cudaMemcpyAsync(J_out, d_J, sizeof(double) * (size_t)B * T_max, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(Tstar_out, d_T, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st);
-    if (Jstar_out) cudaMemcpyAsync(Jstar_out, d_Js, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st);
-    if (status) cudaMemcpyAsync(status, d_st, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st);
-    return report_cuda(cudaStreamSynchronize(st), "hop_select_from_x0_host_f64");
+    return report_cuda(e0 != cudaSuccess ? e0 : e1, "hop_select_from_x0_host_f64");
 }
 
 }  // extern "C"
