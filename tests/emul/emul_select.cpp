@@ -98,7 +98,7 @@ int run_fused_mma(const hop::FusedArgs& p) {
     if (p.mode >= 2) hop::mma::pipe_const_fill<D, M>(cst.data(), 0, 1);
     for (int b = 0; b < p.B; ++b) {
         MmaFusedJob<D, M> j{&p, b, scratch.data(), cst.data()};
-        auto fn = p.mode == 4 ? mma_pipe_lane<D, M, 2> : p.mode == 3 ? mma_pipe_lane<D, M, 1> : p.mode == 2 ? mma_pipe_lane<D, M, 0>
+        auto fn = p.mode == 5 ? mma_pipe_lane<D, M, 3> : p.mode == 4 ? mma_pipe_lane<D, M, 2> : p.mode == 3 ? mma_pipe_lane<D, M, 1> : p.mode == 2 ? mma_pipe_lane<D, M, 0>
                                 : (p.mode == 1 ? mma_fused_lane<D, M, 1> : mma_fused_lane<D, M, 0>);
         if (hop::simt::run_warp(fn, &j)) return -1;
     }

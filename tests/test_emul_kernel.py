@@ -76,7 +76,7 @@ def test_emulated_dmma_generic_kernel_matches_oracle(d, m, N):
     assert np.array_equal(T, np.argmin(Jo + w[:, None] * np.arange(1, N + 1), axis=1) + 1)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])   # 2 / 3 / 4 = pipelined FAST schedule: unrolled / looped / looped + shared-memory pivot exchange
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])   # 5: 4 with two pivots per loop trip + high-word zeroing; 2 / 3 / 4 = pipelined FAST schedule: unrolled / looped / looped + shared-memory pivot exchange
 def test_emulated_dmma_fused_kernel_matches_reference_golden(mode):
     g = golden("case_Quadrotor")
     F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case("Quadrotor", N=128)

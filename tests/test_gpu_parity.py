@@ -391,6 +391,30 @@ def test_warp_and_thread_backward_kernels_agree_bit_for_bit(name):
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)
+def test_parallel_and_serial_line_search_kernels_agree_bit_for_bit(name):
+    """forward_linesearch_fixedT has two device mappings: the five step sizes side by side (six threads per problem, the
+    cost evaluated while rolling) and one thread per problem trying them in turn.  Each candidate is the same
+    instruction sequence, the first improving alpha wins in both => identical trajectories, histories and statuses.
+    Perturbed initial states make iterations with alpha < 1 and fully rejected iterations both occur."""
+    from hop import _cabi
+    lib = _cabi.require_device()
+    case = cases.make_case(name, N=128) if name == "Quadrotor" else cases.make_case(name)
+    n = case[1].size
+    rng = np.random.default_rng(4)
+    x0s = case[1][None] + 0.3 * rng.standard_normal((45, n))
+    out = {}
+    try:
+        for variant in (0, 1):
+            lib.hop_test_set_linesearch_variant(variant)
+            out[variant] = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=6, use_central_diff=False, mode=api.MODE_FAST)
+    finally:
+        lib.hop_test_set_linesearch_variant(0)
+    for key in ("X", "U", "J_hist", "T_hist", "n_hist", "T_star", "status"):
+        assert torch.equal(torch.nan_to_num(out[0][key].double(), nan=-1.0), torch.nan_to_num(out[1][key].double(), nan=-1.0)), key
+    assert int(out[0]["n_hist"].max()) >= 3
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
 def test_bruteforce_curve_matches_reference_golden_and_oracle(name):
     """solver.py:293-358 on the device (one warp per horizon) against the reference's own output (first 48 horizons in
     the goldens) and against the oracle over the whole window."""

@@ -18,6 +18,7 @@ int dispatch_linearize(int B, int sys, const double* params_host, int N, const d
                        double* A, double* Bm, cudaStream_t st);
 extern int g_linearize_variant;
 extern int g_backward_variant;
+extern int g_linesearch_variant;
 struct DdpConst {
     const double *xg, *w, *u_ref, *Q, *R, *Qf;
     unsigned wrap_mask;
@@ -408,6 +409,12 @@ __global__ void k_probe_dfma(int iters, double seed, double* sink) {
 int hop_test_set_backward_variant(int variant) {
     const int old = g_backward_variant;
     if (variant == 0 || variant == 1) g_backward_variant = variant;
+    return old;
+}
+
+int hop_test_set_linesearch_variant(int variant) {
+    const int old = g_linesearch_variant;
+    if (variant == 0 || variant == 1) g_linesearch_variant = variant;
     return old;
 }
 

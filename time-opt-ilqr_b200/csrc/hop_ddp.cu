@@ -134,6 +134,84 @@ __global__ void k_linesearch(int B, DynParams2 prm, int N, const double* X, cons
     acc[b] = a;
 }
 
+// Line search with the five step sizes of solver.py:240 side by side.  A CTA of six warps serves 32 instances
+// (lane = instance, warp = role, so no warp diverges): warps 0..4 roll out alpha = (1, .5, .25, .1, .05) and evaluate
+// the cost on the fly, warp 5 evaluates J_old at the new T* (solver.py:253).  The reference accepts the FIRST alpha
+// with J_new < J_old; the CTA takes the same decision from six values per instance in shared memory.  Warp 0 stores its
+// candidate while rolling (alpha = 1 is accepted most of the time); another winner rolls once more with stores.  Every
+// candidate is computed by the same instruction sequence as in k_linesearch, so X_new, U_new, J and `accepted` are
+// bit-identical -- in one or two roll-out latencies instead of up to five plus a cost pass each (the batch sizes of the
+// HOP-DDP configurations leave the machine empty, so the extra threads are free).
+constexpr int kLsRoles = 6;
+template <int SYS>
+__global__ void __launch_bounds__(kLsRoles * 32) k_linesearch_par(int B, DynParams2 prm, int N, const double* X, const double* U,
+                                                                    DdpConst c, const int* T, const double* k_list,
+                                                                    const double* K_list, const int* ok, const int* done,
+                                                                    double* Xn, double* Un, double* Jn, int* acc) {
+    constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
+    __shared__ double sJ[kLsRoles][32];
+    __shared__ int sOk[kLsRoles][32];
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const int b_raw = blockIdx.x * 32 + lane;
+    const bool valid = b_raw < B;
+    const int b = valid ? b_raw : B - 1;
+    const bool active = valid && !((done && done[b]) || (ok && !ok[b]));
+    if (valid && role == 0) acc[b] = 0;
+    const ddp::CostConst cc = cost_const<n>(c, b);
+    const double* Xb = X + (size_t)b * (N + 1) * n;
+    const double* Ub = U + (size_t)b * N * m;
+    const double* kb = k_list + (size_t)b * N * m;
+    const double* Kb = K_list + (size_t)b * N * m * n;
+    double* Xnb = Xn + (size_t)b * (N + 1) * n;
+    double* Unb = Un + (size_t)b * N * m;
+    const int Tb = T[b];
+    const double alpha = role == 0 ? 1.0 : role == 1 ? 0.5 : role == 2 ? 0.25 : role == 3 ? 0.1 : 0.05;
+    double J = HUGE_VAL;
+    bool cand_ok = false;
+    if (active) {
+        if (role == 0) cand_ok = ddp::linesearch_candidate<SYS, true>(prm.p, N, Xb, Ub, cc, Tb, kb, Kb, alpha, Xnb, Unb, &J);
+        else if (role < 5) cand_ok = ddp::linesearch_candidate<SYS, false>(prm.p, N, Xb, Ub, cc, Tb, kb, Kb, alpha, nullptr, nullptr, &J);
+        else J = ddp::cost_timeopt_true<n, m>(Xb, Ub, cc, Tb);
+    }
+    sJ[role][lane] = J;
+    sOk[role][lane] = cand_ok ? 1 : 0;
+    __syncthreads();
+    if (!active) return;
+    const double J_old = sJ[5][lane];
+    int winner = -1;
+#pragma unroll
+    for (int r = 4; r >= 0; --r)
+        if (sOk[r][lane] && sJ[r][lane] < J_old) winner = r;
+    if (winner > 0 && role == winner)
+        ddp::linesearch_candidate<SYS, true>(prm.p, N, Xb, Ub, cc, Tb, kb, Kb, alpha, Xnb, Unb, &J);
+    if (winner >= 0) {
+        if (role == winner) { Jn[b] = J; acc[b] = 1; }
+        return;
+    }
+    for (size_t i = role; i < (size_t)(N + 1) * n; i += kLsRoles) Xnb[i] = Xb[i];
+    for (size_t i = role; i < (size_t)N * m; i += kLsRoles) Unb[i] = Ub[i];
+    if (role == 0) { Jn[b] = J_old; acc[b] = 0; }
+}
+// line-search kernel: 0 step sizes side by side (default), 1 one thread per problem trying them in turn (test / A-B hook;
+// identical bits)
+int g_linesearch_variant = getenv("HOP_LS_SERIAL") ? atoi(getenv("HOP_LS_SERIAL")) : 0;
+template <int SYS>
+static int launch_linesearch(int B, const DynParams2& prm, int N, const double* X, const double* U, const DdpConst& c, const int* T,
+                             const double* kl, const double* Kl, const int* ok, const int* done, double* Xn, double* Un,
+                             double* Jn, int* acc, cudaStream_t st) {
+    const int threads = 64;
+    // Six threads per instance only pay while they fit next to each other: measured on B200, forward phase of a 12-iteration
+    // solve: Segway B = 25 7.6 -> 2.5 ms, Cartpole B = 4096 67.5 -> 16.1 ms, Quadrotor B = 16384 22.1 -> 28.3 ms (130
+    // registers: the machine holds ~75k such threads, 16384 x 6 no longer fit in one wave).  $HOP_LS_PAR_MAX_BATCH overrides.
+    static const long par_max = getenv("HOP_LS_PAR_MAX_BATCH") ? atol(getenv("HOP_LS_PAR_MAX_BATCH")) : 8192;
+    if (g_linesearch_variant != 0 || B > par_max) {
+        k_linesearch<SYS><<<(B + threads - 1) / threads, threads, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, done, Xn, Un, Jn, acc);
+        return check_launch("k_linesearch");
+    }
+    k_linesearch_par<SYS><<<(B + 31) / 32, kLsRoles * 32, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, done, Xn, Un, Jn, acc);
+    return check_launch("k_linesearch_par");
+}
+
 // After a selection: an instance whose selection raised in the reference (status low byte != 0) stops
 // here ("crash", run_suite.py:137-157); otherwise T_sel is the horizon to optimise at.
 __global__ void k_after_select(int B, const int* sel_status, int* done, int* status_out) {
@@ -241,8 +319,7 @@ static int ddp_backward_linesearch(int B, const DynParams2& prm, int N, const do
     else k_backward_warp<n, m><<<grid1(B, kBwWarps), kBwWarps * 32, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
     if (int rc = check_launch("k_backward")) return rc;
     if (mid) cudaEventRecord(mid, st);
-    k_linesearch<SYS><<<grid1(B, threads), threads, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, done, Xn, Un, Jn, acc);
-    return check_launch("k_linesearch");
+    return launch_linesearch<SYS>(B, prm, N, X, U, c, T, kl, Kl, ok, done, Xn, Un, Jn, acc, st);
 }
 
 int dispatch_backward_linesearch(int sys, int B, const double* params_host, int N, const double* A, const double* Bm,
@@ -265,8 +342,7 @@ template <int SYS>
 static int launch_linesearch_only(int B, const DynParams2& prm, int N, const double* X, const double* U, const DdpConst& c,
                                   const int* T, const double* kl, const double* Kl, const int* ok, double* Xn, double* Un,
                                   double* Jn, int* acc, cudaStream_t st) {
-    k_linesearch<SYS><<<grid1(B, 64), 64, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, nullptr, Xn, Un, Jn, acc);
-    return check_launch("k_linesearch");
+    return launch_linesearch<SYS>(B, prm, N, X, U, c, T, kl, Kl, ok, nullptr, Xn, Un, Jn, acc, st);
 }
 int dispatch_linesearch(int sys, int B, const double* params_host, int N, const double* X, const double* U, const DdpConst& c,
                         const int* T, const double* kl, const double* Kl, const int* ok, double* Xn, double* Un, double* Jn,

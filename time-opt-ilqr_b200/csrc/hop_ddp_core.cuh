@@ -609,4 +609,58 @@ HOP_DEVICE void forward_linesearch(const double* prm, int N, const double* X, co
     *accepted = 0;
 }
 
+// ---- the five step sizes of solver.py:233-286 evaluated SIDE BY SIDE ----------------------------------
+// One candidate of the line search: roll the closed-loop policy du = K dx + alpha k out to N and evaluate
+// cost_timeopt_true of the candidate on the fly (same terms, same accumulation order as the function above applied to
+// the stored trajectory).  STORE: also write the candidate into X_new / U_new.  Returns false when the candidate has
+// to be skipped (non-finite state somewhere on [1, N], solver.py:273-276); J is +inf where cost_timeopt_true returns inf.
+template <int SYS, bool STORE>
+HOP_DEVICE bool linesearch_candidate(const double* prm, int N, const double* X, const double* U, const CostConst& c, int T,
+                                     const double* k_list, const double* K_list, double a, double* X_new, double* U_new,
+                                     double* J_out) {
+    constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
+    double x[n], xn[n], u[m], e[n], du[m];
+    for (int i = 0; i < n; ++i) { x[i] = X[i]; if (STORE) X_new[i] = x[i]; }
+    double acc = 0.0, J = HUGE_VAL;
+    bool inf = (T <= 0);
+    for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < m; ++i) u[i] = U[(size_t)k * m + i];
+        if (k < T) {
+            double dx[n];
+            for (int i = 0; i < n; ++i) {
+                double v = sub(x[i], X[(size_t)k * n + i]);
+                if ((c.wrap_mask >> i) & 1u) v = wrap_pi(v);
+                dx[i] = v;
+            }
+            for (int i = 0; i < m; ++i) {
+                double s = 0.0;
+                for (int j = 0; j < n; ++j) s = add(s, mul(K_list[(size_t)k * m * n + i * n + j], dx[j]));
+                u[i] = add(u[i], add(s, mul(a, k_list[(size_t)k * m + i])));
+            }
+            // stage term of the candidate (solver.py:92-101)
+            wrapped_error<n>(x, c.xg, c.wrap_mask, e);
+#pragma unroll
+            for (int i = 0; i < m; ++i) du[i] = sub(u[i], c.u_ref[i]);
+            if (!all_finite<n>(x) || !all_finite<m>(u) || !all_finite<n>(e) || !all_finite<m>(du)) inf = true;
+            acc = add(acc, add(add(mul(0.5, quad_form<n>(c.Q, e)), mul(0.5, quad_form<m>(c.R, du))), c.w));
+        } else if (k == T) {
+            wrapped_error<n>(x, c.xg, c.wrap_mask, e);                          // terminal term at X_new[T] (solver.py:102-105)
+            if (!all_finite<n>(x) || !all_finite<n>(e)) inf = true;
+            J = add(acc, mul(0.5, quad_form<n>(c.Qf, e)));
+        }
+        if (STORE)
+            for (int i = 0; i < m; ++i) U_new[(size_t)k * m + i] = u[i];
+        dynamics<SYS>(prm, x, u, xn);
+        for (int i = 0; i < n; ++i) { x[i] = xn[i]; if (STORE) X_new[(size_t)(k + 1) * n + i] = xn[i]; }
+        if (!all_finite<n>(xn)) return false;
+    }
+    if (T >= N) {
+        wrapped_error<n>(x, c.xg, c.wrap_mask, e);
+        if (!all_finite<n>(e)) inf = true;
+        J = add(acc, mul(0.5, quad_form<n>(c.Qf, e)));
+    }
+    *J_out = inf ? HUGE_VAL : J;
+    return true;
+}
+
 }}  // namespace hop::ddp

@@ -84,7 +84,8 @@ __device__ __noinline__ void select_fused_seq_cold(const FusedArgs& p, int b, do
 
 // MODE 0: EXACT, 1: FAST sequential, 2: FAST software-pipelined (hop_select_pipe_body.cuh) with MODE 1 as its cold path,
 // 3: as 2 with the pivot sweep as run-time loops over groups of four pivots (a quarter of the code),
-// 4: as 3 with the pivot row / column exchange through shared memory instead of shuffles
+// 4: as 3 with the pivot row / column exchange through shared memory instead of shuffles,
+// 5: as 4 with two pivots per loop trip (compile-time buffer parity) and high-word zeroing of the pivot row
 template <int D, int M, int MODE, int MINB>
 __global__ void __launch_bounds__(kMmaWarps * 32, MINB) k_select_fused_mma(const FusedArgs p) {
     extern __shared__ __align__(16) double smem[];
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32, MINB) k_select_fused_mma(const
     double* scratch = smem + (size_t)warp * mma::kWarpScratch;
     if (MODE >= 2) {
         if (b >= p.B || (p.skip && p.skip[b])) return;
-        if (mma::select_fused_pipe_body<D, M, MODE == 4 ? 2 : MODE == 3 ? 1 : 0>(p, b, scratch, cst)) return;
+        if (mma::select_fused_pipe_body<D, M, MODE == 5 ? 3 : MODE == 4 ? 2 : MODE == 3 ? 1 : 0>(p, b, scratch, cst)) return;
         select_fused_seq_cold<D, M>(p, b, scratch, cst);
     } else {
         mma::select_fused_body<D, M, MODE>(p, b, scratch, cst);
@@ -221,14 +222,17 @@ int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st) {
     if (n == 12 && m == 4) {
         if (p.mode != HOP_MODE_FAST) return launch_fused_mma<13, 4, 0>(p, st);
         // A/B switches (all variants compute the same function): HOP_FAST_SEQ=1 sequential sweep, HOP_PIPE_UNROLL=1 unrolled
-        // pipelined sweep, HOP_PIPE_SHFL=1 looped sweep with the shuffle exchange; default: looped + shared-memory exchange
+        // pipelined sweep, HOP_PIPE_SHFL=1 looped sweep with the shuffle exchange, HOP_PIPE_U2=0 one pivot per loop trip;
+        // default: shared-memory exchange, two pivots per trip, high-word zeroing
         static const bool seq = getenv("HOP_FAST_SEQ") && atoi(getenv("HOP_FAST_SEQ")) != 0;
         static const bool unrolled = getenv("HOP_PIPE_UNROLL") && atoi(getenv("HOP_PIPE_UNROLL")) != 0;
         static const bool shfl = getenv("HOP_PIPE_SHFL") && atoi(getenv("HOP_PIPE_SHFL")) != 0;
         if (seq) return launch_fused_mma<13, 4, 1>(p, st);
         if (unrolled) return launch_fused_mma<13, 4, 2>(p, st);
         if (shfl) return launch_fused_mma<13, 4, 3>(p, st);
-        return launch_fused_mma<13, 4, 4>(p, st);
+        static const bool u1 = getenv("HOP_PIPE_U2") && atoi(getenv("HOP_PIPE_U2")) == 0;   // HOP_PIPE_U2=0: one pivot per loop trip
+        if (u1) return launch_fused_mma<13, 4, 4>(p, st);
+        return launch_fused_mma<13, 4, 5>(p, st);
     }
     set_last_error("hop_select_fused_f64: (n, m) not instantiated; supported: (2,1) (4,1) (12,4)");
     return HOP_E_UNSUPPORTED_DIMS;

@@ -199,6 +199,21 @@ HOP_DEVICE void ld2(const double* p, double& a, double& b) {
     a = p[0]; b = p[1];
 #endif
 }
+// a, or a value that acts as zero, when z: only the HIGH word is cleared (one SEL instead of two).  What is left is
+// the low word read as a subnormal (< 2^-1042); the only consumer is the addend of  fma(x, y, .)  with |x y| > 1e-290
+// (or x y == 0 exactly, and then a == 0 and its low word is zero too), so the rounded result is the one a true zero gives
+// (a product that is an exact rounding tie, probability 2^-53, aside).
+HOP_DEVICE double zero_hi_if(double a, bool z) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(z ? 0 : __double2hiint(a), __double2loint(a));
+#else
+    unsigned long long bits;
+    __builtin_memcpy(&bits, &a, 8);
+    if (z) bits &= 0xffffffffull;
+    __builtin_memcpy(&a, &bits, 8);
+    return a;
+#endif
+}
 template <int GI>
 HOP_DEVICE void gjs_store(const Mat& a, double* buf, bool isrow, int t) {      // pivot row: lanes g == gj
     if (isrow) {
@@ -210,7 +225,7 @@ template <int GI, int GS>
 HOP_DEVICE void fes_store(const Mat& a, double* buf, bool iscol, int g) {      // pivot COLUMN (lower tiles): lanes t == tj
     if (iscol) st2(buf + 2 * g, a.v[0][GI][GS], a.v[1][GI][GS]);
 }
-template <int D, int GI, int GS>
+template <int D, int GI, int GS, bool HIZ = false>
 HOP_DEVICE void gjs_apply(Mat& a, int tj, const LaneGeo& L, int& signs, const double* buf, bool isrow, bool iscol) {
     double pr[2][2], f[2];
     ld2(buf + 4 * L.t, pr[0][0], pr[1][0]);
@@ -226,7 +241,13 @@ HOP_DEVICE void gjs_apply(Mat& a, int tj, const LaneGeo& L, int& signs, const do
         a.v[1][GI][GS] = 0.0;
         pr[GI][GS] = -1.0;
     }
-    if (isrow) {
+    if (HIZ) {
+#pragma unroll
+        for (int J = 0; J < 2; ++J)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) a.v[GI][J][s] = zero_hi_if(a.v[GI][J][s], isrow);
+        if (isrow) f[GI] = -rinv;
+    } else if (isrow) {
 #pragma unroll
         for (int J = 0; J < 2; ++J)
 #pragma unroll
@@ -256,27 +277,38 @@ HOP_DEVICE void fes_apply(Mat& a, int tj, const LaneGeo& L, int& signs, double& 
 #pragma unroll
     for (int s = 0; s < 2; ++s) a.v[1][1][s] = fma(-f[1], pr[1][s], a.v[1][1][s]);
 }
-// one pivot round of the three sweeps; a1, a2 hold NEGATED matrices (see above), x the lower tiles of X0 + eps I
-template <int D, int GI, int GS>
+// one pivot round of the three sweeps; a1, a2 hold NEGATED matrices (see above), x the lower tiles of X0 + eps I.
+// PAR: parity of the exchange buffer, -1 = tj & 1 at run time; a compile-time parity turns every shared-memory address
+// of the round into base register + immediate.
+template <int D, int GI, int GS, int PAR = -1, bool HIZ = false>
 HOP_DEVICE void gj3s_round(Mat& a1, Mat& a2, Mat& x, int tj, const LaneGeo& L, int& signs, double& p, double* rowb) {
     const int gj = 2 * tj + GS;
     const bool isrow = (L.g == gj), iscol = (L.t == tj);
-    double* buf = rowb + (tj & 1) * 48;
+    double* buf = rowb + (PAR < 0 ? (tj & 1) : PAR) * 48;
     gjs_store<GI>(a1, buf, isrow, L.t);
     gjs_store<GI>(a2, buf + 16, isrow, L.t);
     fes_store<GI, GS>(x, buf + 32, iscol, L.g);
     simt::sync();
-    gjs_apply<D, GI, GS>(a1, tj, L, signs, buf, isrow, iscol);
-    gjs_apply<D, GI, GS>(a2, tj, L, signs, buf + 16, isrow, iscol);
+    gjs_apply<D, GI, GS, HIZ>(a1, tj, L, signs, buf, isrow, iscol);
+    gjs_apply<D, GI, GS, HIZ>(a2, tj, L, signs, buf + 16, isrow, iscol);
     fes_apply<D, GI, GS>(x, tj, L, signs, p, buf + 32);
 }
-template <int D, int GI, int GS, bool UNROLL>
+// U2: the run-time loop advances two pivots per trip (buffer parity known at compile time, half the loop overhead,
+// twice the code of the plain loop) and the pivot-row zeroing is a high-word select (zero_hi_if)
+template <int D, int GI, int GS, bool UNROLL, bool U2 = false>
 HOP_DEVICE void gj3s_group(Mat& a1, Mat& a2, Mat& x, const LaneGeo& L, int& signs, double& p, double* rowb) {
     constexpr int first = 8 * GI + 4 * GS;
     constexpr int cnt = (D - first) < 4 ? (D - first) : 4;
     if (UNROLL) {
 #pragma unroll
         for (int tj = 0; tj < cnt; ++tj) gj3s_round<D, GI, GS>(a1, a2, x, tj, L, signs, p, rowb);
+    } else if (U2) {
+#pragma unroll 1
+        for (int tj = 0; tj + 1 < cnt; tj += 2) {
+            gj3s_round<D, GI, GS, 0, true>(a1, a2, x, tj, L, signs, p, rowb);
+            gj3s_round<D, GI, GS, 1, true>(a1, a2, x, tj + 1, L, signs, p, rowb);
+        }
+        if (cnt & 1) gj3s_round<D, GI, GS, 0, true>(a1, a2, x, cnt - 1, L, signs, p, rowb);
     } else {
 #pragma unroll 1
         for (int tj = 0; tj < cnt; ++tj) gj3s_round<D, GI, GS>(a1, a2, x, tj, L, signs, p, rowb);
@@ -368,7 +400,8 @@ HOP_DEVICE void rank1_add(Mat& Dm, const double (&r)[2], const double (&c)[2][2]
 // tiles keeps it (error at T* 8e-8 instead of 4e-10 on the S1 goldens).  X0 only feeds pivots and is fine.
 
 // Returns true when the problem was solved by the pipelined sweep; false => caller must run the sequential body.
-// SCHED 0: unrolled sweep, shuffle exchange; 1: looped sweep, shuffle exchange; 2: looped sweep, shared-memory exchange
+// SCHED 0: unrolled sweep, shuffle exchange; 1: looped sweep, shuffle exchange; 2: looped sweep, shared-memory exchange;
+// 3: as 2 with two pivots per loop trip and high-word zeroing of the pivot row
 template <int D, int M, int SCHED>
 HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratch, const double* cst) {
     using FC = FusedConst<D, M>;
@@ -377,7 +410,7 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
     using PS = PipeSlab;
     constexpr int n = D - 1;
     constexpr int NT = (D + 7) / 8, KB = (D + 3) / 4, KBM = (M + 3) / 4, NTM = (M + 7) / 8;
-    constexpr bool LOOPED = (SCHED != 0), SMX = (SCHED == 2);
+    constexpr bool LOOPED = (SCHED != 0), SMX = (SCHED >= 2), U2 = (SCHED == 3);
     double* rowb = scratch + PipeSlab::ROWB;
     constexpr bool R1 = LastCol<D>::split;          // last k-block as a rank-1 DFMA update
     constexpr int KD = R1 ? KB - 1 : KB;            // k-blocks left on the tensor pipe
@@ -599,13 +632,13 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
         vecA(V, k + 2, xcur, ucur);
         int signs = 0;
         if (SMX) {
-            gj3s_group<D, 0, 0, false>(W, Wt, X0, L, signs, piv, rowb);
+            gj3s_group<D, 0, 0, false, U2>(W, Wt, X0, L, signs, piv, rowb);
             vecB(V);
-            gj3s_group<D, 0, 1, false>(W, Wt, X0, L, signs, piv, rowb);
+            gj3s_group<D, 0, 1, false, U2>(W, Wt, X0, L, signs, piv, rowb);
             vecC(V, k + 2);
-            gj3s_group<D, 1, 0, false>(W, Wt, X0, L, signs, piv, rowb);
+            gj3s_group<D, 1, 0, false, U2>(W, Wt, X0, L, signs, piv, rowb);
             vecD(V, do_vec);
-            gj3s_group<D, 1, 1, false>(W, Wt, X0, L, signs, piv, rowb);
+            gj3s_group<D, 1, 1, false, U2>(W, Wt, X0, L, signs, piv, rowb);
         } else {
             gj3_group<D, 0, 0, !LOOPED>(W, Wt, X0, L, signs, piv);
             vecB(V);
