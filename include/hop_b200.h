@@ -196,6 +196,9 @@ int hop_test_set_linearize_variant(int variant);
  * < -1 = query only.  Below the threshold the lane-group kernel runs; the two produce identical bits.  Returns the
  * previous value. */
 long hop_test_set_tpp_min_batch(long min_batch);
+/* Test hook: fused selection kernel of the small systems (n <= 4), 0 = one matrix element per lane, a warp per problem
+ * [default], 1 = lane group per problem; identical bits.  Returns the previous value. */
+int hop_test_set_fused_small_variant(int variant);
 /* Test hook: line-search kernel, 0 = the five step sizes side by side, six threads per problem [default], 1 = one thread
  * per problem trying them in turn; identical bits.  Returns the previous value. */
 int hop_test_set_linesearch_variant(int variant);

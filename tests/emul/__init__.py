@@ -29,7 +29,7 @@ class FusedArgs(C.Structure):
 def build(force=False):
     srcs = [os.path.join(_HERE, f) for f in ("simt_emul.cpp", "simt_emul.h", "emul_select.cpp")]
     srcs += [os.path.join(_CSRC, f) for f in ("hop_select_core.cuh", "hop_select_body.cuh", "hop_simt.cuh", "hop_mma.cuh",
-                                              "hop_select_mma_body.cuh", "hop_select_pipe_body.cuh", "hop_select_scan_body.cuh", "hop_select_gpipe_body.cuh", "hop_select_tpp_body.cuh")]
+                                              "hop_select_mma_body.cuh", "hop_select_pipe_body.cuh", "hop_select_scan_body.cuh", "hop_select_gpipe_body.cuh", "hop_select_tpp_body.cuh", "hop_select_epl_body.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-DHOP_HOST_EMUL", "-Wno-unknown-pragmas", "-I" + _HERE, "-I" + _CSRC, "-fPIC",
                                "-shared", "-o", _SO, os.path.join(_HERE, "simt_emul.cpp"),
@@ -71,7 +71,7 @@ def select_generic(A_aug, B_aug, Q_aug, R_inv, z0, QT, T_min, T_max, w_explicit=
 
 
 def select_fused(A, Bm, a_resid, X, U, xg, w, u_ref, Q, R, Qf, wrap_mask, T_min, T_max, q_reg=1e-9, rho_reg=1e-12,
-                 jitter=1e-9, max_tries=8, mma=False, mode=0):
+                 jitter=1e-9, max_tries=8, mma=False, mode=0, epl=False):
     A, Bm, X, U, xg, w, u_ref, Q, R, Qf = map(_d, (A, Bm, X, U, xg, w, u_ref, Q, R, Qf))
     ar = None if a_resid is None else _d(a_resid)
     Bsz, N, n = A.shape[:3]
@@ -81,7 +81,7 @@ def select_fused(A, Bm, a_resid, X, U, xg, w, u_ref, Q, R, Qf, wrap_mask, T_min,
                   0 if U.ndim == 2 else U.shape[1] * U.shape[2], _p(xg), _p(w), _p(u_ref),
                   _p(Q), _p(R), _p(Qf), wrap_mask, q_reg, rho_reg, mode, None, _p(J), T.ctypes.data_as(_ip), _p(Js),
                   st.ctypes.data_as(_ip))
-    rc = (lib().emul_select_fused_mma if mma else lib().emul_select_fused)(n, m, C.byref(a))
+    rc = (lib().emul_select_fused_epl if epl else lib().emul_select_fused_mma if mma else lib().emul_select_fused)(n, m, C.byref(a))
     assert rc == 0, f"emulated kernel failed rc={rc}"
     return J, T, Js, st
 

@@ -9,6 +9,7 @@
 #include "hop_select_scan_body.cuh"
 #include "hop_select_gpipe_body.cuh"
 #include "hop_select_tpp_body.cuh"
+#include "hop_select_epl_body.cuh"
 
 namespace {
 template <int D, int M, int G>
@@ -224,5 +225,32 @@ extern "C" int emul_select_generic_tpp(int d, int m, const hop::SelectArgs* p) {
     if (d == 3 && m == 1) return run_generic_tpp<3, 1>(*p);
     if (d == 4 && m == 2) return run_generic_tpp<4, 2>(*p);
     if (d == 5 && m == 1) return run_generic_tpp<5, 1>(*p);
+    return -2;
+}
+
+// ---- element-per-lane fused body of the small systems (hop_select_epl_body.cuh): one warp per problem
+namespace {
+template <int D, int M>
+struct EplJob { const hop::FusedArgs* p; int b; double* scratch; const double* cst; };
+template <int D, int M>
+void epl_lane(void* a) {
+    auto* j = (EplJob<D, M>*)a;
+    hop::epl::select_fused_epl_body<D, M>(*j->p, j->b, j->scratch, j->cst);
+}
+template <int D, int M>
+int run_fused_epl(const hop::FusedArgs& p) {
+    std::vector<double> scratch(2 * D * ((D + 1) & ~1), -7.0);
+    std::vector<double> cst(hop::FusedConst<D, M>::SIZE, 0.0);
+    hop::fused_const_fill<D, M>(p, cst.data(), 0, 1);
+    for (int b = 0; b < p.B; ++b) {
+        EplJob<D, M> j{&p, b, scratch.data(), cst.data()};
+        if (hop::simt::run_warp(epl_lane<D, M>, &j)) return -1;
+    }
+    return 0;
+}
+}  // namespace
+extern "C" int emul_select_fused_epl(int n, int m, const hop::FusedArgs* p) {
+    if (n == 2 && m == 1) return run_fused_epl<3, 1>(*p);
+    if (n == 4 && m == 1) return run_fused_epl<5, 1>(*p);
     return -2;
 }

@@ -163,3 +163,27 @@ def test_emulated_thread_per_problem_kernel_is_bit_identical_to_the_lane_group_k
     assert np.array_equal(Jt, Jg, equal_nan=True) and np.array_equal(Jst, Jsg, equal_nan=True)
     Jo, _ = O.propagator_batch(A[:1], B[:1], Q[:1], Rinv[:1], z0[:1], QT[:1], T_use=N - 1)
     assert rel(Jt[:1], Jo) <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["DoubleIntegrator", "Segway_Balance", "Cartpole_SwingUp"])
+def test_emulated_element_per_lane_fused_kernel_is_bit_identical_to_the_lane_group_kernel(name):
+    """hop_select_epl_body.cuh (a warp per problem, lane 5r + c owns element (r, c), everything by shuffles) performs the
+    lane-group kernel's IEEE operations element for element: J, T*, J*, status identical bit for bit on the nominal
+    trajectories of the reference cases, with per-instance goals / weights, a residual a_k, and a NaN in one instance."""
+    g = golden("case_" + name)
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case(name, N=int(g["N"]))
+    n = x0.size
+    T_max = min(T_max, 60); T_min = min(T_min, 20)
+    rng = np.random.default_rng(1)
+    B = 3
+    A = np.repeat(g["A_fwd"][None], B, 0); Bm = np.repeat(g["B_fwd"][None], B, 0)
+    X = np.repeat(g["X"][None], B, 0) + 1e-3 * rng.standard_normal((B,) + g["X"].shape)
+    U = np.repeat(g["U"][None], B, 0); ar = np.repeat(g["a_resid"][None], B, 0) + 1e-4 * rng.standard_normal((B,) + g["a_resid"].shape)
+    xgs = xg[None] + 0.01 * rng.standard_normal((B, n)); ws = w * np.array([1.0, 0.5, 2.0])
+    A[2, 5, 0, 0] = np.nan
+    args = (A, Bm, ar, X, U, xgs, ws, u_ref, Q, R, O.as_terminal_weight(alpha, n), O.wrap_mask(wrap_idx), T_min, T_max)
+    Jg, Tg, Jsg, stg = emul.select_fused(*args)
+    Je, Te, Jse, ste = emul.select_fused(*args, epl=True)
+    assert (stg[2] & 0xFF) == 1 and (stg[0] & 0xFF) == 0
+    assert np.array_equal(ste, stg) and np.array_equal(Te, Tg)
+    assert np.array_equal(Je, Jg, equal_nan=True) and np.array_equal(Jse, Jsg, equal_nan=True)

@@ -390,6 +390,29 @@ def test_warp_and_thread_backward_kernels_agree_bit_for_bit(name):
         assert torch.equal(torch.nan_to_num(out[0][key].double(), nan=-1.0), torch.nan_to_num(out[1][key].double(), nan=-1.0)), key
 
 
+@pytest.mark.parametrize("name", ["DoubleIntegrator", "Segway_Balance", "Cartpole_SwingUp"])
+def test_element_per_lane_and_lane_group_fused_kernels_agree_bit_for_bit(name):
+    """The fused selection of the small systems has two device mappings (a warp per problem with one matrix element per
+    lane -- the low-latency default -- and a lane group per problem).  Same IEEE operations per element => the whole
+    batched HOP-DDP solve (every selection of every iteration feeds the next one) is identical bit for bit."""
+    from hop import _cabi
+    lib = _cabi.require_device()
+    case = cases.make_case(name)
+    n = case[1].size
+    rng = np.random.default_rng(6)
+    x0s = case[1][None] + 0.2 * rng.standard_normal((41, n))
+    out = {}
+    try:
+        for variant in (0, 1):
+            lib.hop_test_set_fused_small_variant(variant)
+            out[variant] = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=5, use_central_diff=False, mode=api.MODE_EXACT)
+    finally:
+        lib.hop_test_set_fused_small_variant(0)
+    for key in ("X", "U", "J_hist", "T_hist", "n_hist", "T_star", "J_curve", "status"):
+        assert torch.equal(torch.nan_to_num(out[0][key].double(), nan=-1.0), torch.nan_to_num(out[1][key].double(), nan=-1.0)), key
+    assert torch.isfinite(out[0]["J_curve"]).any()
+
+
 @pytest.mark.parametrize("name", CASE_NAMES)
 def test_parallel_and_serial_line_search_kernels_agree_bit_for_bit(name):
     """forward_linesearch_fixedT has two device mappings: the five step sizes side by side (six threads per problem, the

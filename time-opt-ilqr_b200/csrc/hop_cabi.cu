@@ -19,6 +19,7 @@ int dispatch_linearize(int B, int sys, const double* params_host, int N, const d
 extern int g_linearize_variant;
 extern int g_backward_variant;
 extern int g_linesearch_variant;
+extern int g_fused_small_variant;
 struct DdpConst {
     const double *xg, *w, *u_ref, *Q, *R, *Qf;
     unsigned wrap_mask;
@@ -415,6 +416,12 @@ int hop_test_set_backward_variant(int variant) {
 int hop_test_set_linesearch_variant(int variant) {
     const int old = g_linesearch_variant;
     if (variant == 0 || variant == 1) g_linesearch_variant = variant;
+    return old;
+}
+
+int hop_test_set_fused_small_variant(int variant) {
+    const int old = g_fused_small_variant;
+    if (variant == 0 || variant == 1) g_fused_small_variant = variant;
     return old;
 }
 

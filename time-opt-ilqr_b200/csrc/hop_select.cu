@@ -194,6 +194,8 @@ static int launch_fused_mma(const FusedArgs& p, cudaStream_t st) {
 // one problem per THREAD (d <= 5, large batches): hop_select_tpp.cu.  Returns HOP_E_UNSUPPORTED_DIMS without touching the
 // error string when (d, m, p) is not for that kernel.
 int dispatch_select_generic_tpp(int d, int m, const SelectArgs& p, cudaStream_t st);
+// one matrix element per LANE, fused form of the small systems: hop_select_epl.cu (same convention)
+int dispatch_select_fused_epl(int n, int m, const FusedArgs& p, cudaStream_t st);
 
 int dispatch_select_generic(int d, int m, int mode, const SelectArgs& p, cudaStream_t st) {
     if (mode == HOP_MODE_SCAN) {
@@ -217,6 +219,10 @@ int dispatch_select_generic(int d, int m, int mode, const SelectArgs& p, cudaStr
 }
 
 int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st) {
+    if (n <= 4) {
+        const int rc = dispatch_select_fused_epl(n, m, p, st);
+        if (rc != HOP_E_UNSUPPORTED_DIMS) return rc;
+    }
     if (n == 2 && m == 1) return launch_fused<3, 1, 4>(p, st);
     if (n == 4 && m == 1) return launch_fused<5, 1, 8>(p, st);
     if (n == 12 && m == 4) {
