@@ -36,8 +36,12 @@ static int launch_fused_epl(const FusedArgs& p, cudaStream_t st) {
 // identical bits)
 int g_fused_small_variant = getenv("HOP_FUSED_LANES") ? atoi(getenv("HOP_FUSED_LANES")) : 0;
 
+// A warp per problem only pays while the batch leaves the machine empty (measured on B200, x0 -> T* pipeline, element per
+// lane vs lane group: Segway B = 25 0.86 vs 1.30 ms, Cartpole B = 25 1.42 vs 2.13 ms, DI B = 25 0.28 vs 0.40 ms; at
+// B = 4096 the lane-group kernel, which packs 4-8 problems into a warp, is ahead: 2.15 vs 1.88 ms).  $HOP_EPL_MAX_BATCH overrides.
 int dispatch_select_fused_epl(int n, int m, const FusedArgs& p, cudaStream_t st) {
-    if (g_fused_small_variant != 0) return HOP_E_UNSUPPORTED_DIMS;
+    static const long max_batch = getenv("HOP_EPL_MAX_BATCH") ? atol(getenv("HOP_EPL_MAX_BATCH")) : 1024;
+    if (g_fused_small_variant != 0 || p.B > max_batch) return HOP_E_UNSUPPORTED_DIMS;
     if (n == 2 && m == 1) return launch_fused_epl<3, 1>(p, st);
     if (n == 4 && m == 1) return launch_fused_epl<5, 1>(p, st);
     return HOP_E_UNSUPPORTED_DIMS;
