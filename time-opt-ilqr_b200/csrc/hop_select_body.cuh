@@ -82,22 +82,53 @@ HOP_DEVICE void select_generic_body(const SelectArgs& p, int b_raw, double* sm) 
     const size_t base = (size_t)b * p.N;
     double* SA = sm + Ge::SA; double* SX = sm + Ge::SX; double* SQ = sm + Ge::SQ; double* SB = sm + Ge::SB;
 
-    for (int k = 0; k < p.T_max; ++k) {
+    // The blocks of step k+1 are loaded into registers while step k computes (every lane owns the elements
+    // i = r, r + G, ... of each block) and moved to the slab at the top of step k+1: the global-load latency, which
+    // was exposed once per step (ncu: long_scoreboard 2.2 per issue, the top stall), hides behind the sweep.
+    constexpr int PA = (D * D + G - 1) / G, PB = (D * M + G - 1) / G, PR = (M * M + G - 1) / G;
+    struct Fetch { double a[PA], q[PA], t[PA], b[PB], ri[PR]; };
+    auto fetch = [&](int k, Fetch& f) {
         const double* Ak = p.A_aug + (base + k) * D * D;
         const double* Qk = p.Q_aug + (base + k) * D * D;
         const double* Tk = p.QT + (base + k) * D * D;
         const double* Bk = p.B_aug + (base + k) * D * M;
-        simt::sync();
-        for (int i = r; i < D * D; i += G) {
-            const int row = i / D, col = i % D;
-            SA[col * DP + row] = Ak[i];
-            SX[row * DP + col] = Qk[i];
-            SQ[row * DP + col] = Tk[i];
+#pragma unroll
+        for (int u = 0; u < PA; ++u) {
+            const int i = r + u * G;
+            const bool in = i < D * D;
+            f.a[u] = in ? Ak[i] : 0.0; f.q[u] = in ? Qk[i] : 0.0; f.t[u] = in ? Tk[i] : 0.0;
         }
-        for (int i = r; i < D * M; i += G) SB[(i % M) * DP + (i / M)] = Bk[i];
-        if (p.rinv_step_stride)
-            for (int i = r; i < M * M; i += G)
-                sm[Ge::SR + (i / M) * Ge::MP + (i % M)] = p.R_inv[(size_t)b * rinv_inst + (size_t)k * p.rinv_step_stride + i];
+#pragma unroll
+        for (int u = 0; u < PB; ++u) { const int i = r + u * G; f.b[u] = (i < D * M) ? Bk[i] : 0.0; }
+        if (p.rinv_step_stride) {
+#pragma unroll
+            for (int u = 0; u < PR; ++u) {
+                const int i = r + u * G;
+                f.ri[u] = (i < M * M) ? p.R_inv[(size_t)b * rinv_inst + (size_t)k * p.rinv_step_stride + i] : 0.0;
+            }
+        }
+    };
+    Fetch cur;
+    fetch(0, cur);
+    for (int k = 0; k < p.T_max; ++k) {
+        simt::sync();
+#pragma unroll
+        for (int u = 0; u < PA; ++u) {
+            const int i = r + u * G;
+            if (i < D * D) {
+                const int row = i / D, col = i % D;
+                SA[col * DP + row] = cur.a[u];
+                SX[row * DP + col] = cur.q[u];
+                SQ[row * DP + col] = cur.t[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PB; ++u) { const int i = r + u * G; if (i < D * M) SB[(i % M) * DP + (i / M)] = cur.b[u]; }
+        if (p.rinv_step_stride) {
+#pragma unroll
+            for (int u = 0; u < PR; ++u) { const int i = r + u * G; if (i < M * M) sm[Ge::SR + (i / M) * Ge::MP + (i % M)] = cur.ri[u]; }
+        }
+        if (k + 1 < p.T_max) fetch(k + 1, cur);
         simt::sync();
         {
             double q[D];
@@ -197,21 +228,42 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* sm, con
     const size_t baseN = (size_t)b * p.N;
     const size_t baseX = (size_t)b * (p.N + 1);
 
-    for (int k = 0; k < p.T_max; ++k) {
+    // Inputs of step k+1 are loaded into registers while step k computes (lane r owns the elements i = r, r + G, ... of
+    // A_k and B_k, and component r of U_k, X_k, X_{k+1}, a_k) and moved to the slab at the top of step k+1, so the
+    // global-load latency hides behind the sweep instead of being exposed once per step.
+    constexpr int PA = (n * n + G - 1) / G, PB = (n * M + G - 1) / G;
+    struct Fetch { double a[PA], b[PB], u, x0, x1, ar; };
+    auto fetch = [&](int k, Fetch& f) {
         const double* Ak = p.A + (baseN + k) * n * n;
         const double* Bk = p.Bm + (baseN + k) * n * M;
+#pragma unroll
+        for (int q = 0; q < PA; ++q) { const int i = r + q * G; f.a[q] = (i < n * n) ? Ak[i] : 0.0; }
+#pragma unroll
+        for (int q = 0; q < PB; ++q) { const int i = r + q * G; f.b[q] = (i < n * M) ? Bk[i] : 0.0; }
+        f.u = (r < M) ? p.U[(size_t)b * p.u_stride + (size_t)k * M + r] : 0.0;
+        f.x0 = isx ? p.X[(baseX + k) * n + r] : 0.0;
+        f.x1 = isx ? p.X[(baseX + k + 1) * n + r] : 0.0;
+        f.ar = (isx && p.a_resid) ? p.a_resid[(baseN + k) * n + r] : 0.0;
+    };
+    Fetch cur;
+    fetch(0, cur);
+    for (int k = 0; k < p.T_max; ++k) {
         simt::sync();
         // ---- A_aug^T, B_aug^T (augmented.py:50-56)
-        for (int i = r; i < n * n; i += G) SA[(i % n) * DP + (i / n)] = Ak[i];
-        for (int i = r; i < n * M; i += G) SB[(i % M) * DP + (i / M)] = Bk[i];
-        if (r < M) V3[r] = p.U[(size_t)b * p.u_stride + (size_t)k * M + r] - cst[FC::UREF + r];   // du
+#pragma unroll
+        for (int q = 0; q < PA; ++q) { const int i = r + q * G; if (i < n * n) SA[(i % n) * DP + (i / n)] = cur.a[q]; }
+#pragma unroll
+        for (int q = 0; q < PB; ++q) { const int i = r + q * G; if (i < n * M) SB[(i % M) * DP + (i / M)] = cur.b[q]; }
+        if (r < M) V3[r] = cur.u - cst[FC::UREF + r];   // du
         double ev = 0.0;
         if (isx) {
-            ev = p.X[(baseX + k) * n + r] - xg_r;                                   // e = wrap(X_k - xg)
+            ev = cur.x0 - xg_r;                                                      // e = wrap(X_k - xg)
             if (wrap_r) ev = wrap_pi(ev);
         }
         if (act) V1[r] = ev;
-        const double ak = (isx && p.a_resid) ? p.a_resid[(baseN + k) * n + r] : 0.0;
+        const double ak = cur.ar;
+        const double x_next = cur.x1;
+        if (k + 1 < p.T_max) fetch(k + 1, cur);
         simt::sync();
         if (isx) {
             double s = 0.0;
@@ -245,7 +297,7 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int b_raw, double* sm, con
         simt::sync();
         double et = 0.0;
         if (isx) {
-            et = p.X[(baseX + k + 1) * n + r] - xg_r;
+            et = x_next - xg_r;
             if (wrap_r) et = wrap_pi(et);
         }
         if (act) V1[r] = et;
