@@ -1,5 +1,6 @@
 // hop_cabi.cu -- extern "C" surface of libhop_b200.so (see include/hop_b200.h for the contract).
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -503,8 +504,10 @@ int hop_select_from_x0_host_f64(int B, int sys, const double* params_host, int N
     if (!g_host.consts_ready) {
         if (int rc = report_cuda(cudaEventCreateWithFlags(&g_host.consts_ready, cudaEventDisableTiming), "cudaEventCreate")) return rc;
     }
+    static const int chunks_max = getenv("HOP_HOST_CHUNKS") ? atoi(getenv("HOP_HOST_CHUNKS")) : kHostChunksMax;   // A/B switch
     int chunks = (B + kHostChunkMin - 1) / kHostChunkMin;
-    chunks = chunks < 1 ? 1 : (chunks > kHostChunksMax ? kHostChunksMax : chunks);
+    chunks = chunks < 1 ? 1 : (chunks > chunks_max ? chunks_max : chunks);
+    if (chunks < 1) chunks = 1;
     const int per = (((B + chunks - 1) / chunks) + 3) & ~3;       // whole CTAs of the selection kernel
     const int lanes = chunks > 1 ? 2 : 1;                         // workspaces (= streams) in use
     const bool shared_U = (u_batch_stride == 0);

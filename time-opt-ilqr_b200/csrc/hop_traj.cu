@@ -285,8 +285,9 @@ __device__ __forceinline__ void quad_fd_column(const double* p, const double* x0
     }
 }
 
-template <bool CENTRAL>
-__global__ void __launch_bounds__(128) k_linearize_quad_row(int B, DynParams prm, int N, const double* __restrict__ X,
+// MINB: CTAs per SM the register allocation is bounded for (3 -> 168 registers, 4 -> 128 with ~130 B of spills)
+template <bool CENTRAL, int MINB = 3>
+__global__ void __launch_bounds__(128, MINB) k_linearize_quad_row(int B, DynParams prm, int N, const double* __restrict__ X,
                                                             const double* __restrict__ U, long ustride, double epsx, double epsu,
                                                             double relx, double relu, int f0_from_x, const int* __restrict__ skip,
                                                             double* __restrict__ A, double* __restrict__ Bm) {
@@ -403,7 +404,9 @@ static int launch_linearize(int B, const DynParams& prm, int N, const double* X,
         if (variant == 0) {
             const size_t rows = (size_t)B * N;
             const unsigned g = (unsigned)((rows + threads - 1) / threads);
+            static const bool four = getenv("HOP_LIN_MINB") && atoi(getenv("HOP_LIN_MINB")) == 4;   // A/B switch
             if (central) k_linearize_quad_row<true><<<g, threads, 0, st>>>(B, prm, N, X, U, ustride, epsx, epsu, relx, relu, 0, skip, A, Bm);
+            else if (four) k_linearize_quad_row<false, 4><<<g, threads, 0, st>>>(B, prm, N, X, U, ustride, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm);
             else k_linearize_quad_row<false><<<g, threads, 0, st>>>(B, prm, N, X, U, ustride, epsx, epsu, relx, relu, f0_from_x, skip, A, Bm);
             return check_launch("k_linearize_quad_row");
         }
