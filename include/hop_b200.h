@@ -196,6 +196,10 @@ int hop_test_set_linearize_variant(int variant);
  * < -1 = query only.  Below the threshold the lane-group kernel runs; the two produce identical bits.  Returns the
  * previous value. */
 long hop_test_set_tpp_min_batch(long min_batch);
+/* Test hook: hop_select_f64 for d in {12, 13}: 1 = the input-only inversions E_k = chol_inv(Q_k), X_t = chol_inv(QT_t) run
+ * in a parallel pre-pass (k_preinvert), 0 = inside the sequential kernel, -1 = pre-pass for B <= 1024 only [default]; identical
+ * bits.  Returns the previous value. */
+int hop_test_set_generic_pre(int on);
 /* Test hook: fused selection kernel of the small systems (n <= 4), 0 = one matrix element per lane, a warp per problem
  * [default], 1 = lane group per problem; identical bits.  Returns the previous value. */
 int hop_test_set_fused_small_variant(int variant);

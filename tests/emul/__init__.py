@@ -15,7 +15,8 @@ _ip = C.POINTER(C.c_int)
 class SelectArgs(C.Structure):
     _fields_ = [("B", C.c_int), ("N", C.c_int), ("T_min", C.c_int), ("T_max", C.c_int), ("jitter", C.c_double),
                 ("max_tries", C.c_int), ("A_aug", _dp), ("B_aug", _dp), ("Q_aug", _dp), ("R_inv", _dp), ("z0", _dp),
-                ("QT", _dp), ("rinv_step_stride", C.c_long), ("w_explicit", _dp), ("J_out", _dp), ("T_out", _ip), ("Jstar_out", _dp), ("status", _ip)]
+                ("QT", _dp), ("rinv_step_stride", C.c_long), ("w_explicit", _dp), ("J_out", _dp), ("T_out", _ip), ("Jstar_out", _dp), ("status", _ip),
+                ("E_pre", _dp), ("X_pre", _dp), ("pre_bad", _ip)]
 
 
 class FusedArgs(C.Structure):

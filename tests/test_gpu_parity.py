@@ -390,6 +390,37 @@ def test_warp_and_thread_backward_kernels_agree_bit_for_bit(name):
         assert torch.equal(torch.nan_to_num(out[0][key].double(), nan=-1.0), torch.nan_to_num(out[1][key].double(), nan=-1.0)), key
 
 
+@pytest.mark.parametrize("d,m,N,T_max", [(12, 4, 48, 48), (13, 4, 64, 61), (13, 4, 8, 1)])
+def test_pre_inverted_and_in_kernel_sweep_b_agree_bit_for_bit(d, m, N, T_max):
+    """hop_select_f64, d in {12, 13}: the input-only inversions E_k = chol_inv(Q_k), X_t = chol_inv(QT_t) either run
+    inside the sequential kernel (sweep B) or in a parallel pre-pass over every (problem, step) with the same interleaved
+    sweep.  Same bits -- including instances that leave the pipelined path (ladder, LU fallback, NaN)."""
+    from hop import _cabi
+    lib = _cabi.require_device()
+    B = 23
+    A, Bm, Q, R, z0, w, QT = s2_batch(range(B), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    if T_max > 8:
+        Q[1, 3] = np.diag(np.r_[np.ones(d - 1), -1e-4])       # ladder
+        QT[2, 5] = -np.eye(d)                                  # LU fallback
+        A[B - 1, 7, 1, 1] = np.nan
+    args = (_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, T_max)
+    out = {}
+    try:
+        for on in (0, 1):
+            lib.hop_test_set_generic_pre(on)
+            sel = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w))
+            out[on] = tuple(x.cpu().numpy() for x in (sel.J, sel.T_star, sel.J_star, sel.status))
+    finally:
+        lib.hop_test_set_generic_pre(-1)
+    for a, b in zip(out[1], out[0]):
+        assert np.array_equal(a, b, equal_nan=True)
+    if T_max > 8:
+        st = out[1][3]
+        assert st[1] == 0x300 or st[1] == 0x100
+        assert st[2] == 0x300 and (st[B - 1] & 0xFF) == 1 and st[0] == 0
+
+
 @pytest.mark.parametrize("name", ["DoubleIntegrator", "Segway_Balance", "Cartpole_SwingUp"])
 def test_element_per_lane_and_lane_group_fused_kernels_agree_bit_for_bit(name):
     """The fused selection of the small systems has two device mappings (a warp per problem with one matrix element per

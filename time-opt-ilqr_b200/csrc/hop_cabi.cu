@@ -21,6 +21,7 @@ extern int g_linearize_variant;
 extern int g_backward_variant;
 extern int g_linesearch_variant;
 extern int g_fused_small_variant;
+extern int g_generic_pre;
 struct DdpConst {
     const double *xg, *w, *u_ref, *Q, *R, *Qf;
     unsigned wrap_mask;
@@ -423,6 +424,12 @@ int hop_test_set_linesearch_variant(int variant) {
 int hop_test_set_fused_small_variant(int variant) {
     const int old = g_fused_small_variant;
     if (variant == 0 || variant == 1) g_fused_small_variant = variant;
+    return old;
+}
+
+int hop_test_set_generic_pre(int on) {
+    const int old = g_generic_pre;
+    if (on >= -1 && on <= 1) g_generic_pre = on;
     return old;
 }
 

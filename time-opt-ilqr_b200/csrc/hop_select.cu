@@ -147,14 +147,92 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) k_select_generic_pipe(const
     if (mma::select_generic_pipe_body<D, M>(p, b, slab)) return;
     select_generic_seq_cold<D, M>(p, b, slab);
 }
+// ---- pre-inverted input blocks: E_k = chol_inv(Q_k), X_t = chol_inv(QT_t) for every (problem, step) in parallel --------
+constexpr int kPreWarps = 4;
+// four lanes per matrix, eight matrices per warp; matrix index = 2 (b T_max + k) + {0: Q_aug, 1: QT}
+template <int D>
+__global__ void __launch_bounds__(kPreWarps * 32) k_preinvert(const SelectArgs p, double* E, double* X, int* bad) {
+    const size_t mat = ((size_t)blockIdx.x * kPreWarps * 32 + threadIdx.x) >> 2;
+    const size_t total = 2 * (size_t)p.B * p.T_max;
+    const bool live = mat < total;
+    const size_t mm = live ? mat : total - 1;                                    // idle groups shadow the last matrix
+    const size_t task = mm >> 1, b = task / p.T_max, k = task % p.T_max;
+    const size_t off = (b * p.N + k) * D * D;
+    mma::pre_invert_cols<D>(((mm & 1) ? p.QT : p.Q_aug) + off, p.jitter, ((mm & 1) ? X : E) + off, bad + b, live);
+}
+template <int D, int M>
+__global__ void __launch_bounds__(kMmaWarps * 32, 3) k_select_generic_pipe_pre(const SelectArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * kMmaWarps + warp;
+    if (b >= p.B) return;
+    double* slab = smem + (size_t)warp * mma::GpipeSlab<D, M>::SIZE;
+    if (mma::select_generic_pipe_body<D, M, true>(p, b, slab)) return;
+    select_generic_seq_cold<D, M>(p, b, slab);
+}
+
+// workspace of the pre-pass: one cached device arena per process (E, X: 2 N d^2 doubles per problem, + one flag), bounded
+// by kPreArenaMax -- larger batches run as consecutive chunks on the caller's stream, which orders the re-use.
+namespace {
+struct PreArena { void* buf = nullptr; size_t cap = 0; int device = -1; };
+PreArena g_pre;
+constexpr size_t kPreArenaMax = (size_t)8 << 30;
+}  // namespace
+// 1: always, 0: never (sweep B inside the sequential kernel), -1 [default]: for small batches only.  Measured on B200
+// (S2, d = 13, N = 128): B = 8: 0.95 -> 0.76 ms (one sweep latency per step instead of two); B = 65 536: 63.3 -> 68.2 ms
+// (sequential kernel 63.3 -> 46.5 ms, but the pre-pass moves 45 GB and costs 19.8 ms): it pays where latency matters.
+int g_generic_pre = getenv("HOP_GENERIC_PRE") ? atoi(getenv("HOP_GENERIC_PRE")) : -1;
+constexpr int kGenericPreMaxBatch = 1024;
+
 template <int D, int M>
 static int launch_generic_pipe(const SelectArgs& p, cudaStream_t st) {
     const size_t smem = sizeof(double) * (size_t)kMmaWarps * mma::GpipeSlab<D, M>::SIZE;
-    cudaError_t e = cudaFuncSetAttribute(k_select_generic_pipe<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return report_cuda(e, "cudaFuncSetAttribute(k_select_generic_pipe)");
-    const int grid = (p.B + kMmaWarps - 1) / kMmaWarps;
-    k_select_generic_pipe<D, M><<<grid, kMmaWarps * 32, smem, st>>>(p);
-    return check_launch("k_select_generic_pipe");
+    if (g_generic_pre == 0 || (g_generic_pre < 0 && p.B > kGenericPreMaxBatch)) {
+        cudaError_t e = cudaFuncSetAttribute(k_select_generic_pipe<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return report_cuda(e, "cudaFuncSetAttribute(k_select_generic_pipe)");
+        const int grid = (p.B + kMmaWarps - 1) / kMmaWarps;
+        k_select_generic_pipe<D, M><<<grid, kMmaWarps * 32, smem, st>>>(p);
+        return check_launch("k_select_generic_pipe");
+    }
+    cudaError_t e = cudaFuncSetAttribute(k_select_generic_pipe_pre<D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return report_cuda(e, "cudaFuncSetAttribute(k_select_generic_pipe_pre)");
+    const size_t per_problem = sizeof(double) * 2 * (size_t)p.N * D * D + sizeof(int);
+    size_t chunk = kPreArenaMax / per_problem;
+    if (chunk > (size_t)p.B) chunk = (size_t)p.B;
+    if (chunk < 1) chunk = 1;
+    const size_t s_mat = ((sizeof(double) * chunk * p.N * D * D + 255) / 256) * 256;
+    const size_t need = 2 * s_mat + sizeof(int) * chunk;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_pre.device != dev || need > g_pre.cap) {
+        if (g_pre.buf) { cudaDeviceSynchronize(); cudaFree(g_pre.buf); }
+        g_pre.buf = nullptr; g_pre.cap = 0; g_pre.device = dev;
+        if (int rc = report_cuda(cudaMalloc(&g_pre.buf, need), "cudaMalloc(pre-inversion arena)")) return rc;
+        g_pre.cap = need;
+    }
+    double* E = (double*)g_pre.buf;
+    double* X = (double*)((char*)g_pre.buf + s_mat);
+    int* bad = (int*)((char*)g_pre.buf + 2 * s_mat);
+    const size_t rinv_inst = (size_t)(p.rinv_step_stride ? p.N : 1) * M * M;
+    for (size_t b0 = 0; b0 < (size_t)p.B; b0 += chunk) {
+        SelectArgs q = p;
+        q.B = (int)(((size_t)p.B - b0) < chunk ? ((size_t)p.B - b0) : chunk);
+        const size_t om = b0 * p.N * D * D;
+        q.A_aug = p.A_aug + om; q.Q_aug = p.Q_aug + om; q.QT = p.QT + om;
+        q.B_aug = p.B_aug + b0 * p.N * D * M;
+        q.R_inv = p.R_inv + b0 * rinv_inst;
+        q.z0 = p.z0 + b0 * D;
+        q.w_explicit = p.w_explicit ? p.w_explicit + b0 : nullptr;
+        q.J_out = p.J_out + b0 * p.T_max; q.T_out = p.T_out + b0; q.Jstar_out = p.Jstar_out + b0; q.status = p.status + b0;
+        q.E_pre = E; q.X_pre = X; q.pre_bad = bad;
+        if (int rc = report_cuda(cudaMemsetAsync(bad, 0, sizeof(int) * (size_t)q.B, st), "memset(pre_bad)")) return rc;
+        const size_t mats = 2 * (size_t)q.B * q.T_max;                           // 8 matrices per warp
+        k_preinvert<D><<<(unsigned)((mats + 8 * kPreWarps - 1) / (8 * kPreWarps)), kPreWarps * 32, 0, st>>>(q, E, X, bad);
+        if (int rc = check_launch("k_preinvert")) return rc;
+        k_select_generic_pipe_pre<D, M><<<(q.B + kMmaWarps - 1) / kMmaWarps, kMmaWarps * 32, smem, st>>>(q);
+        if (int rc = check_launch("k_select_generic_pipe_pre")) return rc;
+    }
+    return 0;
 }
 
 template <int D, int M>

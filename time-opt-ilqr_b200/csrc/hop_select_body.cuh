@@ -22,6 +22,10 @@ struct SelectArgs {
     int* T_out;                 // [B]
     double* Jstar_out;          // [B]
     int* status;                // [B]
+    // pre-inverted input blocks (hop_select.cu: k_preinvert + k_select_generic_pipe<.., PRE>), else null:
+    // E_pre[b][k] = chol_inv(Q_aug[b][k]), X_pre[b][k] = chol_inv(QT[b][k]), pre_bad[b] != 0 => some inversion needs the ladder
+    const double *E_pre, *X_pre;
+    const int* pre_bad;
 };
 
 struct FusedArgs {

@@ -90,26 +90,124 @@ HOP_DEVICE void add_jitter(Mat& a, double eps, const LaneGeo& L) {
             if (L.row(I) == L.col(I, s) && L.row(I) < D) a.v[I][I][s] += eps;
 }
 
+// Sweep B only reads input blocks, so it has no place on the sequential critical path: with PRE the two inversions of
+// every step come from a fully parallel pre-pass (pre_invert_pair: one warp per (problem, step), the same interleaved
+// sweep, hence the same bits) and this body stages E_k / X_t instead of Q_k / QT_t -- the same bytes -- and runs one
+// sweep latency per step.  A problem whose pre-pass met a non-positive pivot or a non-finite value goes to the
+// sequential body, which owns the jitter ladder.
+template <int D>
+HOP_DEVICE void pre_invert_pair(const double* Q, const double* QT, double jitter, double* E, double* X, int* bad_out) {
+    LaneGeo L;
+    L.init();
+    Mat a1, a2;
+    mat_load(a1, Q, D, D, D, L);
+    mat_sym(a1, L);
+    mat_load(a2, QT, D, D, D, L);
+    mat_sym(a2, L);
+#pragma unroll
+    for (int I = 0; I < 2; ++I)
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+            if (L.row(I) == L.col(I, s) && L.row(I) < D) { a1.v[I][I][s] += jitter; a2.v[I][I][s] += jitter; }
+    int signs = 0;
+    gj2_group<D, 0, 0>(a1, a2, L, signs); gj2_group<D, 0, 1>(a1, a2, L, signs);
+    gj2_group<D, 1, 0>(a1, a2, L, signs); gj2_group<D, 1, 1>(a1, a2, L, signs);
+    const bool fin = mat_all_finite(a1) && mat_all_finite(a2);
+    HOP_FOR_ELEMS(I, J, s) {
+        const int R = L.row(I), C = L.col(J, s);
+        if (R < D && C < D) { E[R * D + C] = a1.v[I][J][s]; X[R * D + C] = a2.v[I][J][s]; }
+    }
+    if (L.lane == 0 && (signs < 0 || !fin)) *bad_out = 1;
+}
+
+// The same inversion, FOUR LANES PER MATRIX (lane q of a group owns columns 4q .. 4q+3, all rows, in registers): a
+// pivot costs one broadcast of the pivot column (D shuffles inside the group) instead of the fragment layout's row AND
+// column exchange per lane, and a warp inverts eight matrices at once -- the fragment sweep is shuffle bound in a
+// pre-pass (14 double shuffles per pivot and matrix, ~10 ms of shuffles alone for 65 536 x 128 steps).  Every element
+// goes through the operations of gj_pivot (rinv = pivot_rcp3(p), f_i = a_ij rinv, a_ic <- fma(-f_i, a_jc, a_ic), pivot
+// row rinv a_jc, pivot column -f_i, pivot rinv), so the result has the same bits as pre_invert_pair / sweep B.
+// src / dst: one D x D row-major block; bad_out: flag of the owning problem.
+template <int D>
+HOP_DEVICE void pre_invert_cols(const double* src, double jitter, double* dst, int* bad_out, bool live) {
+    static_assert(D > 8 && D <= 16, "four lanes x four columns");
+    const int q = simt::lane_id() & 3;
+    double a[D][4];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int C = 4 * q + cc;
+            double v = 0.0;
+            if (C < D) {
+                v = 0.5 * (src[i * D + C] + src[C * D + i]);                     // utils.py:35-37
+                if (i == C) v += jitter;                                         // utils.py:83
+            }
+            a[i][cc] = v;
+        }
+    int signs = 0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const int qj = j >> 2, cj = j & 3;                                       // owner lane of column j, its slot
+        double colv[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) colv[i] = simt::shfl(a[i][cj], qj, 4);
+        const double p = colv[j];
+        signs |= hi_word(p);
+        const double rinv = pivot_rcp3(p);
+        const bool own = (q == qj);
+        double prow[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) prow[cc] = a[j][cc];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const double f = colv[i] * rinv;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                double v;
+                if (i == j) v = fma(rinv, prow[cc], 0.0);
+                else v = fma(-f, prow[cc], a[i][cc]);
+                if (cc == cj) v = own ? ((i == j) ? rinv : -f) : v;
+                a[i][cc] = v;
+            }
+        }
+    }
+    bool fin = true;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int C = 4 * q + cc;
+            if (C < D) {
+                if (live) dst[i * D + C] = a[i][cc];
+                fin = fin && isfinite(a[i][cc]);
+            }
+        }
+    if (live && (signs < 0 || !fin)) *bad_out = 1;
+}
+
 // Returns true when the problem was solved by the pipelined sweep; false => caller must run the sequential body.
-template <int D, int M>
+template <int D, int M, bool PRE = false>
 HOP_DEVICE bool select_generic_pipe_body(const SelectArgs& p, int b, double* slab) {
     using GS_ = GpipeSlab<D, M>;
     constexpr int NT = (D + 7) / 8, KB = (D + 3) / 4, KBM = (M + 3) / 4, NTM = (M + 7) / 8;
     constexpr bool R1 = LastCol<D>::split;
     constexpr int KD = R1 ? KB - 1 : KB;
     static_assert(D > 8 && D <= 16, "one-problem-per-warp mapping: 9 <= d <= 16");
+    if (PRE && p.pre_bad[b] != 0) return false;
     LaneGeo L;
     L.init();
     const size_t base = (size_t)b * p.N;
     const size_t rinv_inst = (size_t)(p.rinv_step_stride ? p.N : 1) * M * M;
+    const double* srcQ = PRE ? p.E_pre : p.Q_aug;                               // PRE: the inverses, same layout
+    const double* srcT = PRE ? p.X_pre : p.QT;
     // ---- staging: step s -> buffer s % 3, 8-byte cp.async granules
     auto issue = [&](int s) {
         if (s < p.T_max) {
             double* st = slab + (s % 3) * GS_::STAGE;
             const double* gA = p.A_aug + (base + s) * D * D;
             const double* gB = p.B_aug + (base + s) * D * M;
-            const double* gQ = p.Q_aug + (base + s) * D * D;
-            const double* gT = p.QT + (base + s) * D * D;
+            const double* gQ = srcQ + (base + s) * D * D;
+            const double* gT = srcT + (base + s) * D * D;
             for (int i = L.lane; i < D * D; i += 32) {
                 simt::cp_async8(st + GS_::oA + i, gA + i);
                 simt::cp_async8(st + GS_::oQ + i, gQ + i);
@@ -122,8 +220,10 @@ HOP_DEVICE bool select_generic_pipe_body(const SelectArgs& p, int b, double* sla
     // chol_inv input: sym(block) + eps I  (utils.py:74,83)
     auto load_spd = [&](Mat& S, const double* src) {
         mat_load(S, src, D, D, D, L);
-        mat_sym(S, L);
-        add_jitter<D>(S, p.jitter, L);
+        if (!PRE) {
+            mat_sym(S, L);
+            add_jitter<D>(S, p.jitter, L);
+        }
     };
     auto ident = [&](Mat& S) { HOP_FOR_ELEMS(I, J, s) S.v[I][J][s] = (L.row(I) == L.col(J, s)) ? 1.0 : 0.0; };
     Mat RinvT;
@@ -145,13 +245,17 @@ HOP_DEVICE bool select_generic_pipe_body(const SelectArgs& p, int b, double* sla
         Mat E0;
         load_spd(E0, slab + 0 * GS_::STAGE + GS_::oQ);
         load_spd(Xt, slab + 0 * GS_::STAGE + GS_::oT);
-        gj2_group<D, 0, 0>(E0, Xt, L, signs); gj2_group<D, 0, 1>(E0, Xt, L, signs);
-        gj2_group<D, 1, 0>(E0, Xt, L, signs); gj2_group<D, 1, 1>(E0, Xt, L, signs);
+        if (!PRE) {
+            gj2_group<D, 0, 0>(E0, Xt, L, signs); gj2_group<D, 0, 1>(E0, Xt, L, signs);
+            gj2_group<D, 1, 0>(E0, Xt, L, signs); gj2_group<D, 1, 1>(E0, Xt, L, signs);
+        }
         Mat dummy;
         ident(dummy);
         if (p.T_max > 1) load_spd(En, slab + 1 * GS_::STAGE + GS_::oQ); else ident(En);
-        gj2_group<D, 0, 0>(En, dummy, L, signs); gj2_group<D, 0, 1>(En, dummy, L, signs);
-        gj2_group<D, 1, 0>(En, dummy, L, signs); gj2_group<D, 1, 1>(En, dummy, L, signs);
+        if (!PRE) {
+            gj2_group<D, 0, 0>(En, dummy, L, signs); gj2_group<D, 0, 1>(En, dummy, L, signs);
+            gj2_group<D, 1, 0>(En, dummy, L, signs); gj2_group<D, 1, 1>(En, dummy, L, signs);
+        }
         Mat A, Bm, Ft, G, BR;
         mat_load(A, slab + GS_::oA, D, D, D, L);
         mat_load(Bm, slab + GS_::oB, D, M, M, L);
@@ -263,8 +367,10 @@ HOP_DEVICE bool select_generic_pipe_body(const SelectArgs& p, int b, double* sla
             simt::sync();
             load_spd(Xt, stg + GS_::oT);
             if (k + 2 < p.T_max) load_spd(En, slab + ((k + 2) % 3) * GS_::STAGE + GS_::oQ); else ident(En);
-            gj2_group<D, 0, 0>(En, Xt, L, signs); gj2_group<D, 0, 1>(En, Xt, L, signs);
-            gj2_group<D, 1, 0>(En, Xt, L, signs); gj2_group<D, 1, 1>(En, Xt, L, signs);
+            if (!PRE) {
+                gj2_group<D, 0, 0>(En, Xt, L, signs); gj2_group<D, 0, 1>(En, Xt, L, signs);
+                gj2_group<D, 1, 0>(En, Xt, L, signs); gj2_group<D, 1, 1>(En, Xt, L, signs);
+            }
         }
     }
     // ---------------- epilogue: cost of the last horizon
