@@ -261,11 +261,14 @@ static int launch_fused_mma_b(const FusedArgs& p, cudaStream_t st) {
 }
 template <int D, int M, int MODE>
 static int launch_fused_mma(const FusedArgs& p, cudaStream_t st) {
-    switch (mma_min_blocks()) {
-        case 2: return launch_fused_mma_b<D, M, MODE, 2>(p, st);
-        case 4: return launch_fused_mma_b<D, M, MODE, 4>(p, st);
-        default: return launch_fused_mma_b<D, M, MODE, 3>(p, st);
+    if constexpr (MODE == 5) {   // the occupancy A/B ($HOP_MMA_MINBLOCKS) exists for the default schedule only (compile time)
+        switch (mma_min_blocks()) {
+            case 2: return launch_fused_mma_b<D, M, MODE, 2>(p, st);
+            case 4: return launch_fused_mma_b<D, M, MODE, 4>(p, st);
+            default: break;
+        }
     }
+    return launch_fused_mma_b<D, M, MODE, 3>(p, st);
 }
 
 
