@@ -619,23 +619,45 @@ HOP_DEVICE bool linesearch_candidate(const double* prm, int N, const double* X, 
                                      const double* k_list, const double* K_list, double a, double* X_new, double* U_new,
                                      double* J_out) {
     constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
+    // Small systems: the policy of step k+1 (U, X, K, k: 10 doubles for n = 4, m = 1) is loaded while step k computes --
+    // the roll-out is one dependent chain per thread and these loads were its top stall (ncu: long_scoreboard 3.7 per issue).
+    constexpr bool PF = (n * m <= 8);
     double x[n], xn[n], u[m], e[n], du[m];
+    double pu[m], pX[n], pK[m * n], pk[m];
+    auto fetch = [&](int k) {
+        for (int i = 0; i < m; ++i) pu[i] = U[(size_t)k * m + i];
+        if (k < T) {
+            for (int i = 0; i < n; ++i) pX[i] = X[(size_t)k * n + i];
+            for (int i = 0; i < m * n; ++i) pK[i] = K_list[(size_t)k * m * n + i];
+            for (int i = 0; i < m; ++i) pk[i] = k_list[(size_t)k * m + i];
+        }
+    };
     for (int i = 0; i < n; ++i) { x[i] = X[i]; if (STORE) X_new[i] = x[i]; }
     double acc = 0.0, J = HUGE_VAL;
     bool inf = (T <= 0);
+    if (PF && N > 0) fetch(0);
     for (int k = 0; k < N; ++k) {
-        for (int i = 0; i < m; ++i) u[i] = U[(size_t)k * m + i];
+        double cX[n], cK[m * n], ck[m];
+        if (PF) {
+            for (int i = 0; i < m; ++i) u[i] = pu[i];
+            for (int i = 0; i < n; ++i) cX[i] = pX[i];
+            for (int i = 0; i < m * n; ++i) cK[i] = pK[i];
+            for (int i = 0; i < m; ++i) ck[i] = pk[i];
+            if (k + 1 < N) fetch(k + 1);
+        } else {
+            for (int i = 0; i < m; ++i) u[i] = U[(size_t)k * m + i];
+        }
         if (k < T) {
             double dx[n];
             for (int i = 0; i < n; ++i) {
-                double v = sub(x[i], X[(size_t)k * n + i]);
+                double v = sub(x[i], PF ? cX[i] : X[(size_t)k * n + i]);
                 if ((c.wrap_mask >> i) & 1u) v = wrap_pi(v);
                 dx[i] = v;
             }
             for (int i = 0; i < m; ++i) {
                 double s = 0.0;
-                for (int j = 0; j < n; ++j) s = add(s, mul(K_list[(size_t)k * m * n + i * n + j], dx[j]));
-                u[i] = add(u[i], add(s, mul(a, k_list[(size_t)k * m + i])));
+                for (int j = 0; j < n; ++j) s = add(s, mul(PF ? cK[i * n + j] : K_list[(size_t)k * m * n + i * n + j], dx[j]));
+                u[i] = add(u[i], add(s, mul(a, PF ? ck[i] : k_list[(size_t)k * m + i])));
             }
             // stage term of the candidate (solver.py:92-101)
             wrapped_error<n>(x, c.xg, c.wrap_mask, e);

@@ -149,9 +149,12 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) k_select_generic_pipe(const
 }
 // ---- pre-inverted input blocks: E_k = chol_inv(Q_k), X_t = chol_inv(QT_t) for every (problem, step) in parallel --------
 constexpr int kPreWarps = 4;
+#ifndef PRE_MINB
+#define PRE_MINB 4   // CTAs per SM the pre-pass is register-bounded for (2 -> 174 registers, 4 -> 128)
+#endif
 // four lanes per matrix, eight matrices per warp; matrix index = 2 (b T_max + k) + {0: Q_aug, 1: QT}
 template <int D>
-__global__ void __launch_bounds__(kPreWarps * 32) k_preinvert(const SelectArgs p, double* E, double* X, int* bad) {
+__global__ void __launch_bounds__(kPreWarps * 32, PRE_MINB) k_preinvert(const SelectArgs p, double* E, double* X, int* bad) {
     const size_t mat = ((size_t)blockIdx.x * kPreWarps * 32 + threadIdx.x) >> 2;
     const size_t total = 2 * (size_t)p.B * p.T_max;
     const bool live = mat < total;
