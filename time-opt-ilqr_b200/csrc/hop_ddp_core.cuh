@@ -311,18 +311,35 @@ HOP_DEVICE int backward_pass_warp(const double* A, const double* Bm, const doubl
         const int i = q / n, j = q % n;
         Vxx[q] = 0.5 * add(c.Qf[i * n + j], c.Qf[j * n + i]);
     }
+    // The inputs of step k-1 (lane owns the elements lane, lane + 32, ... of A and B, and one component of X / U) are
+    // loaded into registers while step k computes and moved to shared memory at the top of step k-1: the sweep is one
+    // dependent chain per warp and these loads were exposed once per step.
+    constexpr int PA = (n * n + 31) / 32, PB = (n * m + 31) / 32;
+    double pa[PA], pb[PB], pxu = 0.0;
+    auto fetch = [&](int k) {
+#pragma unroll
+        for (int u = 0; u < PA; ++u) { const int q = lane + 32 * u; pa[u] = (q < n * n) ? A[(size_t)k * n * n + q] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < PB; ++u) { const int q = lane + 32 * u; pb[u] = (q < n * m) ? Bm[(size_t)k * n * m + q] : 0.0; }
+        pxu = (lane < n) ? X[(size_t)k * n + lane] : ((lane < n + m) ? U[(size_t)k * m + (lane - n)] : 0.0);
+    };
+    fetch(T - 1);
     for (int k = T - 1; k >= 0; --k) {
         simt::sync();
-        for (int q = lane; q < n * n; q += 32) Ak[q] = A[(size_t)k * n * n + q];
-        for (int q = lane; q < n * m; q += 32) Bk[q] = Bm[(size_t)k * n * m + q];
+#pragma unroll
+        for (int u = 0; u < PA; ++u) { const int q = lane + 32 * u; if (q < n * n) Ak[q] = pa[u]; }
+#pragma unroll
+        for (int u = 0; u < PB; ++u) { const int q = lane + 32 * u; if (q < n * m) Bk[q] = pb[u]; }
+        const double xu = pxu;
+        if (k > 0) fetch(k - 1);
         fin = true;
         if (lane < n) {
-            double v = sub(X[(size_t)k * n + lane], c.xg[lane]);
+            double v = sub(xu, c.xg[lane]);
             if ((c.wrap_mask >> lane) & 1u) v = wrap_pi(v);
             e[lane] = v;
             fin = isfinite(v);
         } else if (lane < n + m) {
-            const double v = sub(U[(size_t)k * m + (lane - n)], c.u_ref[lane - n]);
+            const double v = sub(xu, c.u_ref[lane - n]);
             du[lane - n] = v;
             fin = isfinite(v);
         }
