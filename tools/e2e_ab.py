@@ -1,5 +1,9 @@
+#!/usr/bin/env python
+"""A/B tool: times the public host-buffer entry (hop.api.select_horizon_host, 65 536 quadrotor instances from pinned host
+buffers, outputs to pinned host buffers) with wall-clock time around synchronous calls; environment switches such as
+HOP_HOST_CHUNKS / HOP_LIN_MINB select the variant.  Not a bench value (bench.py reports e2e)."""
 import os, sys, json, time
-ROOT="/root/repo"; sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "time-opt-ilqr_b200"))
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "time-opt-ilqr_b200"))
 import numpy as np, torch
 from hop import api, cases
 case = cases.make_case("Quadrotor", N=128)
