@@ -35,16 +35,29 @@ enum { HOP_E_BADARG = -1, HOP_E_UNSUPPORTED_DIMS = -2, HOP_E_NO_DEVICE = -3, HOP
 enum { HOP_ST_OK = 0, HOP_ST_NONFINITE = 1, HOP_ST_LINALG = 2, HOP_ST_ERRMASK = 0xff,
        HOP_ST_FLAG_RETRY = 0x100, HOP_ST_FLAG_LU = 0x200 };
 
-/* selection variants (both are sequential in k and compute the same function)
- *   EXACT: every augmented block is materialised and inverted through the generic chol_inv, in the
- *          reference's operation order.
- *   FAST : fused entry points only (ignored elsewhere): closed-form block inverses for E_k and X_t,
- *          pivot-only evaluation of J(t) = 0.5 / pivot_n(X0), _sym only on the carried state.
- *   SCAN : hop_select_f64 only, (d, m) = (12,4) / (13,4): the prefix composition as a chunked parallel scan over the
+/* selection variants (all compute the reference's function J(T), T*)
+ *   EXACT: the PARITY mode.  The reference's operation order with individually rounded IEEE operations: Cholesky in
+ *          LAPACK dpotf2 order -> two substitutions for the inverse (utils.py:83-85), numpy's left-to-right products,
+ *          _sym exactly where the reference has it, no FMA contraction.  On identical inputs J(T) is bit-identical to
+ *          the plain-C restatement in oracle/ (asserted by the tests), hence T* too.  One warp per problem, blocks in
+ *          shared memory, any 1 <= d, m <= 16.  ~5x slower than FAST.
+ *   FAST : the throughput mode (bench default).  Fused entry points with n = 12: closed-form block inverses for E_k
+ *          and X_t, pivot-only evaluation of J(t) = 0.5 / pivot_n(X0), software-pipelined Gauss-Jordan sweeps in DMMA
+ *          register fragments.  Elsewhere identical to GJ.  Differs from EXACT by rounding only: <= 1e-9 relative on
+ *          well-conditioned problems (S2), ~1e-7 on the J(T) window of the rank-deficient augmented problems, where
+ *          the reference itself is only reproducible to ~5e-8 across BLAS builds.
+ *   GJ   : every augmented block materialised (in registers) and inverted by an in-place Gauss-Jordan sweep with FMA
+ *          (same jitter-ladder decisions as Cholesky: the sweep pivots are the squared Cholesky pivots).  The cold path
+ *          of FAST and the kernels behind hop_select_f64 in FAST mode; instantiated (d, m) only.
+ *   SCAN : hop_select_f64 and hop_select_fused_f64, (d, m) = (12,4) / (13,4): the prefix composition as a chunked parallel scan over the
  *          horizon (one CTA of 8 warps per problem; latency 2T/8 + 7 instead of T steps for ~2x the prefix work) --
  *          for SMALL batches.  Re-association changes the rounding (<= 1e-9 on well-conditioned problems; unsafe on
- *          ill-conditioned ones such as the cartpole embedding), so it is opt-in. */
-enum { HOP_MODE_EXACT = 0, HOP_MODE_FAST = 1, HOP_MODE_SCAN = 2 };
+ *          ill-conditioned ones such as the cartpole embedding), so it is opt-in.
+ *   FP32 : hop_select_f64 only: the EXACT sweep in IEEE single precision (inputs converted on load, J written as double).
+ *          Tolerance on S2 (well conditioned): J within 1e-4 relative, T* reproduced on >= 99 % of instances (the
+ *          mismatches are argmin gaps below the fp32 noise; measured in tests/ and DESIGN.md).  Not for the augmented
+ *          problems: their 1e-9 jitter and 1e-12 regularisation are below fp32 resolution. */
+enum { HOP_MODE_EXACT = 0, HOP_MODE_FAST = 1, HOP_MODE_SCAN = 2, HOP_MODE_GJ = 3, HOP_MODE_FP32 = 4 };
 
 /* device dynamics registry (systems.py closures cannot run on the GPU) */
 enum { HOP_SYS_DOUBLE_INTEGRATOR = 0, /* systems.py:28-50   params [dt]                               */
@@ -58,8 +71,11 @@ const char *hop_version(void);
 const char *hop_last_error_string(void);
 /* number of visible CUDA devices (0 => every compute call returns HOP_E_NO_DEVICE) */
 int hop_device_count(void);
-/* 1 if (d, m) is an instantiated augmented-dimension / control-dimension pair */
+/* 1 if (d, m) is an instantiated augmented-dimension / control-dimension pair of the FAST / GJ / SCAN kernels
+ * ((3,1) (4,2) (5,1) (12,4) (13,4)); HOP_MODE_EXACT and HOP_MODE_FP32 take any 1 <= d, m <= 16 */
 int hop_select_supported(int d, int m);
+/* same question for a given mode */
+int hop_select_supported_mode(int d, int m, int mode);
 
 /* horizon_selection.py:36-86 propagator_all_Jt_aug (+ solver.py:522,590 argmin), batched.
  *   A_aug [B][N][d][d], B_aug [B][N][d][m], Q_aug [B][N][d][d], QT [B][N][d][d] (QT[t-1] = terminal block

@@ -313,8 +313,30 @@ def select_fused(A, B, X, U, xg, u_ref, Q, R, alpha, w, T_min, T_max, wrap_idx=N
     return J, T.value
 
 
+def select_fused_batch(A, B, X, U, xg, u_ref, Q, R, alpha, w, T_min, T_max, wrap_idx=None, a_resid=None, f80=False,
+                       nthreads=1):
+    """select_fused over a batch of GIVEN linearisations: A [B,N,n,n], B [B,N,n,m], X [B,N+1,n], U [B,N,m] or [N,m],
+    xg [B,n] or [n], w [B] or scalar -> (J [B,T_max], T [B], status [B])."""
+    A, B, X = _d(A), _d(B), _d(X)
+    Bsz, N, n = A.shape[0], A.shape[1], A.shape[2]
+    m = B.shape[3]
+    U = _d(np.broadcast_to(np.asarray(U, dtype=float), (Bsz, N, m)))
+    xg = _d(np.broadcast_to(np.asarray(xg, dtype=float), (Bsz, n)))
+    w = _d(np.broadcast_to(np.asarray(w, dtype=float), (Bsz,)))
+    Qf = _d(as_terminal_weight(alpha, n))
+    u_ref, Q, R = _d(u_ref), _d(Q), _d(R)
+    ar = None if a_resid is None else _d(np.asarray(a_resid).reshape(Bsz, N, n))
+    J = np.zeros((Bsz, int(T_max))); T = np.zeros(Bsz, dtype=np.int32); status = np.zeros(Bsz, dtype=np.int32)
+    rc = lib().hopo_select_fused_batch(int(nthreads), Bsz, n, m, N, int(T_min), int(T_max), _p(A), _p(B),
+                                       None if ar is None else _p(ar), _p(X), _p(U), _p(xg), _p(u_ref), _p(Q), _p(R),
+                                       _p(Qf), _p(w), C.c_uint(wrap_mask(wrap_idx)), int(bool(f80)), _p(J), _pi(T),
+                                       _pi(status))
+    _raise(rc, "select_fused_batch")
+    return J, T, status
+
+
 def select_from_x0_batch(sys, p, N, T_min, T_max, x0, U, xg, u_ref, Q, R, alpha, w, wrap_idx=None, central=False,
-                         nthreads=1):
+                         nthreads=1, f80=False):
     n, m = sys_dims(sys)
     x0 = _d(np.asarray(x0).reshape(-1, n))
     Bsz = x0.shape[0]
@@ -323,9 +345,10 @@ def select_from_x0_batch(sys, p, N, T_min, T_max, x0, U, xg, u_ref, Q, R, alpha,
     p, U, u_ref, Q, R = _d(p), _d(U).reshape(N, m), _d(u_ref), _d(Q), _d(R)
     Qf = _d(as_terminal_weight(alpha, n))
     J = np.zeros((Bsz, int(T_max))); T = np.zeros(Bsz, dtype=np.int32); status = np.zeros(Bsz, dtype=np.int32)
-    rc = lib().hopo_select_from_x0_batch(int(nthreads), Bsz, int(sys), _p(p), int(N), int(T_min), int(T_max), _p(x0),
-                                         _p(U), _p(xg), _p(u_ref), _p(Q), _p(R), _p(Qf), _p(w),
-                                         C.c_uint(wrap_mask(wrap_idx)), int(bool(central)), _p(J), _pi(T), _pi(status))
+    rc = lib().hopo_select_from_x0_batch_ex(int(nthreads), Bsz, int(sys), _p(p), int(N), int(T_min), int(T_max), _p(x0),
+                                            _p(U), _p(xg), _p(u_ref), _p(Q), _p(R), _p(Qf), _p(w),
+                                            C.c_uint(wrap_mask(wrap_idx)), int(bool(central)), int(bool(f80)), _p(J),
+                                            _pi(T), _pi(status))
     _raise(rc, "select_from_x0_batch")
     return J, T, status
 

@@ -433,10 +433,23 @@ int hopo_select_fused(int sys, const double *p, int n, int m, int N, int T_min, 
     return rc;
 }
 
+static int select_from_x0_impl(int sys, const double *p, int N, int T_min, int T_max, const double *x0,
+                               const double *U, const double *xg, const double *u_ref, const double *Q,
+                               const double *R, const double *Qf, double w, unsigned wrap_mask, int central,
+                               int use_f80, double *J, int *T_star);
 int hopo_select_from_x0(int sys, const double *p, int N, int T_min, int T_max, const double *x0,
                         const double *U, const double *xg, const double *u_ref, const double *Q,
                         const double *R, const double *Qf, double w, unsigned wrap_mask, int central,
                         double *J, int *T_star)
+{
+    return select_from_x0_impl(sys, p, N, T_min, T_max, x0, U, xg, u_ref, Q, R, Qf, w, wrap_mask, central, 0, J, T_star);
+}
+/* use_f80: the SELECTION sweep in x87 extended precision on the same fp64 rollout / linearisation ("truth" of the
+ * jittered algorithm, for noise accounting only) */
+static int select_from_x0_impl(int sys, const double *p, int N, int T_min, int T_max, const double *x0,
+                               const double *U, const double *xg, const double *u_ref, const double *Q,
+                               const double *R, const double *Qf, double w, unsigned wrap_mask, int central,
+                               int use_f80, double *J, int *T_star)
 {
     int n, m;
     if (hopo_sys_dims(sys, &n, &m)) return HOP_ERR_ARG;
@@ -446,7 +459,7 @@ int hopo_select_from_x0(int sys, const double *p, int N, int T_min, int T_max, c
     hopo_rollout(sys, p, N, x0, U, X, 1e6);
     hopo_linearize(sys, p, N, X, U, central, 1e-5, 1e-5, 1e-6, 1e-6, A, B);
     int rc = hopo_select_fused(sys, p, n, m, N, T_min, T_max, A, B, NULL, X, U, xg, u_ref, Q, R, Qf, w,
-                               wrap_mask, 0, J, T_star);
+                               wrap_mask, use_f80, J, T_star);
     free(buf);
     return rc;
 }
@@ -705,7 +718,8 @@ done:
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
     int kind, lo, hi;
-    int sys, N, T_min, T_max, central, T_use, d, m;
+    int sys, N, T_min, T_max, central, T_use, d, m, use_f80;
+    const double *A, *B, *X, *a_resid;
     unsigned wrap_mask;
     const double *p, *x0, *U, *xg, *u_ref, *Q, *R, *Qf, *w;
     const double *A_aug, *B_aug, *Q_aug, *R_inv, *z0, *QT;
@@ -718,12 +732,21 @@ static void *hopo_worker(void *arg)
 {
     hopo_job *j = (hopo_job *)arg;
     int n = 0, m = 0;
-    if (j->kind != 1) hopo_sys_dims(j->sys, &n, &m);
+    if (j->kind != 1 && j->kind != 3) hopo_sys_dims(j->sys, &n, &m);
     for (int b = j->lo; b < j->hi; ++b) {
         if (j->kind == 0) {
-            j->status[b] = hopo_select_from_x0(j->sys, j->p, j->N, j->T_min, j->T_max, j->x0 + (size_t)b * n,
+            j->status[b] = select_from_x0_impl(j->sys, j->p, j->N, j->T_min, j->T_max, j->x0 + (size_t)b * n,
                                                j->U, j->xg + (size_t)b * n, j->u_ref, j->Q, j->R, j->Qf, j->w[b],
-                                               j->wrap_mask, j->central, j->J + (size_t)b * j->T_max, &j->T_star[b]);
+                                               j->wrap_mask, j->central, j->use_f80, j->J + (size_t)b * j->T_max,
+                                               &j->T_star[b]);
+        } else if (j->kind == 3) {
+            const size_t N_ = (size_t)j->N;
+            j->status[b] = hopo_select_fused(-1, NULL, j->d, j->m, j->N, j->T_min, j->T_max,
+                                             j->A + (size_t)b * N_ * j->d * j->d, j->B + (size_t)b * N_ * j->d * j->m,
+                                             j->a_resid ? j->a_resid + (size_t)b * N_ * j->d : NULL,
+                                             j->X + (size_t)b * (N_ + 1) * j->d, j->U + (size_t)b * N_ * j->m,
+                                             j->xg + (size_t)b * j->d, j->u_ref, j->Q, j->R, j->Qf, j->w[b], j->wrap_mask,
+                                             j->use_f80, j->J + (size_t)b * j->T_max, &j->T_star[b]);
         } else if (j->kind == 1) {
             const size_t dd = (size_t)j->d * j->d, dm = (size_t)j->d * j->m;
             j->status[b] = propagator_all_Jt_f64(j->T_use, j->d, j->m, j->A_aug + (size_t)b * j->N * dd,
@@ -771,6 +794,34 @@ int hopo_select_from_x0_batch(int nthreads, int Bsz, int sys, const double *p, i
     j.kind = 0; j.sys = sys; j.p = p; j.N = N; j.T_min = T_min; j.T_max = T_max; j.x0 = x0; j.U = U; j.xg = xg;
     j.u_ref = u_ref; j.Q = Q; j.R = R; j.Qf = Qf; j.w = w; j.wrap_mask = wrap_mask; j.central = central;
     j.J = J; j.T_star = T_star; j.status = status;
+    return hopo_fan_out(nthreads, Bsz, &j);
+}
+
+int hopo_select_from_x0_batch_ex(int nthreads, int Bsz, int sys, const double *p, int N, int T_min, int T_max,
+                                 const double *x0, const double *U, const double *xg, const double *u_ref,
+                                 const double *Q, const double *R, const double *Qf, const double *w,
+                                 unsigned wrap_mask, int central, int use_f80, double *J, int *T_star, int *status)
+{
+    hopo_job j; memset(&j, 0, sizeof j);
+    j.kind = 0; j.sys = sys; j.p = p; j.N = N; j.T_min = T_min; j.T_max = T_max; j.x0 = x0; j.U = U; j.xg = xg;
+    j.u_ref = u_ref; j.Q = Q; j.R = R; j.Qf = Qf; j.w = w; j.wrap_mask = wrap_mask; j.central = central;
+    j.use_f80 = use_f80; j.J = J; j.T_star = T_star; j.status = status;
+    return hopo_fan_out(nthreads, Bsz, &j);
+}
+
+/* hopo_select_fused over a batch of given linearisations: A [B][N][n][n], B [B][N][n][m], a_resid [B][N][n] or NULL (= 0),
+ * X [B][N+1][n], U [B][N][m] (per instance), xg [B][n], w [B]. */
+int hopo_select_fused_batch(int nthreads, int Bsz, int n, int m, int N, int T_min, int T_max, const double *A,
+                            const double *B, const double *a_resid, const double *X, const double *U,
+                            const double *xg, const double *u_ref, const double *Q, const double *R,
+                            const double *Qf, const double *w, unsigned wrap_mask, int use_f80, double *J,
+                            int *T_star, int *status)
+{
+    if (n < 1 || n + 1 > HOP_MAXD || m < 1 || m > HOP_MAXM) return HOP_ERR_ARG;
+    hopo_job j; memset(&j, 0, sizeof j);
+    j.kind = 3; j.d = n; j.m = m; j.N = N; j.T_min = T_min; j.T_max = T_max; j.A = A; j.B = B; j.a_resid = a_resid;
+    j.X = X; j.U = U; j.xg = xg; j.u_ref = u_ref; j.Q = Q; j.R = R; j.Qf = Qf; j.w = w; j.wrap_mask = wrap_mask;
+    j.use_f80 = use_f80; j.J = J; j.T_star = T_star; j.status = status;
     return hopo_fan_out(nthreads, Bsz, &j);
 }
 

@@ -102,6 +102,17 @@ int hopo_select_from_x0_batch(int nthreads, int Bsz, int sys, const double *p, i
                               const double *x0, const double *U, const double *xg, const double *u_ref,
                               const double *Q, const double *R, const double *Qf, const double *w,
                               unsigned wrap_mask, int central, double *J, int *T_star, int *status);
+/* same with the selection sweep optionally in x87 extended precision (use_f80; noise accounting only) */
+int hopo_select_from_x0_batch_ex(int nthreads, int Bsz, int sys, const double *p, int N, int T_min, int T_max,
+                                 const double *x0, const double *U, const double *xg, const double *u_ref,
+                                 const double *Q, const double *R, const double *Qf, const double *w,
+                                 unsigned wrap_mask, int central, int use_f80, double *J, int *T_star, int *status);
+/* hopo_select_fused over a batch of GIVEN linearisations (per-instance A, B, a_resid or NULL, X, U, xg, w) */
+int hopo_select_fused_batch(int nthreads, int Bsz, int n, int m, int N, int T_min, int T_max, const double *A,
+                            const double *B, const double *a_resid, const double *X, const double *U,
+                            const double *xg, const double *u_ref, const double *Q, const double *R,
+                            const double *Qf, const double *w, unsigned wrap_mask, int use_f80, double *J,
+                            int *T_star, int *status);
 int hopo_propagator_batch(int nthreads, int Bsz, int N, int T_use, int d, int m, const double *A_aug,
                           const double *B_aug, const double *Q_aug, const double *R_inv, const double *z0,
                           const double *QT, double *J, int *status);

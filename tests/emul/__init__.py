@@ -30,7 +30,7 @@ class FusedArgs(C.Structure):
 def build(force=False):
     srcs = [os.path.join(_HERE, f) for f in ("simt_emul.cpp", "simt_emul.h", "emul_select.cpp")]
     srcs += [os.path.join(_CSRC, f) for f in ("hop_select_core.cuh", "hop_select_body.cuh", "hop_simt.cuh", "hop_mma.cuh",
-                                              "hop_select_mma_body.cuh", "hop_select_pipe_body.cuh", "hop_select_scan_body.cuh", "hop_select_gpipe_body.cuh", "hop_select_tpp_body.cuh", "hop_select_epl_body.cuh")]
+                                              "hop_select_mma_body.cuh", "hop_select_pipe_body.cuh", "hop_select_scan_body.cuh", "hop_select_gpipe_body.cuh", "hop_select_tpp_body.cuh", "hop_select_epl_body.cuh", "hop_select_ref_body.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-DHOP_HOST_EMUL", "-Wno-unknown-pragmas", "-I" + _HERE, "-I" + _CSRC, "-fPIC",
                                "-shared", "-o", _SO, os.path.join(_HERE, "simt_emul.cpp"),
@@ -57,7 +57,7 @@ def _p(a):
 
 
 def select_generic(A_aug, B_aug, Q_aug, R_inv, z0, QT, T_min, T_max, w_explicit=None, jitter=1e-9, max_tries=8,
-                   mma=False, scan=False, pipe=False, tpp=False):
+                   mma=False, scan=False, pipe=False, tpp=False, ref=False, fp32=False):
     A_aug, B_aug, Q_aug, R_inv, z0, QT = map(_d, (A_aug, B_aug, Q_aug, R_inv, z0, QT))
     Bsz, N, d = A_aug.shape[:3]
     m = B_aug.shape[3]
@@ -65,6 +65,10 @@ def select_generic(A_aug, B_aug, Q_aug, R_inv, z0, QT, T_min, T_max, w_explicit=
     J = np.full((Bsz, T_max), np.nan); T = np.zeros(Bsz, np.int32); Js = np.zeros(Bsz); st = np.zeros(Bsz, np.int32)
     a = SelectArgs(Bsz, N, T_min, T_max, jitter, max_tries, _p(A_aug), _p(B_aug), _p(Q_aug), _p(R_inv), _p(z0), _p(QT),
                    (m * m if R_inv.ndim == 4 else 0), _p(wexp), _p(J), T.ctypes.data_as(_ip), _p(Js), st.ctypes.data_as(_ip))
+    if ref or fp32:
+        rc = lib().emul_select_generic_ref(d, m, C.byref(a), int(bool(fp32)))
+        assert rc == 0, f"emulated kernel failed rc={rc}"
+        return J, T, Js, st
     fn = lib().emul_select_generic_tpp if tpp else lib().emul_select_generic_pipe if pipe else lib().emul_select_generic_scan if scan else (lib().emul_select_generic_mma if mma else lib().emul_select_generic)
     rc = fn(d, m, C.byref(a))
     assert rc == 0, f"emulated kernel failed rc={rc}"
@@ -72,7 +76,7 @@ def select_generic(A_aug, B_aug, Q_aug, R_inv, z0, QT, T_min, T_max, w_explicit=
 
 
 def select_fused(A, Bm, a_resid, X, U, xg, w, u_ref, Q, R, Qf, wrap_mask, T_min, T_max, q_reg=1e-9, rho_reg=1e-12,
-                 jitter=1e-9, max_tries=8, mma=False, mode=0, epl=False):
+                 jitter=1e-9, max_tries=8, mma=False, mode=0, epl=False, ref=False):
     A, Bm, X, U, xg, w, u_ref, Q, R, Qf = map(_d, (A, Bm, X, U, xg, w, u_ref, Q, R, Qf))
     ar = None if a_resid is None else _d(a_resid)
     Bsz, N, n = A.shape[:3]
@@ -82,7 +86,7 @@ def select_fused(A, Bm, a_resid, X, U, xg, w, u_ref, Q, R, Qf, wrap_mask, T_min,
                   0 if U.ndim == 2 else U.shape[1] * U.shape[2], _p(xg), _p(w), _p(u_ref),
                   _p(Q), _p(R), _p(Qf), wrap_mask, q_reg, rho_reg, mode, None, _p(J), T.ctypes.data_as(_ip), _p(Js),
                   st.ctypes.data_as(_ip))
-    rc = (lib().emul_select_fused_epl if epl else lib().emul_select_fused_mma if mma else lib().emul_select_fused)(n, m, C.byref(a))
+    rc = (lib().emul_select_fused_ref if ref else lib().emul_select_fused_epl if epl else lib().emul_select_fused_mma if mma else lib().emul_select_fused)(n, m, C.byref(a))
     assert rc == 0, f"emulated kernel failed rc={rc}"
     return J, T, Js, st
 

@@ -254,3 +254,45 @@ extern "C" int emul_select_fused_epl(int n, int m, const hop::FusedArgs* p) {
     if (n == 4 && m == 1) return run_fused_epl<5, 1>(*p);
     return -2;
 }
+
+// ---- HOP_MODE_EXACT / HOP_MODE_FP32: reference-operation-order body (hop_select_ref_body.cuh), one warp per problem
+#include "hop_select_ref_body.cuh"
+namespace {
+template <typename R>
+struct RefGenericJob { const hop::SelectArgs* p; int d, m, b; R* slab; };
+template <typename R>
+void ref_generic_lane(void* a) {
+    auto* j = (RefGenericJob<R>*)a;
+    hop::ref::select_generic_body<R>(*j->p, j->d, j->m, j->b, j->slab);
+}
+template <typename R>
+int run_generic_ref(int d, int m, const hop::SelectArgs& p) {
+    std::vector<R> slab(hop::ref::Layout::make(d, m).size, (R)-7.0);
+    for (int b = 0; b < p.B; ++b) {
+        RefGenericJob<R> j{&p, d, m, b, slab.data()};
+        if (hop::simt::run_warp(ref_generic_lane<R>, &j)) return -1;
+    }
+    return 0;
+}
+struct RefFusedJob { const hop::FusedArgs* p; int n, m, b; double* slab; const double* cst; };
+void ref_fused_lane(void* a) {
+    auto* j = (RefFusedJob*)a;
+    hop::ref::select_fused_body(*j->p, j->n, j->m, j->b, j->slab, j->cst);
+}
+}  // namespace
+extern "C" int emul_select_generic_ref(int d, int m, const hop::SelectArgs* p, int fp32) {
+    if (d < 1 || d > hop::ref::kMaxD || m < 1 || m > hop::ref::kMaxD) return -2;
+    return fp32 ? run_generic_ref<float>(d, m, *p) : run_generic_ref<double>(d, m, *p);
+}
+extern "C" int emul_select_fused_ref(int n, int m, const hop::FusedArgs* p) {
+    if (n < 1 || n + 1 > hop::ref::kMaxD || m < 1 || m > n + 1) return -2;
+    std::vector<double> slab(hop::ref::Layout::make(n + 1, m).size, -7.0);
+    std::vector<double> cst(hop::ref::FusedCst::make(n, m).size, 0.0);
+    hop::ref::fused_cst_fill(*p, n, m, cst.data(), 0, 1);
+    for (int b = 0; b < p->B; ++b) {
+        if (p->skip && p->skip[b]) continue;
+        RefFusedJob j{p, n, m, b, slab.data(), cst.data()};
+        if (hop::simt::run_warp(ref_fused_lane, &j)) return -1;
+    }
+    return 0;
+}

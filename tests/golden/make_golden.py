@@ -188,6 +188,52 @@ def gold_s1_batch():
     save("s1_quadrotor_batch", x0=stack(x0s), J=stack(Js), T=np.asarray(Ts))
 
 
+def _s1_ref_one(xb):
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = quadrotor_128()
+    U = np.tile(u_ref.reshape(1, -1), (N, 1))
+    X = solver.rollout(F, xb, U)
+    A_f, B_f = linearization.linearize_forward_diff_traj(F, X, U)
+    *_, J, T = selection(F, A_f, B_f, X, U, xg, u_ref, Q, R, alpha, w, T_min, T_max, wrap_idx)
+    cols = T + np.arange(-2, 3)
+    J5 = np.array([J[c - 1] if 1 <= c <= T_max else np.nan for c in cols])
+    gap = np.sort(J[T_min - 1:T_max])[:2]
+    return T, J5, (gap[1] - gap[0]) / abs(gap[0])
+
+
+def gold_s1_ref4096(B=4096, seed=0):
+    """S1 at scale through the REAL reference: 4096 instances (the first 4096 of bench.py's rank-0 batch: same generator,
+    same seed), one core-minute each 17; stored: the seed, T*, J at T*-2..T*+2 and the reference's own argmin gap."""
+    import multiprocessing as mp
+    F, x0 = quadrotor_128()[:2]
+    sigma = np.array([0.4, 0.4, 0.4] + [0.0] * 9)
+    xi = np.random.default_rng(seed).standard_normal((B, 12))
+    x0s = x0[None] + sigma[None] * xi
+    with mp.Pool(os.cpu_count()) as pool:
+        res = pool.map(_s1_ref_one, list(x0s), chunksize=16)
+    save("s1_quadrotor_ref4096", seed=seed, T=np.asarray([r[0] for r in res], dtype=np.int32),
+         J_pm2=np.stack([r[1] for r in res]), gap=np.asarray([r[2] for r in res]))
+
+
+def gold_resid(B=4):
+    """Non-zero affine residuals: X is perturbed AFTER the rollout and U around u_ref, so a_k = F(X_k, U_k) - X_{k+1} != 0
+    (linearization.py:269-270; ~1e-4) and du != 0 enter A_aug[:, n] = a_k - B_k du (augmented.py:50).  The reference computes a_k
+    itself inside build_augmented_sequence_QR; it is stored so that the CUDA entry points get the same input."""
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = quadrotor_128()
+    rng = np.random.default_rng(77)
+    sigma = np.array([0.4, 0.4, 0.4] + [0.0] * 9)
+    out = {k: [] for k in ("X", "U", "A", "B", "a_resid", "J", "T")}
+    for b in range(B):
+        U = np.tile(u_ref.reshape(1, -1), (N, 1)) + 0.02 * rng.standard_normal((N, u_ref.size))
+        X = solver.rollout(F, x0 + sigma * rng.standard_normal(12), U)
+        X = X + 1e-4 * rng.standard_normal(X.shape)
+        A_f, B_f = linearization.linearize_forward_diff_traj(F, X, U)
+        a = stack(linearization.compute_affine_residuals(F, X, U)).reshape(N, x0.size)
+        *_, J, T = selection(F, A_f, B_f, X, U, xg, u_ref, Q, R, alpha, w, T_min, T_max, wrap_idx)
+        for k, v in zip(out, (X, U, stack(A_f), stack(B_f), a, J, T)):
+            out[k].append(v)
+    save("resid_Quadrotor", **{k: (np.asarray(v, dtype=np.int64) if k == "T" else stack(v)) for k, v in out.items()})
+
+
 def s2_instance(seed, d, m, N):
     """Synthetic HOP-LQR generator S2 -- draw order: all A, all B, all Q, R, z0, w."""
     r = np.random.default_rng(seed)
@@ -245,9 +291,7 @@ def gold_signatures():
 
 
 if __name__ == "__main__":
-    gold_signatures()
-    gold_utils()
-    gold_dynamics()
-    gold_cases()
-    gold_s1_batch()
-    gold_s2()
+    ALL = {"signatures": gold_signatures, "utils": gold_utils, "dynamics": gold_dynamics, "cases": gold_cases,
+           "s1_batch": gold_s1_batch, "s2": gold_s2, "s1_ref4096": gold_s1_ref4096, "resid": gold_resid}
+    for name in (sys.argv[1:] or list(ALL)):      # no arguments: everything (s1_ref4096 takes ~5 core-minutes)
+        ALL[name]()

@@ -187,3 +187,90 @@ def test_emulated_element_per_lane_fused_kernel_is_bit_identical_to_the_lane_gro
     assert (stg[2] & 0xFF) == 1 and (stg[0] & 0xFF) == 0
     assert np.array_equal(ste, stg) and np.array_equal(Te, Tg)
     assert np.array_equal(Je, Jg, equal_nan=True) and np.array_equal(Jse, Jsg, equal_nan=True)
+
+
+# ------------------------------------------------------------------ HOP_MODE_EXACT: reference operation order (hop_select_ref_body.cuh)
+@pytest.mark.parametrize("d,m,N", [(1, 1, 8), (3, 1, 32), (4, 2, 48), (5, 1, 40), (7, 3, 16), (12, 4, 24), (13, 4, 32), (16, 5, 10)])
+def test_emulated_exact_mode_is_bit_identical_to_the_oracle_on_s2(d, m, N):
+    """HOP_MODE_EXACT issues the reference's operations one IEEE rounding at a time (Cholesky in dpotf2 order, two
+    substitutions, left-to-right products, no FMA): on identical inputs J(T) equals the plain-C oracle bit for bit -- for
+    every d, m <= 16 (run-time dimensions), through the jitter ladder, the LU fallback, T_min > 1 and T_max < N."""
+    A, B, Q, R, z0, w, QT = s2_batch(range(3), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    if N > 8:
+        Q[1, 3] = np.diag(np.r_[np.ones(d - 1), -1e-4])       # ladder
+        QT[2, 5] = -np.eye(d)                                  # LU fallback
+    J, T, Js, st = emul.select_generic(A, B, Q, Rinv, z0, QT, 2, N - 1, w_explicit=w, ref=True)
+    Jo, sto = O.propagator_batch(A, B, Q, Rinv, z0, QT, T_use=N - 1)
+    assert not sto.any() and not (st & 0xFF).any()
+    if N > 8:
+        assert st[0] == 0 and st[1] & 0x100 and st[2] == 0x300
+    assert np.array_equal(J, Jo)
+    tot = Jo + w[:, None] * np.arange(1, N)
+    assert np.array_equal(T, np.argmin(tot[:, 1:], axis=1) + 2)
+    assert np.array_equal(Js, tot[np.arange(3), T - 1])
+
+
+def test_emulated_exact_mode_status_on_non_finite_input():
+    """A non-finite block raises FloatingPointError in the reference (utils.py:75): status 1, the curve from that step on is NaN,
+    NaN wins the argmin as in np.argmin; the other instances are unaffected."""
+    d, m, N = 4, 2, 8
+    A, B, Q, R, z0, w, QT = s2_batch(range(2), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    A[0, 2, 1, 1] = np.nan
+    J, T, Js, st = emul.select_generic(A, B, Q, Rinv, z0, QT, 1, N, ref=True)
+    Jo, sto = O.propagator_batch(A, B, Q, Rinv, z0, QT)
+    assert (st[0] & 0xFF) == 1 and sto[0] == 1 and st[1] == 0
+    assert np.isfinite(J[0, :2]).all() and np.isnan(J[0, 2:]).all() and T[0] == 3 and np.isnan(Js[0])
+    assert np.array_equal(J[1], Jo[1])
+    Q[1, 0] = np.diag([np.inf, 1.0, 1.0, 1.0])                  # an infinite diagonal entry is non-finite input, not a PD matrix
+    J, T, Js, st = emul.select_generic(A, B, Q, Rinv, z0, QT, 1, N, ref=True)
+    _, sto = O.propagator_batch(A, B, Q, Rinv, z0, QT)
+    assert (st[1] & 0xFF) == 1 and sto[1] == 1
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+@pytest.mark.parametrize("traj", ["nominal", "converged", "residuals"])
+def test_emulated_exact_fused_mode_is_bit_identical_to_the_oracle(name, traj):
+    """Fused form (augmented.py:10-87 built in the slab): the four reference cases on the nominal and the converged
+    trajectory of the reference's own solve, and with a perturbed trajectory whose affine residuals a_k are NOT zero."""
+    g = golden("case_" + name)
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case(name, N=int(g["N"]))
+    n = x0.size
+    T_max = min(T_max, 72 if name == "Quadrotor" else T_max)   # keeps the emulation fast; the curve prefix does not depend on T_max
+    ar = None
+    if traj == "nominal":
+        X, U, A, Bm = g["X"], g["U"], g["A_fwd"], g["B_fwd"]
+    elif traj == "converged":
+        X, U = g["sol_X"], g["sol_U"]
+        A, Bm = O.linearize(F.hop_sys, F.hop_params, X, U)
+    else:
+        rng = np.random.default_rng(5)
+        U = g["U"] + 0.01 * rng.standard_normal(g["U"].shape)
+        X = O.rollout(F.hop_sys, F.hop_params, x0, U) + 1e-4 * rng.standard_normal(g["X"].shape)
+        A, Bm = O.linearize(F.hop_sys, F.hop_params, X, U)
+        ar = O.affine_residuals(F.hop_sys, F.hop_params, X, U)
+        assert np.abs(ar).max() > 1e-5
+    J, T, Js, st = emul.select_fused(A[None], Bm[None], None if ar is None else ar[None], X[None], U[None], xg[None],
+                                     np.array([w]), u_ref, Q, R, O.as_terminal_weight(alpha, n), O.wrap_mask(wrap_idx),
+                                     T_min, T_max, ref=True)
+    Jo, To = O.select_fused(A, Bm, X, U, xg, u_ref, Q, R, alpha, w, T_min, T_max, wrap_idx, a_resid=ar)
+    assert (st[0] & 0xFF) == 0
+    assert np.array_equal(J[0], Jo) and int(T[0]) == To and Js[0] == Jo[To - 1]
+    if traj == "nominal":                                      # and the reference itself
+        tol_win, tol_star, dT = J_TOL[name]
+        Tr = int(g["T0"])
+        if Tr <= T_max:
+            assert abs(int(T[0]) - Tr) <= dT
+            assert abs(J[0, Tr - 1] - g["J_curve0"][Tr - 1]) <= tol_star * abs(g["J_curve0"][Tr - 1])
+
+
+@pytest.mark.parametrize("d,m,N", [(4, 2, 64), (13, 4, 64)])
+def test_emulated_fp32_mode_stays_within_its_stated_tolerance(d, m, N):
+    """HOP_MODE_FP32: the same sweep in IEEE single precision; on the well-conditioned family J within 1e-4, T* reproduced."""
+    A, B, Q, R, z0, w, QT = s2_batch(range(4), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    J, T, Js, st = emul.select_generic(A, B, Q, Rinv, z0, QT, 1, N, w_explicit=w, fp32=True)
+    Jo, _ = O.propagator_batch(A, B, Q, Rinv, z0, QT)
+    assert not st.any() and rel(J, Jo) <= 1e-4
+    assert np.array_equal(T, np.argmin(Jo + w[:, None] * np.arange(1, N + 1), axis=1) + 1)

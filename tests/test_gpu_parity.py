@@ -17,15 +17,18 @@ def _t(a):
     return torch.as_tensor(np.ascontiguousarray(a), device=DEV)
 
 
+@pytest.mark.parametrize("mode", [api.MODE_EXACT, api.MODE_FAST])
 @pytest.mark.parametrize("d,m,N,B", [(3, 1, 32, 9), (4, 2, 64, 33), (5, 1, 64, 7), (12, 4, 128, 5), (13, 4, 128, 6),
                                      (13, 4, 256, 3), (4, 2, 256, 2)])
-def test_select_generic_matches_oracle_on_s2(d, m, N, B):
+def test_select_generic_matches_oracle_on_s2(d, m, N, B, mode):
     A, Bm, Q, R, z0, w, QT = s2_batch(range(B), d, m, N)
     Rinv = np.stack([O.chol_inv(r) for r in R])
-    sel = api.propagator_all_Jt_aug_batched(_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, N, w_explicit=_t(w))
+    sel = api.propagator_all_Jt_aug_batched(_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, N, w_explicit=_t(w), mode=mode)
     Jo, sto = O.propagator_batch(A, Bm, Q, Rinv, z0, QT, nthreads=4)
     J = sel.J.cpu().numpy()
     assert not sel.status.cpu().numpy().any() and not sto.any()
+    if mode == api.MODE_EXACT:
+        assert np.array_equal(J, Jo)                               # reference operation order: bit-identical to the oracle
     assert rel(J, Jo) <= 1e-9                                      # north-star tolerance
     tot = Jo + w[:, None] * np.arange(1, N + 1)
     assert np.array_equal(sel.T_star.cpu().numpy(), np.argmin(tot, axis=1) + 1)
@@ -47,7 +50,7 @@ def test_select_generic_matches_reference_golden_s2():
 
 @pytest.mark.parametrize("name", CASE_NAMES)
 @pytest.mark.parametrize("traj", ["nominal", "converged"])
-@pytest.mark.parametrize("mode", [api.MODE_EXACT, api.MODE_FAST])
+@pytest.mark.parametrize("mode", [api.MODE_EXACT, api.MODE_GJ, api.MODE_FAST])
 def test_select_fused_matches_reference_golden(name, traj, mode):
     g = golden("case_" + name)
     F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case(name, N=int(g["N"]))
@@ -62,6 +65,9 @@ def test_select_fused_matches_reference_golden(name, traj, mode):
     J = sel.J.cpu().numpy()[0]
     tol_win, tol_star, dT = J_TOL[name]
     assert (int(sel.status[0]) & 0xFF) == 0
+    if mode == api.MODE_EXACT:      # identical inputs => identical bits
+        Jo, To = O.select_fused(A, Bm, X, U, xg, u_ref, Q, R, alpha, w, T_min, T_max, wrap_idx)
+        assert np.array_equal(J, Jo) and int(sel.T_star[0]) == To
     assert abs(int(sel.T_star[0]) - Tr) <= dT
     assert abs(J[Tr - 1] - Jr[Tr - 1]) <= max(tol_star, 3e-5 if name == "Cartpole_SwingUp" else 0) * abs(Jr[Tr - 1])
     if tol_win is not None:
@@ -77,7 +83,7 @@ def test_scan_mode_matches_sequential_sweep_and_oracle(d, m, N, T_max):
     A, Bm, Q, R, z0, w, QT = s2_batch(range(7), d, m, N)
     Rinv = np.stack([O.chol_inv(r) for r in R])
     args = (_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, T_max)
-    seq = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w))
+    seq = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w), mode=api.MODE_FAST)
     scan = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w), mode=api.MODE_SCAN)
     Js, Jp = seq.J.cpu().numpy(), scan.J.cpu().numpy()
     Lc = -(-T_max // 8)
@@ -98,35 +104,41 @@ def test_scan_mode_is_refused_where_it_is_not_instantiated():
         api.propagator_all_Jt_aug_batched(_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, 8, mode=api.MODE_SCAN)
 
 
-def test_generic_and_fused_agree_bitwise_in_T_and_closely_in_J():
+@pytest.mark.parametrize("mode", [api.MODE_EXACT, api.MODE_GJ])
+def test_generic_and_fused_agree_bitwise_in_T_and_closely_in_J(mode):
     """The fused kernel builds the augmented blocks itself; feeding the oracle-built blocks to the
-    generic kernel must give the same selection."""
+    generic kernel must give the same selection (EXACT: the same bits)."""
     g = golden("case_Quadrotor")
     F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case("Quadrotor", N=128)
     A_aug, B_aug, Q_aug, z0, R_inv = O.build_augmented(g["A_fwd"], g["B_fwd"], g["a_resid"], g["X"], g["U"], xg, u_ref, Q,
                                                        R, w, wrap_idx)
     QT = O.build_terminal(g["X"], xg, alpha, wrap_idx)
     s1 = api.propagator_all_Jt_aug_batched(_t(A_aug[None]), _t(B_aug[None]), _t(Q_aug[None]), _t(R_inv), _t(z0),
-                                           _t(QT[None]), T_min, T_max)
+                                           _t(QT[None]), T_min, T_max, mode=mode)
     s2 = api.select_fused_batched(_t(g["A_fwd"][None]), _t(g["B_fwd"][None]), _t(g["X"][None]), _t(g["U"][None]), xg, w,
-                                  u_ref, Q, R, alpha, T_min, T_max, wrap_idx, a_resid=_t(g["a_resid"][None]))
+                                  u_ref, Q, R, alpha, T_min, T_max, wrap_idx, a_resid=_t(g["a_resid"][None]), mode=mode)
     assert int(s1.T_star[0]) == int(s2.T_star[0]) == int(g["T0"])
+    if mode == api.MODE_EXACT:
+        assert torch.equal(s1.J, s2.J)
     assert rel(s1.J.cpu().numpy()[0, T_min - 1:], s2.J.cpu().numpy()[0, T_min - 1:]) <= 1e-6
 
 
-def test_ladder_fallback_and_nonfinite_status_on_gpu():
+@pytest.mark.parametrize("mode", [api.MODE_EXACT, api.MODE_FAST])
+def test_ladder_fallback_and_nonfinite_status_on_gpu(mode):
     d, m, N = 4, 2, 8
     A, Bm, Q, R, z0, w, QT = s2_batch(range(11), d, m, N)
     Rinv = np.stack([O.chol_inv(r) for r in R])
     Q[1, 3] = np.diag([1.0, 1.0, 1.0, -1e-4])
     QT[2, 5] = -np.eye(d)
     A[9, 2, 1, 1] = np.nan
-    sel = api.propagator_all_Jt_aug_batched(_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, N)
+    sel = api.propagator_all_Jt_aug_batched(_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, N, mode=mode)
     Jo, sto = O.propagator_batch(A, Bm, Q, Rinv, z0, QT)
     st = sel.status.cpu().numpy()
     assert st[0] == 0 and st[1] == 0x100 and st[2] == 0x300 and (st[9] & 0xFF) == 1 and sto[9] == 1
     ok = [i for i in range(11) if i != 9]
     assert rel(sel.J.cpu().numpy()[ok], Jo[ok]) <= 1e-9
+    if mode == api.MODE_EXACT:      # the ladder and the LU fallback in the reference's operation order too
+        assert np.array_equal(sel.J.cpu().numpy()[ok], Jo[ok])
     with pytest.raises(FloatingPointError):
         sel.raise_for_status()
 
@@ -149,7 +161,7 @@ def test_thread_per_problem_and_lane_group_kernels_agree_bit_for_bit(d, m, N, B)
     try:
         for name, thr in (("lanes", 1 << 40), ("threads", 0)):
             lib.hop_test_set_tpp_min_batch(thr)
-            sel = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w))
+            sel = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w), mode=api.MODE_FAST)
             out[name] = tuple(x.cpu().numpy() for x in (sel.J, sel.T_star, sel.J_star, sel.status))
     finally:
         lib.hop_test_set_tpp_min_batch(old)
@@ -247,30 +259,115 @@ def test_rollout_divergence_guard_nan_fills_like_the_reference():
     assert np.isfinite(X[0]).all() and np.isfinite(X[1, 0]).all() and np.isnan(X[1, 1:]).all()
 
 
-@pytest.mark.parametrize("mode", [api.MODE_EXACT, api.MODE_FAST])
+@pytest.mark.parametrize("mode", [api.MODE_EXACT, api.MODE_GJ, api.MODE_FAST])
 def test_s1_from_x0_device_and_host_paths_match_reference_and_oracle(mode):
-    """Headline workload S1: quadrotor n=12, N=128, x0 ~ x0 + sigma xi (first 16 = reference golden)."""
-    g = golden("s1_quadrotor_batch")
+    """Headline workload S1: quadrotor n=12, N=128, x0 ~ x0 + sigma xi, against (i) 4096 instances computed by the REAL
+    reference (tests/golden/s1_quadrotor_ref4096.npz: T*, J at T* +- 2) and (ii) the oracle on every instance with the
+    three-number census (oracle/census.py).  A T* mismatch is only accepted when the fp80 sweep shows the instance to be
+    ill-posed (gap between the two candidates below 10 x the fp64 noise at those horizons); no count is waived."""
+    from oracle import census
+    g = golden("s1_quadrotor_ref4096")
     case = cases.make_case("Quadrotor", N=128)
     F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = case
-    B = 300
-    x0s = s1_x0(B)
+    B = int(g["T"].shape[0])
+    x0s = s1_x0(B, seed=int(g["seed"]))
     sel = api.select_horizon_batched(case, _t(x0s), mode=mode)
     T = sel.T_star.cpu().numpy(); J = sel.J.cpu().numpy()
     assert not (sel.status.cpu().numpy() & 0xFF).any()
-    assert np.array_equal(T[:16], g["T"])                                          # vs the reference
-    assert rel(J[:16, T_min - 1:], g["J"][:16, T_min - 1:]) <= 1e-6
-    U = np.tile(u_ref, (N, 1))
-    Jo, To, sto = O.select_from_x0_batch(F.hop_sys, F.hop_params, N, T_min, T_max, x0s, U, xg, u_ref, Q, R, alpha, w,
-                                         wrap_idx, nthreads=8)
-    mism = np.nonzero(T != To)[0]
-    # any T* mismatch against the oracle must be a near-tie (gap below the fp64 noise floor, SURVEY.md s.9)
-    for b in mism:
-        gap = abs(Jo[b, T[b] - 1] - Jo[b, To[b] - 1]) / abs(Jo[b, To[b] - 1])
-        assert gap < 1e-7, (b, T[b], To[b], gap)
-    assert len(mism) <= 3
-    Jh, Th, Jsh, sth = api.select_horizon_host(case, x0s, mode=mode)
-    assert np.array_equal(Th, T) and np.array_equal(Jh, J) and np.array_equal(sth, sel.status.cpu().numpy())
+    # (i) the reference itself
+    Tr, Jr5 = g["T"].astype(np.int64), g["J_pm2"]                      # J at T*-2 .. T*+2 (NaN outside [1, T_max])
+    cols = Tr[:, None] + np.arange(-2, 3)[None, :]
+    inside = (cols >= 1) & (cols <= T_max)
+    Jg5 = np.where(inside, J[np.arange(B)[:, None], np.clip(cols, 1, T_max) - 1], np.nan)
+    relr = np.abs(Jg5 - Jr5) / np.abs(Jr5)
+    assert np.nanmax(relr) <= (2e-8 if mode == api.MODE_EXACT else 5e-8)        # at T* +- 2, vs the reference
+    rep = census.census_from_x0(case, x0s, J, T, nthreads=8, fp80_stride=4)
+    assert rep["T_star_mismatches_unexplained"] == 0, rep["mismatch_detail"]
+    for b in np.nonzero(T != Tr)[0]:                                   # vs the reference: same rule, through the census list
+        assert int(b) in rep["ill_posed"]["instances"] or any(int(b) == m["instance"] and m["ill_posed"] for m in rep["mismatch_detail"]) \
+            or abs(Jr5[b, 2] - Jr5[b, 2 + int(T[b] - Tr[b])]) <= 1e-8 * abs(Jr5[b, 2]), (b, T[b], Tr[b])
+    assert rep["rel_J_window"]["gpu_vs_oracle"]["max"] <= (2e-8 if mode == api.MODE_EXACT else 1e-6)
+    # the checked implementation is as close to the fp80 truth as the fp64 oracle is (within 3 x)
+    assert rep["rel_J_window"]["gpu_vs_fp80"]["p99"] <= 3.0 * rep["rel_J_window"]["oracle_vs_fp80"]["p99"]
+    Jh, Th, Jsh, sth = api.select_horizon_host(case, x0s[:300], mode=mode)
+    assert np.array_equal(Th, T[:300]) and np.array_equal(Jh, J[:300]) and np.array_equal(sth, sel.status.cpu().numpy()[:300])
+
+
+def test_exact_mode_is_bit_identical_to_the_oracle_on_4096_device_linearisations():
+    """HOP_MODE_EXACT issues the reference's operations one IEEE rounding at a time, so on IDENTICAL inputs its curve is the
+    oracle's curve bit for bit.  Inputs: the rollout + forward-difference linearisation the DEVICE produced for 4096 S1
+    instances (they differ from the host's only through CUDA's sin/cos/tan, <= 2 ulp), downloaded and fed to the oracle."""
+    case = cases.make_case("Quadrotor", N=128)
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = case
+    B = 4096
+    sel = api.HorizonSelector(case, B, device=DEV, mode=api.MODE_EXACT)
+    r = sel(_t(s1_x0(B, seed=31)))
+    X, A, Bm = (t.cpu().numpy() for t in sel.views())
+    Jo, To, sto = O.select_fused_batch(A, Bm, X, np.tile(u_ref, (N, 1)), xg, u_ref, Q, R, alpha, w, T_min, T_max, wrap_idx,
+                                       nthreads=8)
+    assert not sto.any() and not (r.status.cpu().numpy() & 0xFF).any()
+    assert np.array_equal(r.J.cpu().numpy(), Jo)
+    assert np.array_equal(r.T_star.cpu().numpy(), To)
+
+
+@pytest.mark.parametrize("mode", [api.MODE_EXACT, api.MODE_GJ, api.MODE_FAST])
+def test_nonzero_affine_residuals_in_every_selection_kernel(mode):
+    """compute_affine_residuals (linearization.py:269-270) is exactly zero on a consistent rollout, so every other test feeds
+    a_resid = 0.  Here X is perturbed AFTER the rollout (a_k = F(X_k, U_k) - X_{k+1} ~ 1e-3) and the residuals enter
+    A_aug[:, n] = a_k - B_k du (augmented.py:50): fused kernels (TMA-staged a_k in the DMMA bodies) and the LQR-boundary
+    kernels (through k_build_augmented) against the reference golden and the oracle."""
+    g = golden("resid_Quadrotor")
+    case = cases.make_case("Quadrotor", N=128)
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = case
+    X, U, A, Bm, ar = g["X"], g["U"], g["A"], g["B"], g["a_resid"]
+    assert np.abs(ar).max() > 1e-4
+    Bsz = X.shape[0]
+    sel = api.select_fused_batched(_t(A), _t(Bm), _t(X), _t(U), xg, w, u_ref, Q, R, alpha, T_min, T_max, wrap_idx,
+                                   a_resid=_t(ar), mode=mode)
+    J = sel.J.cpu().numpy()
+    Jo, To, sto = O.select_fused_batch(A, Bm, X, U, xg, u_ref, Q, R, alpha, w, T_min, T_max, wrap_idx, a_resid=ar, nthreads=4)
+    assert not sto.any() and not (sel.status.cpu().numpy() & 0xFF).any()
+    if mode == api.MODE_EXACT:
+        assert np.array_equal(J, Jo)
+    # compared on T in [T_min, 70]: beyond, the randomly perturbed controls make the tail of the curve noise-dominated (the
+    # reference itself is 1e-4 away from the fp80 sweep there); on [40, 70] oracle and reference agree to 7e-8
+    win = slice(T_min - 1, 70)
+    assert rel(J[:, win], Jo[:, win]) <= 5e-7
+    assert np.array_equal(sel.T_star.cpu().numpy(), To)
+    assert np.array_equal(To, g["T"])                                          # the reference itself
+    assert rel(J[:, win], g["J"][:, win]) <= 5e-7
+    rows = np.arange(Bsz)
+    assert rel(J[rows, g["T"] - 1], g["J"][rows, g["T"] - 1]) <= 5e-8
+    # without the residuals the curve is a different one (2e-4 on instance 0): the input is live
+    sel0 = api.select_fused_batched(_t(A), _t(Bm), _t(X), _t(U), xg, w, u_ref, Q, R, alpha, T_min, T_max, wrap_idx, mode=mode)
+    assert rel(sel0.J.cpu().numpy()[:, win], Jo[:, win]) > 1e-5
+    if mode != api.MODE_FAST:
+        # LQR-boundary kernels on device-built blocks (hop_build_augmented_f64 carries a_k into A_aug)
+        from hop import _cabi
+        import ctypes as C
+        lib = _cabi.require_device()
+        d, m = 13, 4
+        A_aug = torch.empty((Bsz, N, d, d), dtype=torch.float64, device=DEV); Q_aug = torch.empty_like(A_aug)
+        QT = torch.empty_like(A_aug); B_aug = torch.empty((Bsz, N, d, m), dtype=torch.float64, device=DEV)
+        xg_t = _t(np.broadcast_to(xg, (Bsz, 12)).copy()); w_t = _t(np.full(Bsz, float(w)))
+        p_ = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        Xd, Ud, Ad, Bd, ard = _t(X), _t(U), _t(A), _t(Bm), _t(ar)
+        _cabi.check(lib.hop_build_augmented_f64(Bsz, N, 12, m, p_(Ad), p_(Bd), p_(ard), p_(Xd), p_(Ud), N * m, p_(xg_t), p_(w_t),
+                                                p_(_t(u_ref)), p_(_t(Q)), O.wrap_mask(wrap_idx), 1e-9, 1e-12, p_(A_aug),
+                                                p_(B_aug), p_(Q_aug), None), "hop_build_augmented_f64")
+        _cabi.check(lib.hop_build_terminal_f64(Bsz, N, 12, p_(Xd), p_(xg_t), p_(_t(O.as_terminal_weight(alpha, 12))),
+                                               O.wrap_mask(wrap_idx), 1e-12, p_(QT), None), "hop_build_terminal_f64")
+        z0 = np.zeros(d); z0[-1] = 1.0
+        s1 = api.propagator_all_Jt_aug_batched(A_aug, B_aug, Q_aug, _t(O.chol_inv(0.5 * (R + R.T))), _t(z0), QT, T_min, T_max,
+                                               mode=mode)
+        Ao, Bo, Qo, _, _ = O.build_augmented(A[0], Bm[0], ar[0], X[0], U[0], xg, u_ref, Q, R, w, wrap_idx)
+        assert np.array_equal(A_aug[0].cpu().numpy(), Ao) and np.array_equal(B_aug[0].cpu().numpy(), Bo)
+        assert np.array_equal(Q_aug[0].cpu().numpy(), Qo)
+        assert np.array_equal(QT[0].cpu().numpy(), O.build_terminal(X[0], xg, alpha, wrap_idx))
+        if mode == api.MODE_EXACT:
+            assert np.array_equal(s1.J.cpu().numpy(), Jo)
+        assert rel(s1.J.cpu().numpy()[:, win], Jo[:, win]) <= 5e-7
+        assert np.array_equal(s1.T_star.cpu().numpy(), To)
 
 
 def test_full_size_properties_without_oracle():
@@ -309,22 +406,67 @@ def test_chunked_host_path_equals_the_device_path_on_ragged_chunks():
     assert len(np.unique(Th)) > 3
 
 
-def test_fast_and_exact_modes_agree_on_4096_instances():
-    """MODE_FAST restructures the block inverses algebraically; on the headline workload it must select
-    the same horizon as MODE_EXACT except on near-ties, and agree on J to the fp64 noise floor."""
+@pytest.mark.parametrize("mode", [api.MODE_FAST, api.MODE_GJ])
+def test_fast_and_gj_modes_agree_with_exact_mode_on_4096_instances(mode):
+    """FAST restructures the block inverses algebraically and GJ inverts by Gauss-Jordan with FMA: against HOP_MODE_EXACT on
+    the same device inputs they must agree on J to the stated tolerance (include/hop_b200.h: 1e-6 on the window of the
+    rank-deficient augmented problem, 5e-8 at T*) and select the same horizon except on near-ties: a T* mismatch is only
+    accepted when the gap between the two candidates is below 10 x the distance between the two curves at those horizons."""
     case = cases.make_case("Quadrotor", N=128)
     x0s = _t(s1_x0(4096, seed=11))
     a = api.select_horizon_batched(case, x0s, mode=api.MODE_EXACT)
-    Ta, Ja = a.T_star.cpu().numpy(), a.J.cpu().numpy()
-    b = api.select_horizon_batched(case, x0s, mode=api.MODE_FAST)
-    Tb, Jb = b.T_star.cpu().numpy(), b.J.cpu().numpy()
+    Ta, Ja = a.T_star.cpu().numpy().astype(np.int64), a.J.cpu().numpy()
+    b = api.select_horizon_batched(case, x0s, mode=mode)
+    Tb, Jb = b.T_star.cpu().numpy().astype(np.int64), b.J.cpu().numpy()
     assert not (a.status.cpu().numpy() & 0xFF).any() and not (b.status.cpu().numpy() & 0xFF).any()
     assert rel(Jb[:, 39:], Ja[:, 39:]) <= 1e-6
-    mism = np.nonzero(Ta != Tb)[0]
-    for i in mism:
+    rows = np.arange(4096)
+    assert rel(Jb[rows, Ta - 1], Ja[rows, Ta - 1]) <= 5e-8
+    for i in np.nonzero(Ta != Tb)[0]:
         gap = abs(Ja[i, Ta[i] - 1] - Ja[i, Tb[i] - 1]) / abs(Ja[i, Ta[i] - 1])
-        assert gap < 1e-7
-    assert len(mism) <= 8
+        noise = max(abs(Jb[i, t - 1] - Ja[i, t - 1]) / abs(Ja[i, t - 1]) for t in (Ta[i], Tb[i]))
+        assert gap < 10.0 * noise, (i, Ta[i], Tb[i], gap, noise)
+
+
+def test_fp32_mode_reproduces_T_star_on_the_well_conditioned_family():
+    """HOP_MODE_FP32 (hop_select_f64 only): the EXACT sweep in IEEE single precision.  Stated tolerance on S2 (include/hop_b200.h):
+    J within 1e-4 relative, T* reproduced on >= 99 % of instances, every miss a gap below the fp32 noise."""
+    for d, m, N in ((4, 2, 128), (12, 4, 64), (13, 4, 128)):
+        B = 512
+        A, Bm, Q, R, z0, w, QT = s2_batch(range(B), d, m, N)
+        Rinv = np.stack([O.chol_inv(r) for r in R])
+        args = (_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, N)
+        ex = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w), mode=api.MODE_EXACT)
+        lo = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w), mode=api.MODE_FP32)
+        Je, Jl = ex.J.cpu().numpy(), lo.J.cpu().numpy()
+        Te, Tl = ex.T_star.cpu().numpy().astype(np.int64), lo.T_star.cpu().numpy().astype(np.int64)
+        assert not lo.status.cpu().numpy().any()
+        assert rel(Jl, Je) <= 1e-4
+        miss = np.nonzero(Te != Tl)[0]
+        assert len(miss) <= B // 100, (d, N, len(miss))
+        tot = Je + w[:, None] * np.arange(1, N + 1)
+        for i in miss:
+            assert abs(tot[i, Te[i] - 1] - tot[i, Tl[i] - 1]) <= 1e-4 * abs(tot[i, Te[i] - 1])
+
+
+def test_fused_scan_mode_on_the_quadrotor_embedding():
+    """HOP_MODE_SCAN through the fused entry point (blocks materialised by k_build_augmented / k_build_terminal, then the chunked
+    parallel scan): same T* as the sequential sweep; chunk 0 of the curve within 1e-9, the rest within the re-association noise
+    SURVEY.md s.9 measured on the quadrotor embedding (<= 1e-6 on the window)."""
+    case = cases.make_case("Quadrotor", N=128)
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = case
+    B = 8
+    sel = api.HorizonSelector(case, B, device=DEV, mode=api.MODE_EXACT)
+    ex = sel(_t(s1_x0(B, seed=2)))
+    X, A, Bm = sel.views()
+    sc = api.select_fused_batched(A, Bm, X, _t(np.tile(u_ref, (N, 1))), xg, w, u_ref, Q, R, alpha, T_min, T_max, wrap_idx,
+                                  mode=api.MODE_SCAN)
+    assert not (sc.status.cpu().numpy() & 0xFF).any()
+    Je, Js = ex.J.cpu().numpy(), sc.J.cpu().numpy()
+    assert rel(Js[:, T_min - 1:], Je[:, T_min - 1:]) <= 1e-6
+    Te, Ts = ex.T_star.cpu().numpy().astype(np.int64), sc.T_star.cpu().numpy().astype(np.int64)
+    for i in np.nonzero(Te != Ts)[0]:
+        assert abs(Je[i, Te[i] - 1] - Je[i, Ts[i] - 1]) <= 1e-7 * abs(Je[i, Te[i] - 1])
 
 
 # ------------------------------------------------------------------ HOP-DDP iteration pieces + solver loop
@@ -409,7 +551,7 @@ def test_pre_inverted_and_in_kernel_sweep_b_agree_bit_for_bit(d, m, N, T_max):
     try:
         for on in (0, 1):
             lib.hop_test_set_generic_pre(on)
-            sel = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w))
+            sel = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w), mode=api.MODE_FAST)
             out[on] = tuple(x.cpu().numpy() for x in (sel.J, sel.T_star, sel.J_star, sel.status))
     finally:
         lib.hop_test_set_generic_pre(-1)
@@ -436,7 +578,7 @@ def test_element_per_lane_and_lane_group_fused_kernels_agree_bit_for_bit(name):
     try:
         for variant in (0, 1):
             lib.hop_test_set_fused_small_variant(variant)
-            out[variant] = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=5, use_central_diff=False, mode=api.MODE_EXACT)
+            out[variant] = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=5, use_central_diff=False, mode=api.MODE_GJ)
     finally:
         lib.hop_test_set_fused_small_variant(0)
     for key in ("X", "U", "J_hist", "T_hist", "n_hist", "T_star", "J_curve", "status"):
@@ -510,37 +652,65 @@ def test_propagator_curve_agrees_with_the_bruteforce_curve_on_device():
     assert len(diff) <= B // 10
 
 
-def test_batched_hop_ddp_matches_oracle_on_sampled_quadrotor_instances():
-    """Config 4 (scaled down): quadrotor N=128, sampled x0; every instance runs its own state machine."""
+@pytest.mark.parametrize("mode", [api.MODE_EXACT, api.MODE_FAST])
+def test_batched_hop_ddp_matches_oracle_on_sampled_quadrotor_instances(mode):
+    """Config 4 (scaled down): quadrotor N=128, sampled x0; every instance runs its own state machine.  T_hist must be the
+    oracle's on every instance, with one documented exception: a near-tie in ONE selection may move that entry to the
+    ADJACENT horizon; such an instance must still converge to the same cost (1e-6)."""
     case = cases.make_case("Quadrotor", N=128)
     F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = case
-    x0s = s1_x0(24, seed=5)
-    r = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=12, use_central_diff=False, mode=api.MODE_FAST)
+    Bsz = 24
+    x0s = s1_x0(Bsz, seed=5)
+    r = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=12, use_central_diff=False, mode=mode)
     o = O.ilqr_timeopt_batch(F.hop_sys, F.hop_params, N, T_min, T_max, x0s, np.tile(u_ref, (N, 1)), xg, u_ref, Q, R, alpha, w,
                              wrap_idx, max_iter=12, use_central_diff=False, nthreads=8)
     nh = r["n_hist"].cpu().numpy()
-    assert np.array_equal(nh, o["n_hist"])
     Th = r["T_hist"].cpu().numpy(); Jh = r["J_hist"].cpu().numpy()
-    bad = 0
-    for b in range(24):
-        same = np.array_equal(Th[b, :nh[b]], o["T_hist"][b, :nh[b]])
-        bad += (not same)
-        if same:
+    differing = []
+    for b in range(Bsz):
+        if nh[b] == o["n_hist"][b] and np.array_equal(Th[b, :nh[b]], o["T_hist"][b, :nh[b]]):
             assert rel(Jh[b, :nh[b]], o["J_hist"][b, :nh[b]]) <= 1e-8
-    assert bad <= 1          # a near-tie in one selection may legitimately shift one T_hist entry (SURVEY.md s.9)
-    assert np.array_equal(r["T_star"].cpu().numpy()[Th[:, 0] == o["T_hist"][:, 0]], o["T_star"][Th[:, 0] == o["T_hist"][:, 0]]) or bad
+            assert int(r["T_star"][b]) == int(o["T_star"][b])
+            continue
+        differing.append(b)
+        k = min(nh[b], o["n_hist"][b])
+        first = int(np.nonzero(Th[b, :k] != o["T_hist"][b, :k])[0][0]) if (Th[b, :k] != o["T_hist"][b, :k]).any() else k - 1
+        assert abs(int(Th[b, first]) - int(o["T_hist"][b, first])) <= 1, (b, Th[b, :nh[b]], o["T_hist"][b, :o["n_hist"][b]])
+        assert abs(Jh[b, nh[b] - 1] - o["J_hist"][b, o["n_hist"][b] - 1]) <= 1e-6 * abs(o["J_hist"][b, o["n_hist"][b] - 1])
+    assert len(differing) <= (0 if mode == api.MODE_EXACT else 1), differing
 
 
-def test_cartpole_batched_solve_runs_and_is_noise_limited():
-    """Config 3 flavour: cartpole from perturbed initial states (the reference's own sigma is zero)."""
+def test_cartpole_batched_solve_against_the_oracle_on_identical_initial_states():
+    """Config 3 flavour: cartpole from perturbed initial states (the reference's own sigma is zero), HOP_MODE_EXACT against
+    the oracle on the SAME x0.  The cartpole embedding amplifies rounding (Q has a zero weight: |E_k| ~ 5e8; the jitter
+    ladder and the LU fallback are live), so an instance is only compared when it is WELL-POSED: the fp64 oracle and the
+    oracle with the selection sweep in x87 extended precision produce the same T_hist.  On those, T_hist must be identical
+    and J_hist within 1e-6; the nominal instance (the reference's own run, golden) is compared too."""
     g = golden("case_Cartpole_SwingUp")
     case = cases.make_case("Cartpole_SwingUp")
+    F, x0c, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = case
     rng = np.random.default_rng(0)
-    x0s = np.array([rng.normal(0, .1, 8), rng.normal(0, .1, 8), rng.normal(0, .2, 8), rng.normal(0, .2, 8)]).T
-    x0s[0] = 0.0
-    r = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=12, use_central_diff=False)
-    nh = int(r["n_hist"][0])
-    assert nh == len(g["sol_T_hist"])
-    assert np.abs(r["T_hist"].cpu().numpy()[0, :nh] - g["sol_T_hist"]).max() <= 2
-    assert rel(r["J_hist"].cpu().numpy()[0, :nh], g["sol_J_hist"]) <= 5e-2
+    Bsz = 32
+    x0s = np.array([rng.normal(0, .1, Bsz), rng.normal(0, .1, Bsz), rng.normal(0, .2, Bsz), rng.normal(0, .2, Bsz)]).T
+    x0s[0] = x0c
+    r = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=12, use_central_diff=False, mode=api.MODE_EXACT)
+    kw = dict(max_iter=12, use_central_diff=False, nthreads=8)
+    args = (F.hop_sys, F.hop_params, N, T_min, T_max, x0s, np.tile(u_ref, (N, 1)), xg, u_ref, Q, R, alpha, w, wrap_idx)
+    o64 = O.ilqr_timeopt_batch(*args, **kw)
+    o80 = O.ilqr_timeopt_batch(*args, f80_select=True, **kw)
+    nh = r["n_hist"].cpu().numpy(); Th = r["T_hist"].cpu().numpy(); Jh = r["J_hist"].cpu().numpy()
+    well = [b for b in range(Bsz) if o64["n_hist"][b] == o80["n_hist"][b]
+            and np.array_equal(o64["T_hist"][b, :o64["n_hist"][b]], o80["T_hist"][b, :o80["n_hist"][b]])]
+    assert len(well) >= Bsz // 2
     assert torch.isfinite(r["J_hist"][:, 0]).all()
+    same = 0
+    for b in well:
+        k = o64["n_hist"][b]
+        if nh[b] == k and np.array_equal(Th[b, :k], o64["T_hist"][b, :k]):
+            same += 1
+            assert rel(Jh[b, :k], o64["J_hist"][b, :k]) <= 1e-6
+    # the device dynamics differ from the host's by CUDA's sin/cos (<= 2 ulp); on a well-posed instance that must not move T_hist
+    assert same >= len(well) - 1, (same, len(well))
+    n0 = len(g["sol_T_hist"])
+    if 0 in well:
+        assert nh[0] == n0 and np.abs(Th[0, :n0] - g["sol_T_hist"]).max() <= 1      # the reference's own run (oracle: |dT| <= 1)

@@ -179,3 +179,39 @@ def test_argmin_window_first_minimum_and_nan():
     assert O.argmin_window(J, 1, 5) == 3 and O.argmin_window(J, 4, 5) == 4
     J[3] = np.nan
     assert O.argmin_window(J, 1, 5) == 4       # np.argmin: NaN wins
+
+
+def test_oracle_reproduces_4096_reference_selections_of_the_headline_workload():
+    """tests/golden/s1_quadrotor_ref4096.npz: the REAL reference on 4096 S1 instances (quadrotor N=128, the first 4096 of
+    bench.py's rank-0 batch).  The oracle must select the same horizon on every one and reproduce J at T*-2..T*+2 to 1e-8
+    (measured: 0 mismatches, 3.2e-9)."""
+    from _common import s1_x0
+    from hop import cases
+    g = golden("s1_quadrotor_ref4096")
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case("Quadrotor", N=128)
+    B = g["T"].shape[0]
+    assert B == 4096
+    J, T, st = O.select_from_x0_batch(F.hop_sys, F.hop_params, N, T_min, T_max, s1_x0(B, seed=int(g["seed"])),
+                                      np.tile(u_ref, (N, 1)), xg, u_ref, Q, R, alpha, w, wrap_idx, nthreads=8)
+    Tr = g["T"].astype(np.int64)
+    assert not st.any() and np.array_equal(T, Tr)
+    cols = Tr[:, None] + np.arange(-2, 3)[None, :]
+    J5 = J[np.arange(B)[:, None], np.clip(cols, 1, T_max) - 1]
+    assert np.nanmax(np.abs(J5 - g["J_pm2"]) / np.abs(g["J_pm2"])) <= 1e-8
+
+
+def test_oracle_with_nonzero_affine_residuals_matches_the_reference():
+    from hop import cases
+    g = golden("resid_Quadrotor")
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case("Quadrotor", N=128)
+    assert np.abs(g["a_resid"]).max() > 1e-4
+    for b in range(g["X"].shape[0]):
+        a = O.affine_residuals(F.hop_sys, F.hop_params, g["X"][b], g["U"][b])
+        assert np.abs(a - g["a_resid"][b]).max() <= 1e-15
+    J, T, st = O.select_fused_batch(g["A"], g["B"], g["X"], g["U"], xg, u_ref, Q, R, alpha, w, T_min, T_max, wrap_idx,
+                                    a_resid=g["a_resid"], nthreads=4)
+    assert not st.any() and np.array_equal(T, g["T"])
+    assert rel(J[:, T_min - 1:70], g["J"][:, T_min - 1:70]) <= 2e-7        # (beyond T = 70 the tail is noise-dominated)
+    assert rel(J[np.arange(4), T - 1], g["J"][np.arange(4), T - 1]) <= 5e-8
+    J0, _, _ = O.select_fused_batch(g["A"], g["B"], g["X"], g["U"], xg, u_ref, Q, R, alpha, w, T_min, T_max, wrap_idx, nthreads=4)
+    assert rel(J0[:, T_min - 1:70], g["J"][:, T_min - 1:70]) > 1e-5        # the residuals matter

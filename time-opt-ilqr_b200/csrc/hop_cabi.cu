@@ -60,6 +60,9 @@ int launch_build_augmented(int B, int N, int n, int m, const double* A, const do
 int launch_build_terminal(int B, int N, int n, const double* X, const double* xg, const double* Qf, unsigned wrap_mask,
                           double rho_reg, double* QT, cudaStream_t st);
 int sys_dims(int sys, int* n, int* m);
+int stream_alloc(void** ptr, size_t bytes, cudaStream_t st, const char* what);
+void stream_free(void* ptr, cudaStream_t st);
+int launch_scan_consts(int B, int d, int m, const double* R_inv1, double* R_inv, double* z0, cudaStream_t st);
 
 static thread_local std::string g_err;
 void set_last_error(const char* msg) { g_err = msg ? msg : ""; }
@@ -97,13 +100,19 @@ int hop_device_count(void) {
 int hop_select_supported(int d, int m) {
     return (d == 3 && m == 1) || (d == 4 && m == 2) || (d == 5 && m == 1) || (d == 12 && m == 4) || (d == 13 && m == 4);
 }
+int hop_select_supported_mode(int d, int m, int mode) {
+    if (mode == HOP_MODE_EXACT || mode == HOP_MODE_FP32) return d >= 1 && d <= 16 && m >= 1 && m <= 16;
+    if (mode == HOP_MODE_SCAN) return (d == 12 || d == 13) && m == 4;
+    if (mode == HOP_MODE_FAST || mode == HOP_MODE_GJ) return hop_select_supported(d, m);
+    return 0;
+}
 
 int hop_select_f64(int B, int N, int d, int m, int T_min, int T_max, const double* A_aug, const double* B_aug,
                    const double* Q_aug, const double* R_inv, long rinv_step_stride, const double* z0, const double* QT,
                    const double* w_explicit, int mode, double* J_out, int* Tstar_out, double* Jstar_out, int* status,
                    void* stream) {
     if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N ||
-        (mode != HOP_MODE_EXACT && mode != HOP_MODE_FAST && mode != HOP_MODE_SCAN) ||
+        mode < HOP_MODE_EXACT || mode > HOP_MODE_FP32 ||
         (rinv_step_stride != 0 && rinv_step_stride != (long)m * m)) {
         set_last_error("hop_select_f64: bad argument (need 1 <= T_min <= T_max <= N, rinv_step_stride in {0, m*m})");
         return HOP_E_BADARG;
@@ -121,12 +130,41 @@ int hop_select_fused_f64(int B, int N, int n, int m, int T_min, int T_max, const
                          const double* u_ref, const double* Q, const double* R, const double* Qf, unsigned wrap_mask,
                          double q_reg, double rho_reg, int mode, double* J_out, int* Tstar_out, double* Jstar_out,
                          int* status, void* stream) {
-    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || (mode != HOP_MODE_EXACT && mode != HOP_MODE_FAST)) {
-        set_last_error("hop_select_fused_f64: bad argument (need 1 <= T_min <= T_max <= N, mode in {EXACT, FAST})");
+    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || (mode != HOP_MODE_EXACT && mode != HOP_MODE_FAST && mode != HOP_MODE_GJ && mode != HOP_MODE_SCAN)) {
+        set_last_error("hop_select_fused_f64: bad argument (need 1 <= T_min <= T_max <= N, mode in {EXACT, FAST, GJ, SCAN})");
         return HOP_E_BADARG;
     }
     if (int rc = need_device()) return rc;
     if (B == 0) return 0;
+    if (mode == HOP_MODE_SCAN) {
+        // the scan kernel works at the LQR boundary: materialise the augmented blocks (augmented.py:10-87) in a stream-ordered
+        // scratch allocation, then run the chunked parallel scan over the horizon.  Small batches only (that is where it pays).
+        if (!hop_select_supported_mode(n + 1, m, HOP_MODE_SCAN)) {
+            set_last_error("hop_select_fused_f64: HOP_MODE_SCAN is instantiated for (n, m) = (11,4) and (12,4) only");
+            return HOP_E_UNSUPPORTED_DIMS;
+        }
+        cudaStream_t st = (cudaStream_t)stream;
+        const int d = n + 1;
+        const size_t dd = (size_t)B * N * d * d, dm = (size_t)B * N * d * m;
+        const size_t total = sizeof(double) * (3 * dd + dm + (size_t)B * m * m + (size_t)B * d + (size_t)m * m) + sizeof(int);
+        void* ws = nullptr;
+        if (int rc = stream_alloc(&ws, total, st, "cudaMallocAsync(scan workspace)")) return rc;
+        double* A_aug = (double*)ws; double* Q_aug = A_aug + dd; double* QT = Q_aug + dd; double* B_aug = QT + dd;
+        double* R_inv = B_aug + dm; double* z0 = R_inv + (size_t)B * m * m; double* R1 = z0 + (size_t)B * d;
+        int* st1 = (int*)(R1 + m * m);
+        int rc = launch_build_augmented(B, N, n, m, A, Bm, a_resid, X, U, u_batch_stride, xg, w, u_ref, Q, wrap_mask, q_reg,
+                                        rho_reg, A_aug, B_aug, Q_aug, st);
+        if (!rc) rc = launch_build_terminal(B, N, n, X, xg, Qf, wrap_mask, rho_reg, QT, st);
+        if (!rc) rc = launch_chol(1, m, 0, R, nullptr, R1, kJitter, kMaxTries, st1, st);              // augmented.py:23
+        if (!rc) rc = launch_scan_consts(B, d, m, R1, R_inv, z0, st);                                 // augmented.py:59
+        if (!rc) {
+            SelectArgs q{B, N, T_min, T_max, kJitter, kMaxTries, A_aug, B_aug, Q_aug, R_inv, z0, QT, 0, nullptr,
+                         J_out, Tstar_out, Jstar_out, status};
+            rc = dispatch_select_generic(d, m, HOP_MODE_SCAN, q, st);
+        }
+        stream_free(ws, st);
+        return rc;
+    }
     FusedArgs p{B, N, T_min, T_max, kJitter, kMaxTries, A, Bm, a_resid, X, U, u_batch_stride, xg, w, u_ref, Q, R, Qf,
                 wrap_mask, q_reg, rho_reg, mode, nullptr, J_out, Tstar_out, Jstar_out, status};
     return dispatch_select_fused(n, m, p, (cudaStream_t)stream);
@@ -313,8 +351,9 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T
                          int* iters_run_host, double* timers_host, void* stream) {
     int n = 0, m = 0;
     if (sys_dims(sys, &n, &m)) { set_last_error("hop_ilqr_timeopt_f64: unknown system id"); return HOP_E_BADARG; }
-    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || max_iter < 0) {
-        set_last_error("hop_ilqr_timeopt_f64: bad argument");
+    if (B < 0 || N < 1 || T_min < 1 || T_max < T_min || T_max > N || max_iter < 0 ||
+        (mode != HOP_MODE_EXACT && mode != HOP_MODE_FAST && mode != HOP_MODE_GJ)) {
+        set_last_error("hop_ilqr_timeopt_f64: bad argument (need 1 <= T_min <= T_max <= N, max_iter >= 0, mode in {EXACT, FAST, GJ})");
         return HOP_E_BADARG;
     }
     if (int rc = need_device()) return rc;
@@ -336,9 +375,13 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T
         return dispatch_select_fused(n, m, p, st);
     };
     // optional per-phase device timing (the reference's timers dict: linearize / select / backward / forward)
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    struct Events {   // destroyed on every exit path
+        cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        ~Events() { for (auto& x : e) if (x) cudaEventDestroy(x); }
+    } evs;
+    cudaEvent_t* ev = evs.e;
     double tsum[4] = {0.0, 0.0, 0.0, 0.0};
-    if (timers_host) for (auto& e : ev) cudaEventCreate(&e);
+    if (timers_host) for (auto& e : evs.e) HOP_TRY(report_cuda(cudaEventCreate(&e), "cudaEventCreate"));
     auto mark = [&](int i) { if (timers_host) cudaEventRecord(ev[i], st); };
     auto collect = [&]() {
         if (!timers_host) return;
@@ -387,10 +430,8 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T
     HOP_TRY(launch_finalize(B, cap, n_hist, T_hist, ws.T_bar, T_star, st));
 #undef HOP_TRY
     if (iters_run_host) *iters_run_host = iters;
-    if (timers_host) {
+    if (timers_host)
         for (int i = 0; i < 4; ++i) timers_host[i] = tsum[i];
-        for (auto& e : ev) cudaEventDestroy(e);
-    }
     return 0;
 }
 
@@ -544,35 +585,39 @@ int hop_select_from_x0_host_f64(int B, int sys, const double* params_host, int N
     char* d_ws = q;
     double* d_uref = d_c; double* d_Q = d_uref + m; double* d_R = d_Q + n * n; double* d_Qf = d_R + m * m;
     cudaStream_t s0 = g_host.stream[0];
-    cudaMemcpyAsync(d_uref, u_ref, sizeof(double) * m, cudaMemcpyHostToDevice, s0);
-    cudaMemcpyAsync(d_Q, Q, sizeof(double) * n * n, cudaMemcpyHostToDevice, s0);
-    cudaMemcpyAsync(d_R, R, sizeof(double) * m * m, cudaMemcpyHostToDevice, s0);
-    cudaMemcpyAsync(d_Qf, Qf, sizeof(double) * n * n, cudaMemcpyHostToDevice, s0);
-    if (shared_U) cudaMemcpyAsync(d_U, U, sizeof(double) * nU, cudaMemcpyHostToDevice, s0);
-    cudaEventRecord(g_host.consts_ready, s0);
-    if (lanes > 1) cudaStreamWaitEvent(g_host.stream[1], g_host.consts_ready, 0);
     int rc = 0;
+    auto copy = [&](void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st, const char* what) {
+        if (rc == 0) rc = report_cuda(cudaMemcpyAsync(dst, src, bytes, kind, st), what);
+    };
+    copy(d_uref, u_ref, sizeof(double) * m, cudaMemcpyHostToDevice, s0, "H2D u_ref");
+    copy(d_Q, Q, sizeof(double) * n * n, cudaMemcpyHostToDevice, s0, "H2D Q");
+    copy(d_R, R, sizeof(double) * m * m, cudaMemcpyHostToDevice, s0, "H2D R");
+    copy(d_Qf, Qf, sizeof(double) * n * n, cudaMemcpyHostToDevice, s0, "H2D Qf");
+    if (shared_U) copy(d_U, U, sizeof(double) * nU, cudaMemcpyHostToDevice, s0, "H2D U");
+    if (rc == 0) rc = report_cuda(cudaEventRecord(g_host.consts_ready, s0), "cudaEventRecord");
+    if (rc == 0 && lanes > 1) rc = report_cuda(cudaStreamWaitEvent(g_host.stream[1], g_host.consts_ready, 0), "cudaStreamWaitEvent");
     for (int c = 0; c < chunks && rc == 0; ++c) {
         const int b0 = c * per, cb = (B - b0) < per ? (B - b0) : per;
         if (cb <= 0) break;
         cudaStream_t st = g_host.stream[c % lanes];
         const size_t o = (size_t)b0;
-        cudaMemcpyAsync(d_x0 + o * n, x0 + o * n, sizeof(double) * (size_t)cb * n, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(d_xg + o * n, xg + o * n, sizeof(double) * (size_t)cb * n, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(d_w + o, w + o, sizeof(double) * (size_t)cb, cudaMemcpyHostToDevice, st);
+        copy(d_x0 + o * n, x0 + o * n, sizeof(double) * (size_t)cb * n, cudaMemcpyHostToDevice, st, "H2D x0");
+        copy(d_xg + o * n, xg + o * n, sizeof(double) * (size_t)cb * n, cudaMemcpyHostToDevice, st, "H2D xg");
+        copy(d_w + o, w + o, sizeof(double) * (size_t)cb, cudaMemcpyHostToDevice, st, "H2D w");
         const double* dU = d_U;
         if (!shared_U) {
-            cudaMemcpyAsync(d_U + o * N * m, U + o * N * m, sizeof(double) * (size_t)cb * N * m, cudaMemcpyHostToDevice, st);
+            copy(d_U + o * N * m, U + o * N * m, sizeof(double) * (size_t)cb * N * m, cudaMemcpyHostToDevice, st, "H2D U");
             dU = d_U + o * N * m;
         }
+        if (rc) break;
         rc = hop_select_from_x0_f64(cb, sys, params_host, N, T_min, T_max, d_x0 + o * n, dU, u_batch_stride, d_xg + o * n,
                                     d_w + o, d_uref, d_Q, d_R, d_Qf, wrap_mask, central, mode, d_ws + (c % lanes) * s_ws, s_ws,
                                     d_J + o * T_max, d_T + o, d_Js + o, d_st + o, st);
         if (rc) break;
-        if (J_out) cudaMemcpyAsync(J_out + o * T_max, d_J + o * T_max, sizeof(double) * (size_t)cb * T_max, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(Tstar_out + o, d_T + o, sizeof(int) * (size_t)cb, cudaMemcpyDeviceToHost, st);
-        if (Jstar_out) cudaMemcpyAsync(Jstar_out + o, d_Js + o, sizeof(double) * (size_t)cb, cudaMemcpyDeviceToHost, st);
-        if (status) cudaMemcpyAsync(status + o, d_st + o, sizeof(int) * (size_t)cb, cudaMemcpyDeviceToHost, st);
+        if (J_out) copy(J_out + o * T_max, d_J + o * T_max, sizeof(double) * (size_t)cb * T_max, cudaMemcpyDeviceToHost, st, "D2H J");
+        copy(Tstar_out + o, d_T + o, sizeof(int) * (size_t)cb, cudaMemcpyDeviceToHost, st, "D2H T*");
+        if (Jstar_out) copy(Jstar_out + o, d_Js + o, sizeof(double) * (size_t)cb, cudaMemcpyDeviceToHost, st, "D2H J*");
+        if (status) copy(status + o, d_st + o, sizeof(int) * (size_t)cb, cudaMemcpyDeviceToHost, st, "D2H status");
     }
     cudaError_t e0 = cudaStreamSynchronize(g_host.stream[0]);
     cudaError_t e1 = lanes > 1 ? cudaStreamSynchronize(g_host.stream[1]) : cudaSuccess;

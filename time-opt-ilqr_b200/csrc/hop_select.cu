@@ -174,13 +174,34 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) k_select_generic_pipe_pre(c
     select_generic_seq_cold<D, M>(p, b, slab);
 }
 
-// workspace of the pre-pass: one cached device arena per process (E, X: 2 N d^2 doubles per problem, + one flag), bounded
-// by kPreArenaMax -- larger batches run as consecutive chunks on the caller's stream, which orders the re-use.
+// workspace of the pre-pass (E, X: 2 N d^2 doubles per problem, + one flag): stream-ordered allocation on the CALLER'S stream
+// (cudaMallocAsync / cudaFreeAsync), so concurrent calls on different streams or host threads never share scratch and nothing
+// outlives the call; bounded by kPreArenaMax -- larger batches run as consecutive chunks on the same stream, which orders the
+// re-use.  The device's default memory pool keeps freed blocks (release threshold raised once per device), so repeated calls
+// do not go back to the driver.
 namespace {
-struct PreArena { void* buf = nullptr; size_t cap = 0; int device = -1; };
-PreArena g_pre;
 constexpr size_t kPreArenaMax = (size_t)8 << 30;
+int pool_keep_cached() {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return 0;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
+    done[dev] = true;
+    return 0;
+}
 }  // namespace
+int stream_alloc(void** ptr, size_t bytes, cudaStream_t st, const char* what) {
+    pool_keep_cached();
+    return report_cuda(cudaMallocAsync(ptr, bytes, st), what);
+}
+void stream_free(void* ptr, cudaStream_t st) {
+    if (ptr) cudaFreeAsync(ptr, st);
+}
 // 1: always, 0: never (sweep B inside the sequential kernel), -1 [default]: for small batches only.  Measured on B200
 // (S2, d = 13, N = 128): B = 8: 0.95 -> 0.76 ms (one sweep latency per step instead of two); B = 65 536: 63.3 -> 68.2 ms
 // (sequential kernel 63.3 -> 46.5 ms, but the pre-pass moves 45 GB and costs 19.8 ms): it pays where latency matters.
@@ -205,17 +226,12 @@ static int launch_generic_pipe(const SelectArgs& p, cudaStream_t st) {
     if (chunk < 1) chunk = 1;
     const size_t s_mat = ((sizeof(double) * chunk * p.N * D * D + 255) / 256) * 256;
     const size_t need = 2 * s_mat + sizeof(int) * chunk;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (g_pre.device != dev || need > g_pre.cap) {
-        if (g_pre.buf) { cudaDeviceSynchronize(); cudaFree(g_pre.buf); }
-        g_pre.buf = nullptr; g_pre.cap = 0; g_pre.device = dev;
-        if (int rc = report_cuda(cudaMalloc(&g_pre.buf, need), "cudaMalloc(pre-inversion arena)")) return rc;
-        g_pre.cap = need;
-    }
-    double* E = (double*)g_pre.buf;
-    double* X = (double*)((char*)g_pre.buf + s_mat);
-    int* bad = (int*)((char*)g_pre.buf + 2 * s_mat);
+    void* arena = nullptr;
+    if (int rc = stream_alloc(&arena, need, st, "cudaMallocAsync(pre-inversion workspace)")) return rc;
+    double* E = (double*)arena;
+    double* X = (double*)((char*)arena + s_mat);
+    int* bad = (int*)((char*)arena + 2 * s_mat);
+    int rc_all = 0;
     const size_t rinv_inst = (size_t)(p.rinv_step_stride ? p.N : 1) * M * M;
     for (size_t b0 = 0; b0 < (size_t)p.B; b0 += chunk) {
         SelectArgs q = p;
@@ -228,14 +244,15 @@ static int launch_generic_pipe(const SelectArgs& p, cudaStream_t st) {
         q.w_explicit = p.w_explicit ? p.w_explicit + b0 : nullptr;
         q.J_out = p.J_out + b0 * p.T_max; q.T_out = p.T_out + b0; q.Jstar_out = p.Jstar_out + b0; q.status = p.status + b0;
         q.E_pre = E; q.X_pre = X; q.pre_bad = bad;
-        if (int rc = report_cuda(cudaMemsetAsync(bad, 0, sizeof(int) * (size_t)q.B, st), "memset(pre_bad)")) return rc;
+        if ((rc_all = report_cuda(cudaMemsetAsync(bad, 0, sizeof(int) * (size_t)q.B, st), "memset(pre_bad)"))) break;
         const size_t mats = 2 * (size_t)q.B * q.T_max;                           // 8 matrices per warp
         k_preinvert<D><<<(unsigned)((mats + 8 * kPreWarps - 1) / (8 * kPreWarps)), kPreWarps * 32, 0, st>>>(q, E, X, bad);
-        if (int rc = check_launch("k_preinvert")) return rc;
+        if ((rc_all = check_launch("k_preinvert"))) break;
         k_select_generic_pipe_pre<D, M><<<(q.B + kMmaWarps - 1) / kMmaWarps, kMmaWarps * 32, smem, st>>>(q);
-        if (int rc = check_launch("k_select_generic_pipe_pre")) return rc;
+        if ((rc_all = check_launch("k_select_generic_pipe_pre"))) break;
     }
-    return 0;
+    stream_free(arena, st);
+    return rc_all;
 }
 
 template <int D, int M>
@@ -281,7 +298,12 @@ int dispatch_select_generic_tpp(int d, int m, const SelectArgs& p, cudaStream_t 
 // one matrix element per LANE, fused form of the small systems: hop_select_epl.cu (same convention)
 int dispatch_select_fused_epl(int n, int m, const FusedArgs& p, cudaStream_t st);
 
+// HOP_MODE_EXACT / HOP_MODE_FP32: reference operation order, hop_select_ref.cu
+int dispatch_select_ref_generic(int d, int m, bool fp32, const SelectArgs& p, cudaStream_t st);
+int dispatch_select_ref_fused(int n, int m, const FusedArgs& p, cudaStream_t st);
+
 int dispatch_select_generic(int d, int m, int mode, const SelectArgs& p, cudaStream_t st) {
+    if (mode == HOP_MODE_EXACT || mode == HOP_MODE_FP32) return dispatch_select_ref_generic(d, m, mode == HOP_MODE_FP32, p, st);
     if (mode == HOP_MODE_SCAN) {
         if (d == 12 && m == 4) return launch_generic_scan<12, 4>(p, st);
         if (d == 13 && m == 4) return launch_generic_scan<13, 4>(p, st);
@@ -303,6 +325,7 @@ int dispatch_select_generic(int d, int m, int mode, const SelectArgs& p, cudaStr
 }
 
 int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st) {
+    if (p.mode == HOP_MODE_EXACT) return dispatch_select_ref_fused(n, m, p, st);
     if (n <= 4) {
         const int rc = dispatch_select_fused_epl(n, m, p, st);
         if (rc != HOP_E_UNSUPPORTED_DIMS) return rc;

@@ -38,7 +38,7 @@ struct FusedArgs {
     const double *u_ref, *Q, *R, *Qf;          // shared case constants: [m], [n][n], [m][m], [n][n]
     unsigned wrap_mask;
     double q_reg, rho_reg;
-    int mode;                                  // HOP_MODE_EXACT / HOP_MODE_FAST
+    int mode;                                  // HOP_MODE_EXACT / HOP_MODE_FAST / HOP_MODE_GJ
     const int* skip;                           // optional [B]: non-zero => instance is left untouched
     double* J_out;
     int* T_out;

@@ -198,12 +198,25 @@ __global__ void k_build_terminal(int B, int N, int n, const double* X, const dou
     Qt[n * d + n] = add(mul(2.0, mul(0.5, ePe)), rho_reg);
 }
 
+// fused HOP_MODE_SCAN: per-instance copies of the shared R^-1 and z0 = e_d (augmented.py:23,59) for the LQR-boundary kernel
+__global__ void k_scan_consts(int B, int d, int m, const double* R_inv1, double* R_inv, double* z0) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nr = (size_t)B * m * m, nz = (size_t)B * d;
+    if (gid < nr) R_inv[gid] = R_inv1[gid % (m * m)];
+    if (gid < nz) z0[gid] = ((int)(gid % d) == d - 1) ? 1.0 : 0.0;
+}
+
 static inline int grid1u(size_t total, int threads) { return (int)((total + threads - 1) / threads); }
 
 int launch_chol(int B, int d, int c, const double* A, const double* Bm, double* X, double jitter, int max_tries, int* status,
                 cudaStream_t st) {
     k_chol<<<grid1u(B, 64), 64, 0, st>>>(B, d, c, A, Bm, X, jitter, max_tries, status);
     return check_launch("k_chol");
+}
+int launch_scan_consts(int B, int d, int m, const double* R_inv1, double* R_inv, double* z0, cudaStream_t st) {
+    const size_t total = (size_t)B * (m * m > d ? m * m : d);
+    k_scan_consts<<<grid1u(total, 128), 128, 0, st>>>(B, d, m, R_inv1, R_inv, z0);
+    return check_launch("k_scan_consts");
 }
 int launch_affine_residuals(int B, int sys, const double* params_host, int N, const double* X, const double* U, long ustride,
                             double* a, cudaStream_t st) {

@@ -17,6 +17,7 @@ SIGNATURES = {
     "hop_last_error_string": (C.c_char_p, []),
     "hop_device_count": (_i, []),
     "hop_select_supported": (_i, [_i, _i]),
+    "hop_select_supported_mode": (_i, [_i, _i, _i]),
     "hop_select_f64": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "hop_select_fused_f64": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _u,
                                   _d, _d, _i, _vp, _vp, _vp, _vp, _vp]),

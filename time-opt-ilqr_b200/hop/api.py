@@ -22,9 +22,13 @@ import torch
 from . import _cabi
 from .cases import NPARAMS, SYS_DIMS
 
-MODE_EXACT = 0   # reference operation order, every block through the generic chol_inv
-MODE_FAST = 1    # fused entry points: closed-form block inverses + pivot-only J(t) (same function)
-MODE_SCAN = 2    # propagator_all_Jt_aug_batched only, d in {12, 13}: chunked parallel scan over the horizon (small batches)
+# include/hop_b200.h HOP_MODE_*
+MODE_EXACT = 0   # PARITY mode: the reference's operation order with individually rounded IEEE operations (Cholesky route,
+                 # no FMA); J(T) bit-identical to the plain-C oracle on identical inputs; any d, m <= 16
+MODE_FAST = 1    # throughput mode: closed-form block inverses + pivot-only J(t), pipelined Gauss-Jordan sweeps (same function)
+MODE_SCAN = 2    # d in {12, 13}: chunked parallel scan over the horizon (small batches; re-association changes the rounding)
+MODE_GJ = 3      # materialised blocks + in-place Gauss-Jordan inverse with FMA (the cold path of FAST; instantiated dims only)
+MODE_FP32 = 4    # propagator_all_Jt_aug_batched only: the EXACT sweep in single precision (well-conditioned problems only)
 
 
 @dataclass
@@ -238,11 +242,34 @@ class HorizonSelector:
         Bm = self.workspace[sX + sA:sX + sA + 8 * B * N * n * m].view(torch.float64).view(B, N, n, m)
         return X, A, Bm
 
-    def select_resident(self, xg: torch.Tensor, w: torch.Tensor) -> Selection:
+    def _goal_and_weight(self, xg, w):
+        """xg -> [B, n], w -> [B] fp64 CUDA tensors (scalars / single goals are broadcast; shapes are checked: the kernel
+        indexes xg[b*n + r] and w[b])."""
+        dev = self.device
+        if xg is None:
+            xg = np.broadcast_to(self.xg_default, (self.B, self.n)).copy()
+        xg = _dev(xg, dev)
+        if xg.dim() == 1:
+            xg = xg.expand(self.B, self.n).contiguous()
+        if w is None:
+            w = torch.full((self.B,), self.w_default, dtype=torch.float64, device=dev)
+        elif not isinstance(w, torch.Tensor):
+            w = np.broadcast_to(np.asarray(w, dtype=float), (self.B,)).copy()
+        w = _dev(w, dev)
+        if w.dim() == 0:
+            w = w.expand(self.B).contiguous()
+        if tuple(xg.shape) != (self.B, self.n) or tuple(w.shape) != (self.B,):
+            raise ValueError(f"xg must be [{self.n}] or [{self.B},{self.n}] and w a scalar or [{self.B}]; "
+                             f"got {tuple(xg.shape)} and {tuple(w.shape)}")
+        return xg, w
+
+    def select_resident(self, xg=None, w=None) -> Selection:
         """Fused selection on the (X, A, Bm) already resident in the workspace (no allocation, no copies):
-        the kernel-only step bench.py times."""
+        the kernel-only step bench.py times.  The returned Selection ALIASES the selector's output buffers (J, T_star,
+        J_star, status are overwritten by the next call on this selector); clone what must outlive it."""
         X, A, Bm = self.views()
         dev = self.device
+        xg, w = self._goal_and_weight(xg, w)
         with torch.cuda.device(dev):
             rc = self.lib.hop_select_fused_f64(
                 self.B, self.N, self.n, self.m, self.T_min, self.T_max, _ptr(A), _ptr(Bm), None, _ptr(X), _ptr(self.U),
@@ -251,12 +278,13 @@ class HorizonSelector:
         _cabi.check(rc, "hop_select_fused_f64")
         return Selection(self.J, self.T, self.Js, self.st)
 
-    def __call__(self, x0: torch.Tensor, xg: Optional[torch.Tensor] = None, w: Optional[torch.Tensor] = None) -> Selection:
+    def __call__(self, x0: torch.Tensor, xg=None, w=None) -> Selection:
+        """x0 [B, n] -> Selection.  The result aliases the selector's reused output buffers (see select_resident)."""
         dev = self.device
         x0 = _dev(x0, dev)
-        assert x0.shape == (self.B, self.n)
-        xg = _dev(np.broadcast_to(self.xg_default, (self.B, self.n)).copy(), dev) if xg is None else _dev(xg, dev)
-        w = torch.full((self.B,), self.w_default, dtype=torch.float64, device=dev) if w is None else _dev(w, dev)
+        if tuple(x0.shape) != (self.B, self.n):
+            raise ValueError(f"x0 must be [{self.B},{self.n}], got {tuple(x0.shape)}")
+        xg, w = self._goal_and_weight(xg, w)
         with torch.cuda.device(dev):
             rc = self.lib.hop_select_from_x0_f64(
                 self.B, self.F.hop_sys, self.params.ctypes.data_as(C.c_void_p), self.N, self.T_min, self.T_max,
@@ -268,7 +296,7 @@ class HorizonSelector:
 
 
 def select_horizon_batched(case, x0, xg=None, w=None, central: bool = False, mode: int = MODE_EXACT) -> Selection:
-    """One-shot x0 [B,n] (CUDA tensor) -> Selection."""
+    """One-shot x0 [B,n] (CUDA tensor) -> Selection (owns its outputs: the selector is dropped)."""
     x0 = _dev(x0)
     sel = HorizonSelector(case, x0.shape[0], device=x0.device, central=central, mode=mode)
     return sel(x0, xg, w)
