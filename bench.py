@@ -9,8 +9,10 @@ argmin for one instance (reference: augmented.py:10-87 + horizon_selection.py:36
   value : fused selection kernel on HBM-resident (A, B, X, U), CUDA-event timed, max over ranks.
   e2e   : the public host-buffer call (hop.api.select_horizon_host): pinned-host x0 -> device,
           rollout + FD linearisation + fused selection on device, T*/J*/status/J(T) back to host.
-  --impl reference : the same x0 -> T* pipeline on the host cores through the CPU oracle port
-          (oracle/, plain-C restatement of the reference; the reference is Python and cannot travel).
+  --impl reference : the same x0 -> T* pipeline on the host cores through the REFERENCE ITSELF (the unmodified Python
+          modules staged in oracle/_ref by __graft_entry__.build(), one process per core); the plain-C port
+          (oracle/hop_oracle.c, all host threads) is timed beside it and is the fallback when oracle/_ref is absent
+          (`--ref-kind port` forces it).
 
 Launch: `python bench.py --gpus 1 --steps K --warmup W`, or under torchrun for N > 1 (one rank per
 GPU; the batch is sharded, no collective on the solve path, a final all_gather of T*/J*).
@@ -107,35 +109,60 @@ def cpu_from_x0(case, x0, nthreads):
 
 
 def run_reference(args):
-    """`--impl reference`: CPU oracle port of the x0 -> T* pipeline, all host cores, bounded sample per step."""
+    """`--impl reference`: the reference's own CPU implementation of the x0 -> T* pipeline on all host cores, a bounded
+    sample per step.  kind "reference" = the unmodified Python modules from oracle/_ref (one process per core);
+    kind "port" = oracle/hop_oracle.c on one pthread per core (timed in both cases, reported beside it)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle as O
+    from oracle import ref_py
     from hop import cases
     O.build()
     case = cases.make_case("Quadrotor", N=N_HORIZON)
     cores = os.cpu_count() or 1
-    dt, *_ = cpu_from_x0(case, s1_x0(4 * cores, 1), cores)                 # calibration
+    # ---- the C port: calibrate, then ~2 s of CPU work
+    dt, *_ = cpu_from_x0(case, s1_x0(4 * cores, 1), cores)
     rate = 4 * cores / dt
-    sample = int(max(cores, min(args.batch, round(rate * 4.0 / cores) * cores)))   # ~4 s of CPU work per step
-    x0 = s1_x0(sample, 0)
+    psample = int(max(cores, min(args.batch, round(rate * 2.0 / cores) * cores)))
+    dtp, Jp, Tp, _ = cpu_from_x0(case, s1_x0(psample, 0), cores)
+    port = {"value": psample / dtp, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{psample} instances, oracle/hop_oracle.c on {cores} pthreads"}
+    use_py = ref_py.available() and args.ref_kind != "port"
+    if use_py:
+        pool = ref_py.Pool(cores)
+        sample = 4 * cores                                                  # ~0.45 s per instance and core: ~2 s per step
+        x0 = s1_x0(sample, 0)
+        step = lambda: pool.s1_select(x0)                                   # noqa: E731
+        kind = "reference"
+        what = (f"{sample} instances per step through the unmodified reference modules (oracle/_ref: solver.rollout, "
+                f"linearization.linearize_forward_diff_traj, augmented.*, horizon_selection.propagator_all_Jt_aug), "
+                f"{cores} worker processes, OPENBLAS threads = 1")
+    else:
+        sample = int(max(cores, min(args.batch, round(rate * 4.0 / cores) * cores)))   # ~4 s of CPU work per step
+        x0 = s1_x0(sample, 0)
+        step = lambda: cpu_from_x0(case, x0, cores)                         # noqa: E731
+        kind = "port"
+        what = (f"{sample} instances per step, pthread fan-out of oracle/hop_oracle.c over {cores} host threads "
+                "(oracle/_ref not staged: the reference is pure Python and was not copied by build())")
     for _ in range(args.warmup):
-        cpu_from_x0(case, x0, cores)
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_from_x0(case, x0, cores)
+        out = step()
     el = time.perf_counter() - t0
     val = sample * args.steps / el
+    agree = None
+    if use_py:
+        pool.close()
+        agree = bool(np.array_equal(out[0], Tp[:sample])) if sample <= psample else None
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_step": sample, "threads": cores,
                        "timed": "whole x0 -> T* pipeline on the host cores (the e2e definition of the hop arm)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} instances per step, pthread fan-out of oracle/hop_oracle.c over {cores} host "
-                                       "threads (the reference is pure Python/numpy and is not installable on the box; "
-                                       "its measured speed in the build container is ~17 solves/s/core, SURVEY.md s.6.2)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": what,
+                             "port": port, "T_star_reference_equals_port_on_sample": agree},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -165,7 +192,7 @@ def run_hop(args):
     x0_host.copy_(torch.from_numpy(s1_x0(B, seed=rank)))
 
     # ---- resident inputs for the kernel-only number: rollout + linearisation done once, on device
-    mode = api.MODE_FAST if args.mode == "fast" else api.MODE_EXACT
+    mode = {"fast": api.MODE_FAST, "exact": api.MODE_EXACT, "gj": api.MODE_GJ}[args.mode]
     sel = api.HorizonSelector(case, B, device=dev, mode=mode)
     x0_dev = x0_host.to(dev)
     res = sel(x0_dev)                                   # also warms everything up
@@ -261,41 +288,77 @@ def run_hop(args):
     ach_tf = flop_launch / (ms_launch * 1e-3) / 1e12
     ach_gb = byte_launch / (ms_launch * 1e-3) / 1e9
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": ach_tf / tf.value,
-                "traffic": traffic, "kernel": "k_select_fused_mma<13,4,%s>" % ("pipelined" if mode else "exact"),
+                "traffic": traffic, "kernel": {"fast": "k_select_fused_mma<13,4,pipelined>", "gj": "k_select_fused_mma<13,4,materialised>",
+                                                        "exact": "k_select_ref_fused"}[args.mode],
                 "peak_source": "DFMA microbenchmark in this run (hop_probe_fp64_tflops); nominal 37.2 TFLOP/s",
                 "algorithmic_flop_per_solve": f_alg(N_HORIZON, D_AUG, M_CTRL),
                 "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                         "algorithmic_bytes_per_solve": b_alg_fused(N_HORIZON, n, m),
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}}
 
-    # ---- CPU baseline on a bounded sample of the same workload (oracle port, all host cores)
+    # ---- CPU baseline + parity census (outside every timed region)
+    #  * the C port on ALL B instances of rank 0 (all host cores): throughput + the three-number census of oracle/census.py
+    #    (|gpu-oracle|, |oracle-fp80|, |gpu-fp80|, argmin gaps, ill-posed instances; a T* mismatch must be explained by it)
+    #  * HOP_MODE_EXACT on the same batch on the device: the measured mode against the parity mode
+    #  * the REAL reference (oracle/_ref, unmodified Python) on the first instances: T* equality and solves/s per core
+    #  * the committed reference-generated golden (first 4096 instances of this very batch, tests/golden)
     import oracle as O
+    from oracle import census, ref_py
     O.build()
     cores = os.cpu_count() or 1
-    dtc, *_ = cpu_from_x0(case, s1_x0(4 * cores, 1), cores)
-    rate = 4 * cores / dtc
-    sample = int(max(cores, min(B, round(rate * 12.0 / cores) * cores)))
-    dtc, Jc, Tc, stc = cpu_from_x0(case, x0_np[:sample], cores)
-    mism_idx = np.nonzero(Tc != T_h[:sample])[0]
-    mism = int(mism_idx.size)
-    relJ = float(np.max(np.abs(J_h[:sample, T_min - 1:] - Jc[:, T_min - 1:]) / np.abs(Jc[:, T_min - 1:])))
-    # every T* mismatch is re-examined with the selection sweep in x87 extended precision ("truth" of the same
-    # jittered algorithm): a near-tie whose winner is decided by fp64 rounding is ill-posed for ANY implementation,
-    # the reference included (SURVEY.md s.9 argmin-gap census)
-    detail = []
-    Uc = np.tile(u_ref, (N, 1))
-    for bb in mism_idx[:8]:
-        Xc = O.rollout(F.hop_sys, F.hop_params, x0_np[bb], Uc)
-        Ac, Bc = O.linearize(F.hop_sys, F.hop_params, Xc, Uc)
-        J80, T80 = O.select_fused(Ac, Bc, Xc, Uc, xg, u_ref, Q, R, alpha, w, T_min, T_max, wrap_idx, f80=True)
-        tg, to = int(T_h[bb]), int(Tc[bb])
-        detail.append({"instance": int(bb), "T_gpu": tg, "T_oracle_fp64": to, "T_fp80": int(T80),
-                       "rel_gap_between_the_two_candidates": float(abs(J80[tg - 1] - J80[to - 1]) / abs(J80[to - 1])),
-                       "rel_noise_fp64_vs_fp80_at_T": float(abs(Jc[bb, to - 1] - J80[to - 1]) / abs(J80[to - 1]))})
+    t0c = time.perf_counter()
+    rep = census.census_from_x0(case, x0_np, J_h, T_h, nthreads=cores, fp80_stride=8)
+    t_census = time.perf_counter() - t0c
+    dtc, Jc, Tc, stc = cpu_from_x0(case, x0_np[:min(B, 16384)], cores)          # timed alone (the census also runs fp80 sweeps)
+    sample = min(B, 16384)
+    ex = api.select_horizon_batched(case, x0_dev, mode=api.MODE_EXACT)
+    T_ex = ex.T_star.cpu().numpy().astype(np.int64); J_ex = ex.J.cpu().numpy()
+    Tg = T_h.astype(np.int64)
+    dmode = np.abs(J_h[:, T_min - 1:] - J_ex[:, T_min - 1:]) / np.abs(J_ex[:, T_min - 1:])
+    mm = np.nonzero(T_ex != Tg)[0]
+    unexpl = 0
+    for i in mm:
+        gap = abs(J_ex[i, T_ex[i] - 1] - J_ex[i, Tg[i] - 1]) / abs(J_ex[i, T_ex[i] - 1])
+        noise = max(abs(J_h[i, t - 1] - J_ex[i, t - 1]) / abs(J_ex[i, t - 1]) for t in (T_ex[i], Tg[i]))
+        unexpl += int(not gap < 10.0 * noise)
+    rep_ex = census.census_from_x0(case, x0_np[:sample], J_ex[:sample], T_ex[:sample], nthreads=cores, fp80_stride=8)
+    vs_exact = {"checked": int(B), "T_star_mismatches": int(mm.size), "T_star_mismatches_unexplained": unexpl,
+                "rule": "gap between the two candidates (EXACT curve) < 10 x distance between the two curves at those horizons",
+                "max_rel_J_window": float(dmode.max()), "p99_rel_J_window": float(np.percentile(dmode.max(axis=1), 99)),
+                "exact_mode_vs_oracle": {k: rep_ex[k] for k in ("checked", "T_star_mismatches", "T_star_mismatches_unexplained",
+                                                                 "rel_J_window", "rel_J_at_Tstar")}}
+    golden_chk = None
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "s1_quadrotor_ref4096.npz"))
+        if rank == 0 and int(g["seed"]) == 0 and B >= g["T"].shape[0]:
+            ng = g["T"].shape[0]
+            Tr = g["T"].astype(np.int64)
+            cols = np.clip(Tr[:, None] + np.arange(-2, 3)[None, :], 1, T_max)
+            J5 = J_h[np.arange(ng)[:, None], cols - 1]
+            golden_chk = {"instances": int(ng), "T_star_mismatches": int((Tg[:ng] != Tr).sum()),
+                          "max_rel_J_at_Tstar_pm2": float(np.nanmax(np.abs(J5 - g["J_pm2"]) / np.abs(g["J_pm2"]))),
+                          "what": "first 4096 instances of this batch computed by the REAL reference in the build container "
+                                  "(tests/golden/make_golden.py s1_ref4096)"}
+    except OSError:
+        pass
+    ref_leg = {"available": False, "why": "oracle/_ref not staged"}
+    if ref_py.available():
+        nref = 8 * cores
+        pool = ref_py.Pool(cores)
+        Tpy, Jpy, dpy = pool.s1_select(x0_np[:nref])
+        pool.close()
+        ref_leg = {"available": True, "kind": "reference", "instances": int(nref), "value": nref / dpy, "unit": UNIT,
+                   "cores": cores, "per_core": nref / dpy / cores,
+                   "T_star_equal_gpu": int((Tpy == T_h[:nref]).sum()), "T_star_equal_port": int((Tpy == Tc[:nref]).sum()),
+                   "max_rel_J_window_gpu_vs_reference": float(np.max(np.abs(J_h[:nref, T_min - 1:] - Jpy[:, T_min - 1:]) / np.abs(Jpy[:, T_min - 1:]))),
+                   "max_rel_J_window_port_vs_reference": float(np.max(np.abs(Jc[:nref, T_min - 1:] - Jpy[:, T_min - 1:]) / np.abs(Jpy[:, T_min - 1:]))),
+                   "what": "the unmodified reference modules (oracle/_ref) on the first instances of this batch, one process per core"}
     cpu_baseline = {"value": sample / dtc, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"first {sample} instances of rank 0's batch, x0 -> T* pipeline, oracle/hop_oracle.c on {cores} "
-                              "pthreads (the Python reference itself measured ~17 solves/s/core in the build container)",
-                    "parity_on_sample": {"T_star_mismatches": mism, "max_rel_J_window": relJ, "mismatch_detail": detail}}
+                              "pthreads",
+                    "reference_python": ref_leg,
+                    "parity_on_sample": dict(rep, census_seconds=t_census, mode_checked=args.mode),
+                    "fast_vs_exact_mode_on_device": vs_exact, "reference_golden": golden_chk}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -303,7 +366,10 @@ def run_hop(args):
             "config": {"workload": WORKLOAD,
                        "timed": "value: fused selection kernel on HBM-resident linearisation; e2e: whole x0 -> T* pipeline from pinned host buffers",
                        "batch_per_gpu": B, "global_batch": world * B,
-                       "mode": args.mode + " (sequential in the horizon; software-pipelined pivot sweeps)",
+                       "mode": args.mode + {"fast": " (sequential in the horizon; software-pipelined pivot sweeps; checked against HOP_MODE_EXACT "
+                                                    "and the oracle on every instance: cpu_baseline.parity_on_sample / fast_vs_exact_mode_on_device)",
+                                            "gj": " (materialised blocks, Gauss-Jordan inverse)",
+                                            "exact": " (reference operation order, bit-identical to the oracle on identical inputs)"}[args.mode],
                        "l2": "inputs (A,B,X = %.1f GB per GPU) exceed the 126 MB L2" % (byte_launch / 1e9),
                        "parallelism": f"batch-sharded x{world}, final all_gather of T*/J*" if world > 1 else "single GPU"},
             "clocks": clocks,
@@ -324,8 +390,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["hop", "reference"], default="hop")
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU (weak scaling)")
-    ap.add_argument("--mode", choices=["exact", "fast"], default="fast",
-                    help="selection variant (include/hop_b200.h HOP_MODE_*); both compute the same function")
+    ap.add_argument("--mode", choices=["exact", "fast", "gj"], default="fast",
+                    help="selection variant (include/hop_b200.h HOP_MODE_*); all compute the same function")
+    ap.add_argument("--ref-kind", choices=["auto", "port"], default="auto",
+                    help="--impl reference: auto = the Python reference from oracle/_ref when staged, else the C port")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
