@@ -113,23 +113,52 @@ def _ddp(name, x0s, dev, max_iter, check, label, cfg, N=None, mode=None):
            "phase_seconds_rank0": r["timers"]}
     if rank == 0 and check > 0:
         k = min(check, hi - lo)
-        o = O.ilqr_timeopt_batch(F.hop_sys, F.hop_params, Nn, T_min, T_max, x0s[:k], np.tile(u_ref, (Nn, 1)), xg, u_ref, Q, R,
-                                 alpha, w, wrap_idx, max_iter=max_iter, use_central_diff=False, nthreads=os.cpu_count() or 1)
-        # second opinion: the same algorithm with the selection sweep in x87 extended precision.  Where the two CPU runs
-        # disagree the instance is ill-posed (its T_hist is decided by fp64 rounding: the reference itself flips there,
-        # SURVEY.md s.9), and an independent implementation cannot be asked to reproduce it.
-        o80 = O.ilqr_timeopt_batch(F.hop_sys, F.hop_params, Nn, T_min, T_max, x0s[:k], np.tile(u_ref, (Nn, 1)), xg, u_ref, Q, R,
-                                   alpha, w, wrap_idx, max_iter=max_iter, use_central_diff=False, f80_select=True,
-                                   nthreads=os.cpu_count() or 1)
-        well = [np.array_equal(o["T_hist"][b, :o["n_hist"][b]], o80["T_hist"][b, :o80["n_hist"][b]]) for b in range(k)]
-        same_T = [np.array_equal(Th[b, :nh[b]], o["T_hist"][b, :o["n_hist"][b]]) for b in range(k)]
-        relJ = [rel(Jh[b, :nh[b]], o["J_hist"][b, :nh[b]]) for b in range(k) if same_T[b]]
-        rec["parity_vs_oracle"] = {"checked": k, "well_posed": int(sum(well)),
-                                   "T_hist_identical_among_well_posed": int(sum(s_ and w_ for s_, w_ in zip(same_T, well))),
-                                   "T_hist_identical": int(sum(same_T)),
-                                   "max_rel_J_hist_where_T_identical": float(max(relJ)) if relJ else None,
-                                   "T_star_identical": int((r["T_star"].cpu().numpy()[:k] == o["T_star"][:k]).sum())}
+        rec["parity_vs_oracle"] = ddp_census(case, Nn, x0s[:k], max_iter, {"fast": (nh, Th, Jh, r["T_star"].cpu().numpy())}, dev)
     emit(rec)
+
+
+def ddp_census(case, Nn, x0s, max_iter, runs, dev):
+    """HOP-DDP parity census against the oracle on identical initial states.
+
+    An instance is WELL-POSED when its T_hist is stable under rounding-level perturbations of the reference computation
+    itself: the fp64 oracle, the oracle with the selection sweep in x87 extended precision, and the fp64 oracle started
+    from x0 + 1e-15 and from x0 (1 + 4e-16) all produce the same T_hist (the reference flips on the others when only the BLAS
+    kernel set changes, SURVEY.md s.9 -- an independent implementation cannot be asked to reproduce those).  `runs` maps a
+    label to a device result (n_hist, T_hist, J_hist, T_star); HOP_MODE_EXACT is always run here in addition."""
+    import oracle as O
+    from _common import rel
+    from hop import api
+    F, x0, xg, u_ref, Q, R, alpha, w, _N, T_min, T_max, wrap_idx, _ = case
+    T_max = min(T_max, Nn)
+    k = len(x0s)
+    th = os.cpu_count() or 1
+    kw = dict(max_iter=max_iter, use_central_diff=False, nthreads=th)
+    a = lambda x: (F.hop_sys, F.hop_params, Nn, T_min, T_max, x, np.tile(u_ref, (Nn, 1)), xg, u_ref, Q, R, alpha, w, wrap_idx)  # noqa: E731
+    t0 = time.perf_counter()
+    o = O.ilqr_timeopt_batch(*a(x0s), **kw)
+    t_cpu = time.perf_counter() - t0
+    variants = [O.ilqr_timeopt_batch(*a(x0s), f80_select=True, **kw), O.ilqr_timeopt_batch(*a(x0s + 1e-15), **kw),
+                O.ilqr_timeopt_batch(*a(x0s * (1.0 + 4e-16)), **kw)]
+
+    def same(p, q, b):
+        return p["n_hist"][b] == q["n_hist"][b] and np.array_equal(p["T_hist"][b, :p["n_hist"][b]], q["T_hist"][b, :q["n_hist"][b]])
+    well = np.array([all(same(o, v, b) for v in variants) for b in range(k)])
+    ex = api.ilqr_timeopt_batched(case, torch.as_tensor(x0s, device=dev), max_iter=max_iter, use_central_diff=False,
+                                  mode=api.MODE_EXACT)
+    runs = dict(runs, exact=(ex["n_hist"].cpu().numpy(), ex["T_hist"].cpu().numpy(), ex["J_hist"].cpu().numpy(),
+                             ex["T_star"].cpu().numpy()))
+    out = {"checked": k, "well_posed": int(well.sum()),
+           "well_posed_rule": "T_hist identical among the fp64 oracle, the oracle with an fp80 selection sweep, and the fp64 "
+                              "oracle from x0 + 1e-15 and from x0 (1 + 4e-16)",
+           "oracle_solves_per_s_all_host_threads": k / t_cpu, "host_threads": th}
+    for label, (nh, Th, Jh, Ts) in runs.items():
+        same_T = np.array([nh[b] == o["n_hist"][b] and np.array_equal(Th[b, :nh[b]], o["T_hist"][b, :o["n_hist"][b]]) for b in range(k)])
+        relJ = [rel(Jh[b, :nh[b]], o["J_hist"][b, :nh[b]]) for b in range(k) if same_T[b]]
+        out[label] = {"T_hist_identical": int(same_T.sum()), "T_hist_identical_among_well_posed": int((same_T & well).sum()),
+                      "well_posed_but_different": [int(b) for b in np.nonzero(well & ~same_T)[0][:16]],
+                      "max_rel_J_hist_where_T_identical": float(max(relJ)) if relJ else None,
+                      "T_star_identical": int((Ts[:k] == o["T_star"][:k]).sum())}
+    return out
 
 
 def cfg2(args, dev):
@@ -145,7 +174,7 @@ def cfg3(args, dev):
     B = 256 if args.small else 4096
     rng = np.random.default_rng(0)                                              # the reference's cartpole sigma is 0
     x0s = np.array([rng.normal(0, .1, B), rng.normal(0, .1, B), rng.normal(0, .2, B), rng.normal(0, .2, B)]).T
-    _ddp("Cartpole_SwingUp", x0s, dev, 12, 32, f"Cartpole swing-up HOP-DDP (augmented homogeneous state), {B} random initial "
+    _ddp("Cartpole_SwingUp", x0s, dev, 12, B, f"Cartpole swing-up HOP-DDP (augmented homogeneous state), {B} random initial "
          "states x0 ~ N(0, diag(.1,.1,.2,.2)^2), max-iter 12; T* is ill-posed at the reference's own noise level "
          "(argmin gap 1.3e-5 < 3e-5, SURVEY.md s.9)", 3)
 
@@ -153,7 +182,7 @@ def cfg3(args, dev):
 def cfg4(args, dev):
     from _common import s1_x0
     B = 1024 if args.small else 16384
-    _ddp("Quadrotor", s1_x0(B, seed=4), dev, 12, 32, f"Quadrotor 12-DOF HOP-DDP, N=128, {B} initial states, max-iter 12, "
+    _ddp("Quadrotor", s1_x0(B, seed=4), dev, 12, 1024, f"Quadrotor 12-DOF HOP-DDP, N=128, {B} initial states, max-iter 12, "
          "batch sharded over the ranks", 4, N=128)
 
 

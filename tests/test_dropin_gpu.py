@@ -55,6 +55,10 @@ def test_reference_call_flow_single_instance(m, name, maker):
                                                                                        wrap_idx=wrap_idx)
     QT = m["augmented"].build_terminal_aug_list(X, xg, alpha, wrap_idx=wrap_idx)
     ks = g["ks"]
+    assert np.abs(np.stack([A_aug[k] for k in ks]) - g["A_aug_ks"]).max() <= 2e-9 * max(1.0, np.abs(g["A_aug_ks"]).max())
+    assert np.abs(np.stack([B_aug[k] for k in ks]) - g["B_aug_ks"]).max() <= 2e-9 * max(1.0, np.abs(g["B_aug_ks"]).max())
+    assert all(a.shape == (x0.size + 1, x0.size + 1) for a in A_aug) and all(b.shape == (x0.size + 1, u_ref.size) for b in B_aug)
+    assert np.array_equal(z0, g["z0"])
     assert np.abs(np.stack([Q_aug[k] for k in ks]) - g["Q_aug_ks"]).max() <= 1e-9 * np.abs(g["Q_aug_ks"]).max()
     assert np.abs(np.stack([QT[k] for k in ks]) - g["QT_ks"]).max() <= 1e-9 * np.abs(g["QT_ks"]).max()
     assert np.abs(R_inv - g["R_inv"]).max() <= 1e-12 * np.abs(g["R_inv"]).max()

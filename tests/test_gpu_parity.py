@@ -352,11 +352,13 @@ def test_nonzero_affine_residuals_in_every_selection_kernel(mode):
         xg_t = _t(np.broadcast_to(xg, (Bsz, 12)).copy()); w_t = _t(np.full(Bsz, float(w)))
         p_ = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
         Xd, Ud, Ad, Bd, ard = _t(X), _t(U), _t(A), _t(Bm), _t(ar)
+        ur_t, Q_t, Qf_t = _t(u_ref), _t(Q), _t(O.as_terminal_weight(alpha, 12))   # (kept alive: the launches are asynchronous)
         _cabi.check(lib.hop_build_augmented_f64(Bsz, N, 12, m, p_(Ad), p_(Bd), p_(ard), p_(Xd), p_(Ud), N * m, p_(xg_t), p_(w_t),
-                                                p_(_t(u_ref)), p_(_t(Q)), O.wrap_mask(wrap_idx), 1e-9, 1e-12, p_(A_aug),
+                                                p_(ur_t), p_(Q_t), O.wrap_mask(wrap_idx), 1e-9, 1e-12, p_(A_aug),
                                                 p_(B_aug), p_(Q_aug), None), "hop_build_augmented_f64")
-        _cabi.check(lib.hop_build_terminal_f64(Bsz, N, 12, p_(Xd), p_(xg_t), p_(_t(O.as_terminal_weight(alpha, 12))),
+        _cabi.check(lib.hop_build_terminal_f64(Bsz, N, 12, p_(Xd), p_(xg_t), p_(Qf_t),
                                                O.wrap_mask(wrap_idx), 1e-12, p_(QT), None), "hop_build_terminal_f64")
+        torch.cuda.synchronize()
         z0 = np.zeros(d); z0[-1] = 1.0
         s1 = api.propagator_all_Jt_aug_batched(A_aug, B_aug, Q_aug, _t(O.chol_inv(0.5 * (R + R.T))), _t(z0), QT, T_min, T_max,
                                                mode=mode)
@@ -681,36 +683,27 @@ def test_batched_hop_ddp_matches_oracle_on_sampled_quadrotor_instances(mode):
 
 
 def test_cartpole_batched_solve_against_the_oracle_on_identical_initial_states():
-    """Config 3 flavour: cartpole from perturbed initial states (the reference's own sigma is zero), HOP_MODE_EXACT against
-    the oracle on the SAME x0.  The cartpole embedding amplifies rounding (Q has a zero weight: |E_k| ~ 5e8; the jitter
-    ladder and the LU fallback are live), so an instance is only compared when it is WELL-POSED: the fp64 oracle and the
-    oracle with the selection sweep in x87 extended precision produce the same T_hist.  On those, T_hist must be identical
-    and J_hist within 1e-6; the nominal instance (the reference's own run, golden) is compared too."""
+    """Config 3 flavour: cartpole from perturbed initial states (the reference's own sigma is zero), HOP_MODE_EXACT and
+    HOP_MODE_FAST against the oracle on the SAME x0.  The cartpole embedding amplifies rounding (Q has a zero weight:
+    |E_k| ~ 5e8), so ~30 % of the instances have a T_hist that the REFERENCE COMPUTATION ITSELF does not reproduce under
+    rounding-level perturbations; the census (tests/run_configs.py: ddp_census) calls an instance well-posed when the fp64
+    oracle, the oracle with an fp80 selection sweep, and the fp64 oracle from x0 + 1e-15 / x0 (1 + 4e-16) agree on T_hist.
+    On every well-posed instance T_hist must be IDENTICAL to the oracle's and J_hist within 1e-6."""
+    from run_configs import ddp_census
     g = golden("case_Cartpole_SwingUp")
     case = cases.make_case("Cartpole_SwingUp")
-    F, x0c, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = case
     rng = np.random.default_rng(0)
-    Bsz = 32
+    Bsz = 64
     x0s = np.array([rng.normal(0, .1, Bsz), rng.normal(0, .1, Bsz), rng.normal(0, .2, Bsz), rng.normal(0, .2, Bsz)]).T
-    x0s[0] = x0c
-    r = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=12, use_central_diff=False, mode=api.MODE_EXACT)
-    kw = dict(max_iter=12, use_central_diff=False, nthreads=8)
-    args = (F.hop_sys, F.hop_params, N, T_min, T_max, x0s, np.tile(u_ref, (N, 1)), xg, u_ref, Q, R, alpha, w, wrap_idx)
-    o64 = O.ilqr_timeopt_batch(*args, **kw)
-    o80 = O.ilqr_timeopt_batch(*args, f80_select=True, **kw)
-    nh = r["n_hist"].cpu().numpy(); Th = r["T_hist"].cpu().numpy(); Jh = r["J_hist"].cpu().numpy()
-    well = [b for b in range(Bsz) if o64["n_hist"][b] == o80["n_hist"][b]
-            and np.array_equal(o64["T_hist"][b, :o64["n_hist"][b]], o80["T_hist"][b, :o80["n_hist"][b]])]
-    assert len(well) >= Bsz // 2
+    x0s[0] = case[1]
+    r = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=12, use_central_diff=False, mode=api.MODE_FAST)
     assert torch.isfinite(r["J_hist"][:, 0]).all()
-    same = 0
-    for b in well:
-        k = o64["n_hist"][b]
-        if nh[b] == k and np.array_equal(Th[b, :k], o64["T_hist"][b, :k]):
-            same += 1
-            assert rel(Jh[b, :k], o64["J_hist"][b, :k]) <= 1e-6
-    # the device dynamics differ from the host's by CUDA's sin/cos (<= 2 ulp); on a well-posed instance that must not move T_hist
-    assert same >= len(well) - 1, (same, len(well))
+    rep = ddp_census(case, case[8], x0s, 12, {"fast": (r["n_hist"].cpu().numpy(), r["T_hist"].cpu().numpy(),
+                                                         r["J_hist"].cpu().numpy(), r["T_star"].cpu().numpy())}, DEV)
+    assert rep["well_posed"] >= Bsz // 2, rep
+    for label in ("exact", "fast"):
+        assert rep[label]["T_hist_identical_among_well_posed"] == rep["well_posed"], (label, rep)
+        assert rep[label]["max_rel_J_hist_where_T_identical"] <= 1e-6, (label, rep)
+    # the reference's own run of the nominal instance (golden); the oracle itself is within |dT| <= 1 of it (tests/test_oracle.py)
     n0 = len(g["sol_T_hist"])
-    if 0 in well:
-        assert nh[0] == n0 and np.abs(Th[0, :n0] - g["sol_T_hist"]).max() <= 1      # the reference's own run (oracle: |dT| <= 1)
+    assert int(r["n_hist"][0]) == n0 and np.abs(r["T_hist"].cpu().numpy()[0, :n0] - g["sol_T_hist"]).max() <= 1
