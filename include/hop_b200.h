@@ -155,7 +155,9 @@ int hop_build_augmented_f64(int B, int N, int n, int m, const double *A, const d
 int hop_build_terminal_f64(int B, int N, int n, const double *X, const double *xg, const double *Qf, unsigned wrap_mask,
                            double rho_reg, double *QT, void *stream);
 
-/* solver.py:65-105 cost_timeopt_true, batched: J_out[b] at the per-instance horizon T_star[b] (device int). */
+/* solver.py:65-105 cost_timeopt_true, batched: J_out[b] at the per-instance horizon T_star[b] (device int).
+ * In this and the two entry points below a T_star[b] > N is clamped to N on the device (the trajectories hold N steps);
+ * T_star[b] <= 0 behaves as in the reference (cost = inf; backward pass: ok = 0). */
 int hop_cost_f64(int B, int N, int n, int m, const double *X, const double *U, const double *xg, const double *w,
                  const double *u_ref, const double *Q, const double *R, const double *Qf, unsigned wrap_mask,
                  const int *T_star, double *J_out, void *stream);

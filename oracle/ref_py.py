@@ -120,3 +120,32 @@ def _worker_warm(_):
         pass
     _quadrotor_128()
     return 0
+
+
+# ---- the reference's brute-force curve (solver.py:293-358), config 5's CPU comparator -------------------------------
+def _bf_one(arg):
+    (A, B, X, U, xg, u_ref, Q, R, alpha, w), N = arg
+    solver = _import()["solver"]
+    return solver.bruteforce_all_Jt_backward_expansion(list(A), list(B), X, U, xg, u_ref, Q, R, alpha, w, N, lm_lambda=0.0)
+
+
+def bruteforce_rate(insts, N, procs=None):
+    """solves/s of solver.bruteforce_all_Jt_backward_expansion over `insts` (tuples A, B, X, U, xg, u_ref, Q, R, alpha, w)
+    with one worker process per core."""
+    import multiprocessing as mp
+    procs = int(procs or os.cpu_count() or 1)
+    with mp.get_context("fork").Pool(procs) as pool:
+        pool.map(_worker_warm_import, range(procs))
+        t = time.perf_counter()
+        pool.map(_bf_one, [(a, N) for a in insts])
+        return len(insts) / (time.perf_counter() - t)
+
+
+def _worker_warm_import(_):
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    _import()
+    return 0

@@ -186,8 +186,49 @@ def cfg4(args, dev):
          "batch sharded over the ranks", 4, N=128)
 
 
+def _bruteforce_cpu_timing(d, m, N, n_inst=None):
+    """Config 5's CPU comparator: the reference's brute-force curve (solver.py:293-358 semantics: one Riccati sweep per
+    candidate horizon, O(N^2 d^3)) on the sub-variant S2c (time-invariant Q_k = Q_0, X_{k+1} = A_k X_k, X_0 = z0, U = 0,
+    alpha = 50, lm_lambda = 0), timed on all host cores: the C port through a thread pool (the ctypes call
+    releases the GIL) and, when oracle/_ref is staged, the reference's own Python function on one process per core."""
+    import concurrent.futures as cf
+    import oracle as O
+    from oracle import ref_py
+    from _common import s2_instance
+    th = os.cpu_count() or 1
+    n_inst = n_inst or 2 * th
+
+    def inst(seed):
+        A, B, Q, R, z0, w, QT = s2_instance(seed, d, m, N)
+        X = np.zeros((N + 1, d)); X[0] = z0
+        for k in range(N):
+            X[k + 1] = A[k] @ X[k]
+        return A, B, X, np.zeros((N, m)), np.zeros(d), np.zeros(m), Q[0], R, 50.0, w
+    insts = [inst(s) for s in range(n_inst)]
+    one = lambda a: O.bruteforce_all_Jt(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], N, lm_lambda=0.0)  # noqa: E731
+    one(insts[0])
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(th) as ex:
+        Jb = list(ex.map(one, insts))
+    t_port = time.perf_counter() - t0
+    out = {"instances": n_inst, "host_threads": th, "port_solves_per_s": n_inst / t_port,
+           "what": "bruteforce_all_Jt_backward_expansion semantics (solver.py:293-358) on S2c, all host cores"}
+    # loose sanity (SURVEY.md s.8d): the propagator's 1e-9 jitter has no counterpart in the Riccati sweep (~1e-8)
+    A, B, X, U0, xg0, ur0, Q0, R, alpha, w = insts[0]
+    Jp = O.propagator_all_Jt(A, B, np.tile(Q0, (N, 1, 1)), O.chol_inv(R), X[0], np.tile(50.0 * np.eye(d), (N, 1, 1)))
+    out["rel_propagator_vs_bruteforce_curve"] = float(np.max(np.abs(Jp + w * np.arange(1, N + 1) - Jb[0]) / np.abs(Jb[0])))
+    if ref_py.available():
+        k = min(n_inst, th)
+        out["reference_python_solves_per_s"] = ref_py.bruteforce_rate(insts[:k], N, th)
+        out["reference_python_instances"] = k
+    return out
+
+
 def cfg5(args, dev):
-    """Synthetic batched HOP-LQR sweep (LQR-boundary entry point hop_select_f64)."""
+    """Synthetic batched HOP-LQR sweep (LQR-boundary entry point hop_select_f64): 2^20 instances for EVERY (d, N).  At d = 12 / 13
+    the LQR-boundary inputs of 2^20 instances (0.25 - 1.2 TB) exceed the HBM of 8 GPUs, so the batch is processed as tiles of
+    at most ~40 GB per rank: a tile is generated on the device from its seed, selected, checked and dropped; the reported
+    time is the sum of the selection calls (generation is not timed)."""
     import oracle as O
     from _common import rel, s2_batch
     from hop import api, dist as hdist
@@ -202,44 +243,59 @@ def cfg5(args, dev):
         for N in (64, 128, 256):
             per = b_alg(N, d, m)
             Btot = (1 << 20) if not args.small else (1 << 14)
-            Btot = min(Btot, int(40e9 * G // per))                              # keep each rank's inputs under ~40 GB
             lo, hi = hdist.shard_bounds(Btot, rank, G)
-            B = hi - lo
-            gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
-            A = torch.eye(d, dtype=torch.float64, device=dev).expand(B, N, d, d) + \
-                0.05 / np.sqrt(d) * torch.randn((B, N, d, d), dtype=torch.float64, device=dev, generator=gen)
-            Bm = 0.05 * torch.randn((B, N, d, m), dtype=torch.float64, device=dev, generator=gen)
-            Q = torch.diag_embed(0.5 + 1.5 * torch.rand((B, N, d), dtype=torch.float64, device=dev, generator=gen))
-            QT = (50.0 * torch.eye(d, dtype=torch.float64, device=dev)).expand(B, N, d, d).contiguous()
-            Rd = 0.05 + 0.45 * torch.rand((B, m), dtype=torch.float64, device=dev, generator=gen)
-            Rinv = torch.diag_embed(1.0 / (Rd + 1e-9))                          # chol_inv of a diagonal R (utils.py:79-85)
-            z0 = torch.randn((B, d), dtype=torch.float64, device=dev, generator=gen)
-            w = 0.01 + 0.09 * torch.rand((B,), dtype=torch.float64, device=dev, generator=gen)
-            run = lambda: api.propagator_all_Jt_aug_batched(A, Bm, Q, Rinv, z0, QT, 1, N, w_explicit=w)  # noqa: E731
-            run()
-            sel, dt = timed(run, reps=2)
-            dt = max_over_ranks(dt, dev)
-            rec = {"config": 5, "what": f"synthetic HOP-LQR d={d} m={m} N={N}", "batch": Btot, "device_s": dt,
+            Bmine = hi - lo
+            tile = max(1, min(Bmine, int(40e9 // per)))
+            ntiles = -(-Bmine // tile)
+            dt_sum, nonzero, first = 0.0, 0, None
+            for ti in range(ntiles):
+                B = min(tile, Bmine - ti * tile)
+                gen = torch.Generator(device=dev); gen.manual_seed(1234 + 1000 * rank + ti)
+                A = torch.eye(d, dtype=torch.float64, device=dev).expand(B, N, d, d) + \
+                    0.05 / np.sqrt(d) * torch.randn((B, N, d, d), dtype=torch.float64, device=dev, generator=gen)
+                Bm = 0.05 * torch.randn((B, N, d, m), dtype=torch.float64, device=dev, generator=gen)
+                Q = torch.diag_embed(0.5 + 1.5 * torch.rand((B, N, d), dtype=torch.float64, device=dev, generator=gen))
+                QT = (50.0 * torch.eye(d, dtype=torch.float64, device=dev)).expand(B, N, d, d).contiguous()
+                Rd = 0.05 + 0.45 * torch.rand((B, m), dtype=torch.float64, device=dev, generator=gen)
+                Rinv = torch.diag_embed(1.0 / (Rd + 1e-9))                      # chol_inv of a diagonal R (utils.py:79-85)
+                z0 = torch.randn((B, d), dtype=torch.float64, device=dev, generator=gen)
+                w = 0.01 + 0.09 * torch.rand((B,), dtype=torch.float64, device=dev, generator=gen)
+                run = lambda: api.propagator_all_Jt_aug_batched(A, Bm, Q, Rinv, z0, QT, 1, N, w_explicit=w, mode=api.MODE_FAST)  # noqa: E731
+                if ti == 0:
+                    run()                                                       # warm-up
+                sel, dt = timed(run, reps=2 if ntiles == 1 else 1)
+                dt_sum += dt
+                nonzero += int((sel.status != 0).sum())
+                if ti == 0 and rank == 0:
+                    k = 64
+                    Jo, sto = O.propagator_batch(A[:k].cpu().numpy(), Bm[:k].cpu().numpy(), Q[:k].cpu().numpy(), Rinv[:k].cpu().numpy(),
+                                                 z0[:k].cpu().numpy(), QT[:k].cpu().numpy(), nthreads=os.cpu_count() or 1)
+                    tot = Jo + w[:k].cpu().numpy()[:, None] * np.arange(1, N + 1)
+                    first = {"checked": k, "max_rel_J": rel(sel.J[:k].cpu().numpy(), Jo),
+                             "T_star_identical": int((sel.T_star[:k].cpu().numpy() == np.argmin(tot, 1) + 1).sum())}
+                    ex = api.propagator_all_Jt_aug_batched(A[:k], Bm[:k], Q[:k], Rinv[:k], z0[:k], QT[:k], 1, N, w_explicit=w[:k],
+                                                           mode=api.MODE_EXACT)
+                    first["exact_mode_bit_identical_to_oracle"] = bool(np.array_equal(ex.J.cpu().numpy(), Jo))
+                del A, Bm, Q, QT, Rinv, z0, w, sel
+                torch.cuda.empty_cache()
+            dt = max_over_ranks(dt_sum, dev)
+            rec = {"config": 5, "what": f"synthetic HOP-LQR d={d} m={m} N={N}", "batch": Btot, "tiles_per_rank": ntiles,
+                   "tile_instances": tile, "device_s": dt,
                    "solves_per_s": Btot / dt, "algorithmic_TFLOPs": Btot * f_alg(N, d, m) / dt / 1e12,
-                   "algorithmic_GBs_per_gpu": B * per / dt / 1e9, "hbm_frac_per_gpu": B * per / dt / 1e9 / hbm,
-                   "status_nonzero": int((sel.status != 0).sum())}
+                   "algorithmic_GBs_per_gpu": Bmine * per / dt / 1e9, "hbm_frac_per_gpu": Bmine * per / dt / 1e9 / hbm,
+                   "status_nonzero": nonzero}
             if rank == 0:
-                k = 64
-                Jo, sto = O.propagator_batch(A[:k].cpu().numpy(), Bm[:k].cpu().numpy(), Q[:k].cpu().numpy(), Rinv[:k].cpu().numpy(),
-                                             z0[:k].cpu().numpy(), QT[:k].cpu().numpy(), nthreads=os.cpu_count() or 1)
-                tot = Jo + w[:k].cpu().numpy()[:, None] * np.arange(1, N + 1)
-                rec["parity_vs_oracle"] = {"checked": k, "max_rel_J": rel(sel.J[:k].cpu().numpy(), Jo),
-                                           "T_star_identical": int((sel.T_star[:k].cpu().numpy() == np.argmin(tot, 1) + 1).sum())}
                 # and the reference's own generator (numpy default_rng per instance) on a few instances
                 Ar, Br, Qr, Rr, zr, wr, QTr = s2_batch(range(8), d, m, N)
                 Rir = np.stack([O.chol_inv(r) for r in Rr])
                 s8 = api.propagator_all_Jt_aug_batched(*(torch.as_tensor(x, device=dev) for x in (Ar, Br, Qr, Rir, zr, QTr)), 1, N,
-                                                       w_explicit=torch.as_tensor(wr, device=dev))
+                                                       w_explicit=torch.as_tensor(wr, device=dev), mode=api.MODE_FAST)
                 Jo8, _ = O.propagator_batch(Ar, Br, Qr, Rir, zr, QTr)
-                rec["parity_vs_oracle"]["max_rel_J_reference_generator"] = rel(s8.J.cpu().numpy(), Jo8)
+                first["max_rel_J_reference_generator"] = rel(s8.J.cpu().numpy(), Jo8)
+                rec["parity_vs_oracle"] = first
+                rec["cpu_bruteforce"] = _bruteforce_cpu_timing(d, m, N)
+                rec["speedup_vs_cpu_bruteforce_port_all_cores"] = rec["solves_per_s"] / rec["cpu_bruteforce"]["port_solves_per_s"]
             emit(rec)
-            del A, Bm, Q, QT, Rinv, z0, w, sel
-            torch.cuda.empty_cache()
 
 
 def main():

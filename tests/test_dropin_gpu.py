@@ -82,6 +82,35 @@ def test_reference_call_flow_single_instance(m, name, maker):
     assert sorted(res["timers"]) == ["backward", "forward", "linearize", "select"] and res["timers"]["select"] > 0
 
 
+@pytest.mark.parametrize("maker,T_ref,J_ref,n_ref", [
+    ("make_double_integrator", 25, 6.544382184867515, 3),            # /root/reference/plots/summary.csv:2  (DoubleIntegrator, propagator)
+    ("make_quadrotor", 51, 449.1438881199965, 9),                    # /root/reference/plots/summary.csv:11 (Quadrotor_Hover, propagator)
+])
+def test_legacy_monolith_reproduces_the_shipped_results(m, maker, T_ref, J_ref, n_ref):
+    """The only goldens the reference SHIPS: plots/summary.csv, written by ilqr_propagator.main() with central differences,
+    max_iter=20, lm_init=1e-3, S_window=10 (ilqr_propagator.py:776-780).  Through the legacy-name adapter: T*, n_iterations
+    = len(J_hist) identical, J* within 1e-9.  Deviation from the monolith, irrelevant here: in-kernel ladder of 8 tries instead
+    of 4 (neither case ever fails a Cholesky)."""
+    lp = m["ilqr_propagator"]
+    case = getattr(lp, maker)()
+    assert len(case) == 12                                                     # the monolith's 12-tuple (ilqr_propagator.py:668)
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx = case
+    res = lp.ilqr_timeopt(F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, method="propagator", max_iter=20, lm_init=1e-3,
+                          S_window=10, use_central_diff=True, wrap_idx=wrap_idx)
+    assert sorted(res) == ["J_curve", "J_hist", "T_hist", "T_star", "U", "X", "consistency_check", "timers"]
+    assert res["T_star"] == T_ref and len(res["J_hist"]) == n_ref
+    assert abs(res["J_hist"][-1] - J_ref) <= 1e-9 * J_ref
+    cc = res["consistency_check"]                                              # summary.csv: 4.3e-4 (DI), 7.9e-2 (Quadrotor)
+    assert 0.0 < cc["max_abs_diff"] < (1e-2 if T_ref == 25 else 1.0) and cc["rmse"] <= cc["max_abs_diff"]
+    assert res["J_curve"].shape == (T_max,)
+    # stand-alone linear algebra with the monolith's defaults: 4 tries, then the plain inverse of A + 1e-5 I (the modular
+    # 8-try ladder would end at A + 0.1 I): checked against the monolith's own output for diag(1, -1, 1)
+    Ainv = lp.chol_inv(np.diag([1.0, -1.0, 1.0]))
+    assert np.allclose(np.diag(Ainv), [1.0 / (1.0 + 1e-5), 1.0 / (-1.0 + 1e-5), 1.0 / (1.0 + 1e-5)], rtol=1e-12)
+    with pytest.raises(np.linalg.LinAlgError):
+        lp.chol_solve(-np.eye(3), np.ones(3))
+
+
 def test_run_suite_cli_writes_the_reference_csv_schema(m, tmp_path):
     env = dict(os.environ, PYTHONHASHSEED="0")
     out = tmp_path / "res"

@@ -268,6 +268,10 @@ int hop_cost_f64(int B, int N, int n, int m, const double* X, const double* U, c
                  const int* T_star, double* J_out, void* stream) {
     if (int rc = need_device()) return rc;
     if (B <= 0) return B == 0 ? 0 : HOP_E_BADARG;
+    if (N < 1 || !X || !U || !xg || !w || !u_ref || !Q || !R || !Qf || !T_star || !J_out) {
+        set_last_error("hop_cost_f64: null pointer or N < 1");
+        return HOP_E_BADARG;
+    }
     DdpConst c{xg, w, u_ref, Q, R, Qf, wrap_mask};
     return dispatch_cost(n, m, B, N, X, U, c, T_star, J_out, (cudaStream_t)stream);
 }
@@ -290,6 +294,11 @@ int hop_backward_linesearch_f64(int B, int sys, const double* params_host, int N
                                 double* U_new, double* J_new, int* accepted, void* stream) {
     if (int rc = need_device()) return rc;
     if (B <= 0) return B == 0 ? 0 : HOP_E_BADARG;
+    if (N < 1 || !params_host || !A || !Bm || !X || !U || !xg || !w || !u_ref || !Q || !R || !Qf || !T_star || !lm || !k_out ||
+        !K_out || !ok_out || !err_out || !X_new || !U_new || !J_new || !accepted) {
+        set_last_error("hop_backward_linesearch_f64: null pointer or N < 1");
+        return HOP_E_BADARG;
+    }
     DdpConst c{xg, w, u_ref, Q, R, Qf, wrap_mask};
     return dispatch_backward_linesearch(sys, B, params_host, N, A, Bm, X, U, c, T_star, lm, nullptr, k_out, K_out, ok_out,
                                         err_out, X_new, U_new, J_new, accepted, nullptr, (cudaStream_t)stream);
@@ -301,6 +310,11 @@ int hop_linesearch_f64(int B, int sys, const double* params_host, int N, const d
                        double* X_new, double* U_new, double* J_new, int* accepted, void* stream) {
     if (int rc = need_device()) return rc;
     if (B <= 0) return B == 0 ? 0 : HOP_E_BADARG;
+    if (N < 1 || !params_host || !X || !U || !xg || !w || !u_ref || !Q || !R || !Qf || !T_star || !k_list || !K_list || !X_new ||
+        !U_new || !J_new || !accepted) {
+        set_last_error("hop_linesearch_f64: null pointer or N < 1");
+        return HOP_E_BADARG;
+    }
     DdpConst c{xg, w, u_ref, Q, R, Qf, wrap_mask};
     return dispatch_linesearch(sys, B, params_host, N, X, U, c, T_star, k_list, K_list, ok, X_new, U_new, J_new, accepted,
                                (cudaStream_t)stream);
@@ -511,22 +525,41 @@ int hop_probe_fp64_tflops(int iters, double* tflops_out, double* ms_out) {
 }
 
 // ---- host-buffer variant ------------------------------------------------------------------------
-// The batch is cut into up to four chunks that alternate between two streams: while chunk c runs its three kernels,
-// the J(T) block of chunk c-1 (the bulk of the device -> host traffic, 8 T_max bytes per instance) drains over PCIe
-// and the inputs of chunk c+1 arrive, so only the first upload and the last download are exposed.  It also bounds
-// the linearisation workspace (A, B: 1.7 KB per instance and step) to two chunks instead of the whole batch.
+// The batch is cut into chunks.  Three streams: two alternating "lane" streams carry a chunk's uploads, its selection
+// kernel and its downloads; one HIGH-PRIORITY stream carries the rollout + finite-difference kernels of every chunk.  Those
+// two kernels are HBM-bound (they write the 1.7 KB-per-step linearisation), the selection kernel is FP64-bound: with the
+// higher priority the blocks of chunk c+1's rollout / linearisation are dispatched as soon as SM slots free up and run
+// UNDER chunk c's selection instead of in front of it, so per call only the first chunk's preparation, the selections and
+// the last chunk's download are exposed.  The J(T) block of chunk c-1 (8 T_max bytes per instance, the bulk of the
+// device -> host traffic) drains over PCIe meanwhile.  Two linearisation workspaces (A, B: 1.7 KB per instance and step).
 namespace {
+constexpr int kHostChunksCap = 16;
 struct HostCtx {
     std::mutex mu;
     cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaStream_t pre = nullptr;                       // high priority: rollout + linearisation
     cudaEvent_t consts_ready = nullptr;
+    cudaEvent_t up[kHostChunksCap] = {}, prep[kHostChunksCap] = {}, sel[kHostChunksCap] = {};
     void* buf = nullptr;
     size_t cap = 0;
     int device = -1;
+    void reset() {
+        if (buf) cudaFree(buf);
+        for (auto& st : stream) { if (st) cudaStreamDestroy(st); st = nullptr; }
+        if (pre) cudaStreamDestroy(pre);
+        if (consts_ready) cudaEventDestroy(consts_ready);
+        for (int i = 0; i < kHostChunksCap; ++i) {
+            if (up[i]) cudaEventDestroy(up[i]);
+            if (prep[i]) cudaEventDestroy(prep[i]);
+            if (sel[i]) cudaEventDestroy(sel[i]);
+            up[i] = prep[i] = sel[i] = nullptr;
+        }
+        buf = nullptr; cap = 0; pre = nullptr; consts_ready = nullptr;
+    }
 };
 HostCtx g_host;
-constexpr int kHostChunkMin = 16384;   // instances: below this a chunk no longer fills the machine for several waves
-constexpr int kHostChunksMax = 4;
+constexpr int kHostChunkMin = 8192;    // instances: below this a chunk no longer fills the machine for several waves
+constexpr int kHostChunksMax = 8;
 }  // namespace
 
 int hop_select_from_x0_host_f64(int B, int sys, const double* params_host, int N, int T_min, int T_max,
@@ -541,21 +574,28 @@ int hop_select_from_x0_host_f64(int B, int sys, const double* params_host, int N
     std::lock_guard<std::mutex> lock(g_host.mu);
     int dev = 0;
     cudaGetDevice(&dev);
-    if (g_host.device != dev) {   // one cached arena per process; re-created when the current device changes
-        if (g_host.buf) cudaFree(g_host.buf);
-        for (auto& st : g_host.stream) { if (st) cudaStreamDestroy(st); st = nullptr; }
-        if (g_host.consts_ready) cudaEventDestroy(g_host.consts_ready);
-        g_host.buf = nullptr; g_host.cap = 0; g_host.consts_ready = nullptr; g_host.device = dev;
+    if (g_host.device != dev) {   // one cached context per process; re-created when the current device changes
+        g_host.reset();
+        g_host.device = dev;
     }
     for (auto& st : g_host.stream)
         if (!st) { if (int rc = report_cuda(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate")) return rc; }
+    if (!g_host.pre) {
+        int lo = 0, hi = 0;                                                      // (numerically lower = higher priority)
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (int rc = report_cuda(cudaStreamCreateWithPriority(&g_host.pre, cudaStreamNonBlocking, hi), "cudaStreamCreateWithPriority")) return rc;
+    }
     if (!g_host.consts_ready) {
         if (int rc = report_cuda(cudaEventCreateWithFlags(&g_host.consts_ready, cudaEventDisableTiming), "cudaEventCreate")) return rc;
+        for (int i = 0; i < kHostChunksCap; ++i)
+            for (cudaEvent_t* e : {&g_host.up[i], &g_host.prep[i], &g_host.sel[i]})
+                if (int rc = report_cuda(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "cudaEventCreate")) return rc;
     }
     static const int chunks_max = getenv("HOP_HOST_CHUNKS") ? atoi(getenv("HOP_HOST_CHUNKS")) : kHostChunksMax;   // A/B switch
     int chunks = (B + kHostChunkMin - 1) / kHostChunkMin;
     chunks = chunks < 1 ? 1 : (chunks > chunks_max ? chunks_max : chunks);
     if (chunks < 1) chunks = 1;
+    if (chunks > kHostChunksCap) chunks = kHostChunksCap;
     const int per = (((B + chunks - 1) / chunks) + 3) & ~3;       // whole CTAs of the selection kernel
     const int lanes = chunks > 1 ? 2 : 1;                         // workspaces (= streams) in use
     const bool shared_U = (u_batch_stride == 0);
@@ -596,10 +636,14 @@ int hop_select_from_x0_host_f64(int B, int sys, const double* params_host, int N
     if (shared_U) copy(d_U, U, sizeof(double) * nU, cudaMemcpyHostToDevice, s0, "H2D U");
     if (rc == 0) rc = report_cuda(cudaEventRecord(g_host.consts_ready, s0), "cudaEventRecord");
     if (rc == 0 && lanes > 1) rc = report_cuda(cudaStreamWaitEvent(g_host.stream[1], g_host.consts_ready, 0), "cudaStreamWaitEvent");
+    if (rc == 0) rc = report_cuda(cudaStreamWaitEvent(g_host.pre, g_host.consts_ready, 0), "cudaStreamWaitEvent");
+    static const bool serial_prep = getenv("HOP_HOST_SERIAL_PREP") && atoi(getenv("HOP_HOST_SERIAL_PREP")) != 0;   // A/B switch
     for (int c = 0; c < chunks && rc == 0; ++c) {
         const int b0 = c * per, cb = (B - b0) < per ? (B - b0) : per;
         if (cb <= 0) break;
-        cudaStream_t st = g_host.stream[c % lanes];
+        const int lane = c % lanes;
+        cudaStream_t st = g_host.stream[lane];
+        cudaStream_t sp = serial_prep ? st : g_host.pre;
         const size_t o = (size_t)b0;
         copy(d_x0 + o * n, x0 + o * n, sizeof(double) * (size_t)cb * n, cudaMemcpyHostToDevice, st, "H2D x0");
         copy(d_xg + o * n, xg + o * n, sizeof(double) * (size_t)cb * n, cudaMemcpyHostToDevice, st, "H2D xg");
@@ -610,19 +654,39 @@ int hop_select_from_x0_host_f64(int B, int sys, const double* params_host, int N
             dU = d_U + o * N * m;
         }
         if (rc) break;
-        rc = hop_select_from_x0_f64(cb, sys, params_host, N, T_min, T_max, d_x0 + o * n, dU, u_batch_stride, d_xg + o * n,
-                                    d_w + o, d_uref, d_Q, d_R, d_Qf, wrap_mask, central, mode, d_ws + (c % lanes) * s_ws, s_ws,
-                                    d_J + o * T_max, d_T + o, d_Js + o, d_st + o, st);
+        // workspace of this lane: X | A | Bm (hop_select_from_x0_workspace_bytes layout)
+        char* wsl = d_ws + lane * s_ws;
+        double* Xc = (double*)wsl;
+        double* Ac = (double*)(wsl + align256(sizeof(double) * (size_t)per * (N + 1) * n));
+        double* Bc = (double*)((char*)Ac + align256(sizeof(double) * (size_t)per * N * n * n));
+        if (!serial_prep) {
+            if ((rc = report_cuda(cudaEventRecord(g_host.up[c], st), "cudaEventRecord"))) break;
+            if ((rc = report_cuda(cudaStreamWaitEvent(sp, g_host.up[c], 0), "cudaStreamWaitEvent"))) break;
+            if (c >= lanes && (rc = report_cuda(cudaStreamWaitEvent(sp, g_host.sel[c - lanes], 0), "cudaStreamWaitEvent"))) break;   // workspace re-use
+        }
+        if ((rc = dispatch_rollout(cb, sys, params_host, N, d_x0 + o * n, dU, u_batch_stride, 1e6, Xc, sp))) break;         // solver.py:42
+        // X comes from the rollout above, so F(X_k, U_k) = X[k+1] bit for bit: the linearisation may read f0 from it
+        if ((rc = dispatch_linearize(cb, sys, params_host, N, Xc, dU, u_batch_stride, central, 1e-5, 1e-5, 1e-6, 1e-6, 1, nullptr,
+                                     Ac, Bc, sp))) break;                                                                  // linearization.py:177,216
+        if (!serial_prep) {
+            if ((rc = report_cuda(cudaEventRecord(g_host.prep[c], sp), "cudaEventRecord"))) break;
+            if ((rc = report_cuda(cudaStreamWaitEvent(st, g_host.prep[c], 0), "cudaStreamWaitEvent"))) break;
+        }
+        // a_resid = NULL: on a trajectory produced by the rollout above F(X_k,U_k) - X_{k+1} is exactly 0
+        rc = hop_select_fused_f64(cb, N, n, m, T_min, T_max, Ac, Bc, nullptr, Xc, dU, u_batch_stride, d_xg + o * n, d_w + o, d_uref,
+                                  d_Q, d_R, d_Qf, wrap_mask, 1e-9, 1e-12, mode, d_J + o * T_max, d_T + o, d_Js + o, d_st + o, st);
         if (rc) break;
+        if ((rc = report_cuda(cudaEventRecord(g_host.sel[c], st), "cudaEventRecord"))) break;
         if (J_out) copy(J_out + o * T_max, d_J + o * T_max, sizeof(double) * (size_t)cb * T_max, cudaMemcpyDeviceToHost, st, "D2H J");
         copy(Tstar_out + o, d_T + o, sizeof(int) * (size_t)cb, cudaMemcpyDeviceToHost, st, "D2H T*");
         if (Jstar_out) copy(Jstar_out + o, d_Js + o, sizeof(double) * (size_t)cb, cudaMemcpyDeviceToHost, st, "D2H J*");
         if (status) copy(status + o, d_st + o, sizeof(int) * (size_t)cb, cudaMemcpyDeviceToHost, st, "D2H status");
     }
+    cudaError_t ep = cudaStreamSynchronize(g_host.pre);
     cudaError_t e0 = cudaStreamSynchronize(g_host.stream[0]);
     cudaError_t e1 = lanes > 1 ? cudaStreamSynchronize(g_host.stream[1]) : cudaSuccess;
     if (rc) return rc;
-    return report_cuda(e0 != cudaSuccess ? e0 : e1, "hop_select_from_x0_host_f64");
+    return report_cuda(e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : ep), "hop_select_from_x0_host_f64");
 }
 
 }  // extern "C"

@@ -33,12 +33,19 @@ __device__ __forceinline__ ddp::CostConst cost_const(const DdpConst& c, int b) {
     return cc;
 }
 
+// per-instance horizon of the stand-alone entry points: a caller's T_star[b] > N is clamped to N (the trajectories hold N
+// steps); T_star[b] <= 0 is handled as the reference does (cost = inf, solver.py:71; backward pass: ok = False)
+__device__ __forceinline__ int horizon_of(const int* T, int b, int N) {
+    const int t = T[b];
+    return t > N ? N : t;
+}
+
 template <int n, int m>
 __global__ void k_cost(int B, int N, const double* X, const double* U, DdpConst c, const int* T, double* J) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const ddp::CostConst cc = cost_const<n>(c, b);
-    J[b] = ddp::cost_timeopt_true<n, m>(X + (size_t)b * (N + 1) * n, U + (size_t)b * N * m, cc, T[b]);
+    J[b] = ddp::cost_timeopt_true<n, m>(X + (size_t)b * (N + 1) * n, U + (size_t)b * N * m, cc, horizon_of(T, b, N));
 }
 
 template <int n, int m>
@@ -51,7 +58,7 @@ __global__ void k_backward(int B, int N, const double* A, const double* Bm, cons
     const ddp::CostConst cc = cost_const<n>(c, b);
     int okb = 0;
     const int rc = ddp::backward_pass<n, m>(A + (size_t)b * N * n * n, Bm + (size_t)b * N * n * m, X + (size_t)b * (N + 1) * n,
-                                            U + (size_t)b * N * m, cc, T[b], lm[b], k_out + (size_t)b * N * m,
+                                            U + (size_t)b * N * m, cc, horizon_of(T, b, N), lm[b], k_out + (size_t)b * N * m,
                                             K_out + (size_t)b * N * m * n, &okb);
     ok[b] = (rc == 0) ? okb : 0;
     if (err) err[b] = rc;
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(kBwWarps * 32) k_backward_warp(int B, int N, c
     const ddp::CostConst cc = cost_const<n>(c, b);
     int okb = 0;
     const int rc = ddp::backward_pass_warp<n, m>(A + (size_t)b * N * n * n, Bm + (size_t)b * N * n * m, X + (size_t)b * (N + 1) * n,
-                                                 U + (size_t)b * N * m, cc, T[b], lm[b], k_out + (size_t)b * N * m,
+                                                 U + (size_t)b * N * m, cc, horizon_of(T, b, N), lm[b], k_out + (size_t)b * N * m,
                                                  K_out + (size_t)b * N * m * n, &okb, smem + (size_t)warp * ddp::BwSmem<n, m>::SIZE, lane);
     if (lane == 0) {
         ok[b] = (rc == 0) ? okb : 0;
@@ -127,7 +134,7 @@ __global__ void k_linesearch(int B, DynParams2 prm, int N, const double* X, cons
     const ddp::CostConst cc = cost_const<n>(c, b);
     double J = 0.0;
     int a = 0;
-    ddp::forward_linesearch<SYS>(prm.p, N, X + (size_t)b * (N + 1) * n, U + (size_t)b * N * m, cc, T[b],
+    ddp::forward_linesearch<SYS>(prm.p, N, X + (size_t)b * (N + 1) * n, U + (size_t)b * N * m, cc, horizon_of(T, b, N),
                                  k_list + (size_t)b * N * m, K_list + (size_t)b * N * m * n, Xn + (size_t)b * (N + 1) * n,
                                  Un + (size_t)b * N * m, &J, &a);
     Jn[b] = J;
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(kLsRoles * 32) k_linesearch_par(int B, DynPara
     const double* Kb = K_list + (size_t)b * N * m * n;
     double* Xnb = Xn + (size_t)b * (N + 1) * n;
     double* Unb = Un + (size_t)b * N * m;
-    const int Tb = T[b];
+    const int Tb = horizon_of(T, b, N);
     const double alpha = role == 0 ? 1.0 : role == 1 ? 0.5 : role == 2 ? 0.25 : role == 3 ? 0.1 : 0.05;
     double J = HUGE_VAL;
     bool cand_ok = false;

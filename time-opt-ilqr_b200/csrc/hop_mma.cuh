@@ -122,7 +122,7 @@ HOP_DEVICE bool gj_attempt(Mat& a, const LaneGeo& L) {
         const int Ij = j >> 3, gj = rho_inv(j & 7);             // pivot row: tile row Ij, lanes (gj, *)
         const int Jj = j >> 3, tj = j & 3, sj = (j & 7) >> 2;   // pivot column: tile col Jj, lanes (*, tj), slot sj
         const double p = simt::shfl(a.v[Ij][Jj][sj], (gj << 2) | tj, 32);
-        ok = ok && (p > 0.0);
+        ok = ok && (p > 0.0) && (p <= 1.7976931348623157e308);   // +Inf is non-finite input (utils.py:75), not a pivot
         const double rinv = pivot_rcp(p);
         double pr[2][2], f[2];
 #pragma unroll

@@ -134,7 +134,7 @@ HOP_DEVICE bool gj_attempt(double (&a)[D], int r, double* rowbuf) {
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         const double p = simt::shfl(a[j], j, G);
-        ok = ok && (p > 0.0);
+        ok = ok && (p > 0.0) && (p <= 1.7976931348623157e308);   // +Inf is non-finite input (utils.py:75), not a pivot
         const double rinv = 1.0 / p;
         double* rb = rowbuf + (j & 1) * DP;
         const bool piv = (r == j);

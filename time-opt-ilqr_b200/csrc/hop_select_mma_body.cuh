@@ -208,7 +208,7 @@ HOP_DEVICE double last_pivot(const Mat& S, double eps, const LaneGeo& L, bool& o
     for (int j = 0; j < D; ++j) {
         const int Ij = j >> 3, gj = rho_inv(j & 7), Jj = j >> 3, tj = j & 3, sj = (j & 7) >> 2;
         p = simt::shfl(a.v[Ij][Jj][sj], (gj << 2) | tj, 32);
-        ok = ok && (p > 0.0);
+        ok = ok && (p > 0.0) && (p <= 1.7976931348623157e308);   // +Inf is non-finite input (utils.py:75), not a pivot
         if (j == D - 1) break;
         const double rinv = pivot_rcp(p);
         // rows/cols <= j are dead from here on: once j >= 8 only tile (1,1) is live
