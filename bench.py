@@ -375,8 +375,8 @@ def run_hop(args):
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "hop.api.select_horizon_host -> hop_select_from_x0_host_f64 (pinned host x0; rollout + "
-                           "forward-FD linearisation + fused selection on device, in up to eight chunks: copies and selections on two alternating streams, the HBM-bound rollout / linearisation of the next chunk on a high-priority stream under the FP64-bound selection of the current one; J(T), T*, J*, status back to host)"},
-            "gpu_launches": args.steps, "gpu_launches_e2e": 3 * args.steps * min(8, max(1, -(-B // 8192))),   # e2e: rollout + linearise + select per chunk (hop_cabi.cu: kHostChunkMin / kHostChunksMax)
+                           "forward-FD linearisation + fused selection on device, in up to four chunks on two streams so that copies overlap kernels; J(T), T*, J*, status back to host)"},
+            "gpu_launches": args.steps, "gpu_launches_e2e": 3 * args.steps * min(4, max(1, -(-B // 16384))),   # e2e: rollout + linearise + select per chunk (hop_cabi.cu: kHostChunkMin / kHostChunksMax)
             "roofline": roofline, "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -197,7 +197,8 @@ int hop_linesearch_f64(int B, int sys, const double *params_host, int N, const d
  *   (low byte != 0: the reference would have raised -> run_suite "crash"), *iters_run_host (host int, may be NULL),
  *   timers_host (host double[4] or NULL): device seconds spent in linearize / select / backward / forward, the
  *   keys of the reference's `timers` dict (solver.py:497).
- *   The call synchronises the stream once per outer iteration (early exit when every instance stopped). */
+ *   The call returns after the stream has drained.  Inside, the host never waits for the device between outer iterations:
+ *   the early exit (every instance stopped) is decided one iteration late on an asynchronously copied counter. */
 unsigned long long hop_ilqr_workspace_bytes(int B, int N, int n, int m);
 int hop_ilqr_timeopt_f64(int B, int sys, const double *params_host, int N, int T_min, int T_max, const double *x0,
                          const double *U_init, const double *xg, const double *w, const double *u_ref, const double *Q,

@@ -20,19 +20,38 @@ def stale(target, deps):
     return not os.path.exists(target) or any(os.path.getmtime(d) > os.path.getmtime(target) for d in deps)
 
 
+def includes_of(path, seen=None):
+    """Transitive closure of the quoted #include files of `path` (the per-object dependency list)."""
+    import re
+    seen = set() if seen is None else seen
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    with open(path) as fh:
+        for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', fh.read(), flags=re.M):
+            includes_of(os.path.normpath(os.path.join(os.path.dirname(path), inc)), seen)
+    return seen
+
+
 def build(force=False, verbose=False):
     deps = [os.path.join(HERE, f) for f in SRCS + HDRS]
     if not (force or stale(OUT, deps)):
         return OUT
-    objs = []
 
     def compile_one(src):
         obj = os.path.join(HERE, src.replace(".cu", OBJ_TAG + ".o"))
+        flags_tag = obj + ".flags"
+        flags_now = " ".join(FLAGS)
+        same_flags = os.path.exists(flags_tag) and open(flags_tag).read() == flags_now
+        if not force and same_flags and not stale(obj, sorted(includes_of(os.path.join(HERE, src)))):
+            return obj                                   # object newer than its source and every header it includes
         r = subprocess.run([NVCC, *FLAGS, "-c", os.path.join(HERE, src), "-o", obj], capture_output=True, text=True)
         with open(obj + ".ptxas.log", "w") as fh:
             fh.write(r.stderr)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stderr}")
+        with open(flags_tag, "w") as fh:
+            fh.write(flags_now)
         if verbose:
             print(r.stderr)
         return obj

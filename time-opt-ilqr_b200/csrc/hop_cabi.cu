@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "hop_common.cuh"
 #include "hop_select_body.cuh"
@@ -388,20 +389,29 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T
                     wrap_mask, 1e-9, 1e-12, mode, skip, J_curve, ws.T_sel, ws.Jstar, ws.sel_status};
         return dispatch_select_fused(n, m, p, st);
     };
-    // optional per-phase device timing (the reference's timers dict: linearize / select / backward / forward)
+    // optional per-phase device timing (the reference's timers dict: linearize / select / backward / forward): five events per
+    // outer iteration, all read after the loop -- nothing here makes the host wait for the device
+    const int n_sets = max_iter + 1;
     struct Events {   // destroyed on every exit path
-        cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-        ~Events() { for (auto& x : e) if (x) cudaEventDestroy(x); }
+        std::vector<cudaEvent_t> e;
+        cudaEvent_t done[2] = {nullptr, nullptr};
+        ~Events() {
+            for (auto& x : e) if (x) cudaEventDestroy(x);
+            for (auto& x : done) if (x) cudaEventDestroy(x);
+        }
     } evs;
-    cudaEvent_t* ev = evs.e;
     double tsum[4] = {0.0, 0.0, 0.0, 0.0};
-    if (timers_host) for (auto& e : evs.e) HOP_TRY(report_cuda(cudaEventCreate(&e), "cudaEventCreate"));
-    auto mark = [&](int i) { if (timers_host) cudaEventRecord(ev[i], st); };
-    auto collect = [&]() {
-        if (!timers_host) return;
-        cudaEventSynchronize(ev[4]);
-        for (int i = 0; i < 4; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); tsum[i] += 1e-3 * ms; }
-    };
+    if (timers_host) {
+        evs.e.assign((size_t)5 * n_sets, nullptr);
+        for (auto& e : evs.e) HOP_TRY(report_cuda(cudaEventCreate(&e), "cudaEventCreate"));
+    }
+    for (auto& e : evs.done) HOP_TRY(report_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate"));
+    int set = 0;                                                                     // event set of the current iteration
+    auto ev = [&](int i) { return evs.e[(size_t)5 * set + i]; };
+    auto mark = [&](int i) { if (timers_host) cudaEventRecord(ev(i), st); };
+    // pinned landing zone of the per-iteration "instances still active" counter (one per host thread, kept for the process)
+    static thread_local int* h_active = nullptr;
+    if (!h_active) HOP_TRY(report_cuda(cudaHostAlloc((void**)&h_active, 2 * sizeof(int), cudaHostAllocDefault), "cudaHostAlloc"));
     HOP_TRY(launch_init_state(B, lm_init, ws.lm, ws.done, n_hist, status, st));
     if (U_init) HOP_TRY(report_cuda(cudaMemcpyAsync(U, U_init, sizeof(double) * (size_t)B * N * m, cudaMemcpyDeviceToDevice, st), "copy U_init"));
     else HOP_TRY(launch_tile_u(B, N, m, u_ref, U, st));                                                  // solver.py:480-481
@@ -413,15 +423,19 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T
     HOP_TRY(launch_after_select(B, ws.sel_status, ws.done, status, st));
     mark(2);
     HOP_TRY(dispatch_backward_linesearch(sys, B, params_host, N, ws.A, ws.Bm, X, U, c, ws.T_sel, ws.lm, ws.done, ws.kl, ws.Kl,
-                                         ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, ev[3], st));     // :541-551
+                                         ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, timers_host ? ev(3) : nullptr, st));   // :541-551
     HOP_TRY(launch_warm_update(B, cap, ws.T_sel, ws.ok, ws.acc, ws.Jn, ws.bw_err, ws.done, ws.T_bar, J_hist, T_hist, n_hist,
                                ws.copy, status, st));
     HOP_TRY(launch_copy_accepted(B, (size_t)(N + 1) * n, (size_t)N * m, ws.copy, ws.Xn, ws.Un, X, U, st));
     mark(4);
-    collect();
-    int iters = 0;
+    // Outer loop (:564).  The early exit ("every instance has stopped") is decided ONE ITERATION LATE: iteration `it` is
+    // enqueued before the host looks at the counter of iteration it - 1, so the stream never drains while the host waits.
+    // When that counter is zero the already enqueued iteration finds every instance done and changes nothing.
+    int iters = 0, enqueued = 0;
     for (int it = 0; it < max_iter; ++it) {                                                              // :564
-        ++iters;
+        const int slot = it & 1;
+        set = it + 1;
+        ++enqueued;
         mark(0);
         HOP_TRY(dispatch_linearize(B, sys, params_host, N, X, U, ustride, central, 1e-5, 1e-5, 1e-6, 1e-6, 1, ws.done, ws.A, ws.Bm, st));
         mark(1);
@@ -429,18 +443,28 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T
         HOP_TRY(launch_after_select(B, ws.sel_status, ws.done, status, st));
         mark(2);
         HOP_TRY(dispatch_backward_linesearch(sys, B, params_host, N, ws.A, ws.Bm, X, U, c, ws.T_sel, ws.lm, ws.done, ws.kl,
-                                             ws.Kl, ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, ev[3], st)); // :594-604
-        HOP_TRY(report_cuda(cudaMemsetAsync(ws.n_active, 0, sizeof(int), st), "memset n_active"));
+                                             ws.Kl, ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, timers_host ? ev(3) : nullptr, st)); // :594-604
+        HOP_TRY(report_cuda(cudaMemsetAsync(ws.n_active + slot, 0, sizeof(int), st), "memset n_active"));
         HOP_TRY(launch_ddp_update(B, cap, ws.T_sel, ws.ok, ws.acc, ws.Jn, ws.bw_err, ws.done, ws.T_bar, ws.lm, J_hist, T_hist,
-                                  n_hist, ws.copy, status, ws.n_active, st));                             // :735-748
+                                  n_hist, ws.copy, status, ws.n_active + slot, st));                      // :735-748
         HOP_TRY(launch_copy_accepted(B, (size_t)(N + 1) * n, (size_t)N * m, ws.copy, ws.Xn, ws.Un, X, U, st));
         mark(4);
-        int active = 0;
-        HOP_TRY(report_cuda(cudaMemcpyAsync(&active, ws.n_active, sizeof(int), cudaMemcpyDeviceToHost, st), "read n_active"));
-        HOP_TRY(report_cuda(cudaStreamSynchronize(st), "hop_ilqr_timeopt_f64"));
-        collect();
-        if (active == 0) break;
+        HOP_TRY(report_cuda(cudaMemcpyAsync(h_active + slot, ws.n_active + slot, sizeof(int), cudaMemcpyDeviceToHost, st), "read n_active"));
+        HOP_TRY(report_cuda(cudaEventRecord(evs.done[slot], st), "cudaEventRecord"));
+        iters = it + 1;
+        if (it >= 1) {                                                                                   // look at iteration it - 1
+            HOP_TRY(report_cuda(cudaEventSynchronize(evs.done[slot ^ 1]), "hop_ilqr_timeopt_f64"));
+            if (h_active[slot ^ 1] == 0) { iters = it; break; }
+        }
     }
+    HOP_TRY(report_cuda(cudaStreamSynchronize(st), "hop_ilqr_timeopt_f64"));
+    if (timers_host)
+        for (int q = 0; q <= enqueued; ++q)
+            for (int i = 0; i < 4; ++i) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, evs.e[(size_t)5 * q + i], evs.e[(size_t)5 * q + i + 1]);
+                tsum[i] += 1e-3 * ms;
+            }
     HOP_TRY(launch_finalize(B, cap, n_hist, T_hist, ws.T_bar, T_star, st));
 #undef HOP_TRY
     if (iters_run_host) *iters_run_host = iters;
@@ -525,13 +549,15 @@ int hop_probe_fp64_tflops(int iters, double* tflops_out, double* ms_out) {
 }
 
 // ---- host-buffer variant ------------------------------------------------------------------------
-// The batch is cut into chunks.  Three streams: two alternating "lane" streams carry a chunk's uploads, its selection
-// kernel and its downloads; one HIGH-PRIORITY stream carries the rollout + finite-difference kernels of every chunk.  Those
-// two kernels are HBM-bound (they write the 1.7 KB-per-step linearisation), the selection kernel is FP64-bound: with the
-// higher priority the blocks of chunk c+1's rollout / linearisation are dispatched as soon as SM slots free up and run
-// UNDER chunk c's selection instead of in front of it, so per call only the first chunk's preparation, the selections and
-// the last chunk's download are exposed.  The J(T) block of chunk c-1 (8 T_max bytes per instance, the bulk of the
-// device -> host traffic) drains over PCIe meanwhile.  Two linearisation workspaces (A, B: 1.7 KB per instance and step).
+// The batch is cut into up to four chunks that alternate between two streams: while chunk c runs its three kernels,
+// the J(T) block of chunk c-1 (the bulk of the device -> host traffic, 8 T_max bytes per instance) drains over PCIe
+// and the inputs of chunk c+1 arrive, so only the first upload and the last download are exposed.  It also bounds
+// the linearisation workspace (A, B: 1.7 KB per instance and step) to two chunks instead of the whole batch.
+// Measured (profiles/r2_experiments.txt): one step = 44.3 ms against 43.7 ms of kernels (selection 39.4 + linearisation 3.6 +
+// rollout 0.74).  HOP_HOST_PRIO_PREP=1 moves the HBM-bound rollout / linearisation of every chunk to a HIGH-PRIORITY
+// stream so that they could run under the FP64-bound selection of the previous chunk; on B200 that bought nothing
+// (44.7 ms with 8 chunks, 44.5 ms with 4: the selection kernel holds every SM's register file, a freed slot goes to a
+// linearisation block and the displaced selection work returns later), so it stays an opt-in A/B switch.
 namespace {
 constexpr int kHostChunksCap = 16;
 struct HostCtx {
@@ -558,8 +584,8 @@ struct HostCtx {
     }
 };
 HostCtx g_host;
-constexpr int kHostChunkMin = 8192;    // instances: below this a chunk no longer fills the machine for several waves
-constexpr int kHostChunksMax = 8;
+constexpr int kHostChunkMin = 16384;   // instances: below this a chunk no longer fills the machine for several waves
+constexpr int kHostChunksMax = 4;
 }  // namespace
 
 int hop_select_from_x0_host_f64(int B, int sys, const double* params_host, int N, int T_min, int T_max,
@@ -637,7 +663,7 @@ int hop_select_from_x0_host_f64(int B, int sys, const double* params_host, int N
     if (rc == 0) rc = report_cuda(cudaEventRecord(g_host.consts_ready, s0), "cudaEventRecord");
     if (rc == 0 && lanes > 1) rc = report_cuda(cudaStreamWaitEvent(g_host.stream[1], g_host.consts_ready, 0), "cudaStreamWaitEvent");
     if (rc == 0) rc = report_cuda(cudaStreamWaitEvent(g_host.pre, g_host.consts_ready, 0), "cudaStreamWaitEvent");
-    static const bool serial_prep = getenv("HOP_HOST_SERIAL_PREP") && atoi(getenv("HOP_HOST_SERIAL_PREP")) != 0;   // A/B switch
+    static const bool serial_prep = !(getenv("HOP_HOST_PRIO_PREP") && atoi(getenv("HOP_HOST_PRIO_PREP")) != 0);   // A/B switch (default: serial)
     for (int c = 0; c < chunks && rc == 0; ++c) {
         const int b0 = c * per, cb = (B - b0) < per ? (B - b0) : per;
         if (cb <= 0) break;

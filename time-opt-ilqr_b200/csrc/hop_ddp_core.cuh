@@ -238,7 +238,8 @@ struct BwSmem {   // doubles per warp
     static constexpr int VXX = 0, AK = VXX + n * n, BK = AK + n * n, ATV = BK + n * m, TT = ATV + n * n, QXX = TT + n * n,
                          BTV = QXX + n * n, QUX = BTV + m * n, KK = QUX + m * n, KTQ = KK + m * n, QUU = KTQ + n * m,
                          VX = QUU + m * m, QX = VX + n, VXN = QX + n, EV = VXN + n, QU = EV + n, KAP = QU + m, DU = KAP + m,
-                         SIZE = (DU + m + 1) & ~1;
+                         LXU = DU + m,                          // lx [n], lu [m] of the brute-force sweep
+                         SIZE = (LXU + n + m + 1) & ~1;
 };
 
 // chol_solve (utils.py:96-120) with the right-hand-side columns spread over the lanes: every lane factors the d x d
@@ -457,7 +458,7 @@ HOP_DEVICE int bruteforce_one_T_warp(const double* A, const double* Bm, const do
     double *Vxx = sm + S::VXX, *Ak = sm + S::AK, *Bk = sm + S::BK, *AtV = sm + S::ATV, *t = sm + S::TT, *Qxx = sm + S::QXX;
     double *BtV = sm + S::BTV, *Qux = sm + S::QUX, *iQux = sm + S::KK, *Quu = sm + S::QUU;
     double *Vx = sm + S::VX, *Qx = sm + S::QX, *Vxn = sm + S::VXN, *e = sm + S::EV, *Qu = sm + S::QU, *iQu = sm + S::KAP, *du = sm + S::DU;
-    double *lx = sm + S::KTQ, *lu = sm + S::KTQ + n;                            // (KtQuu is not needed here)
+    double *lx = sm + S::LXU, *lu = sm + S::LXU + n;   // (own slots: n + m doubles do not fit the n m slots of KTQ when m = 1)
     if (lane < n) {
         double v = sub(X[(size_t)T * n + lane], c.xg[lane]);
         if ((c.wrap_mask >> lane) & 1u) v = wrap_pi(v);

@@ -51,7 +51,7 @@ HOP_DEVICE R sub(R a, R b) { return add(a, -b); }   // a - b and a + (-b) round 
 // ---- slab layout (units of R) -------------------------------------------------------------------------------------
 struct Layout {
     int mat;                                                                      // doubles per d x d buffer (even)
-    int A, Q, E, F, G, EB, FB, GB, W, T1, T2, T3, XT, MB, LB;                      // d x d
+    int A, Q, E, F, G, EB, FB, GB, W, T1, T2, T3, XT, MB, LB;                      // d x d (T3 shares Q's buffer, XT shares F's)
     int BM, T4;                                                                   // d x m
     int RI;                                                                       // m x m
     int Z0, V0, V1, V2, V3;                                                       // vectors (kMaxD)
@@ -62,7 +62,9 @@ struct Layout {
         int o = 0;
         l.A = o; o += l.mat; l.Q = o; o += l.mat; l.E = o; o += l.mat; l.F = o; o += l.mat; l.G = o; o += l.mat;
         l.EB = o; o += l.mat; l.FB = o; o += l.mat; l.GB = o; o += l.mat; l.W = o; o += l.mat;
-        l.T1 = o; o += l.mat; l.T2 = o; o += l.mat; l.T3 = o; o += l.mat; l.XT = o; o += l.mat;
+        l.T1 = o; o += l.mat; l.T2 = o; o += l.mat;
+        l.T3 = l.Q;     // Q_k is dead once E_k = chol_inv(Q_k) exists; T3 is first written after that
+        l.XT = l.F;     // F_k is dead after the prefix update; the terminal block is staged there just before the query
         l.MB = o; o += l.mat; l.LB = o; o += l.mat;
         const int dm = (d * m + 1) & ~1;
         l.BM = o; o += dm; l.T4 = o; o += dm;
@@ -143,9 +145,12 @@ template <typename R>
 HOP_DEVICE void solve_factored_identity(int lane, int d, const R* L, R* Y, R* X) {
     if (lane < d) {
         const int c = lane;
-        for (int i = 0; i < d; ++i) {
+        // column c of the identity: Y[i][c] = +0 for i < c, and the terms p < c of the later rows subtract L[i][p] * (+0)
+        // = +-0 from s, which leaves every s (zero or not) unchanged bit for bit -- so those rows and terms are skipped
+        for (int i = 0; i < c; ++i) Y[i * d + c] = (R)0;
+        for (int i = c; i < d; ++i) {
             R s = (i == c) ? (R)1 : (R)0;
-            for (int p = 0; p < i; ++p) s = sub(s, mul(L[i * d + p], Y[p * d + c]));
+            for (int p = c; p < i; ++p) s = sub(s, mul(L[i * d + p], Y[p * d + c]));
             Y[i * d + c] = quo(s, L[i * d + i]);
         }
         for (int i = d - 1; i >= 0; --i) {
@@ -228,15 +233,18 @@ HOP_DEVICE int chol_inv(int lane, int d, const R* Ain, R* Xout, R* Mb, R* Lb, R 
     return ok ? ST_OK : ST_LINALG;
 }
 
-// ---- one step of the sweep on blocks already in the slab: stage k (horizon_selection.py:57-64), prefix k (:66-75), query
-// t = k + 1 (:77-86).  On entry s+L.A = A_k, s+L.BM = B_k, s+L.Q = Q_k, s+L.RI = R^-1, s+L.XT = QT_t (raw), s+L.Z0 = z0.
-// Returns the error code of the first failing chol_inv (the reference raises there) and J(t) in *J_out.
+// ---- one step of the sweep on blocks already in the slab, in two halves (the terminal block of the query is staged in a
+// buffer that is only free after the prefix update):
+//   stage_prefix_step: stage k (horizon_selection.py:57-64) + prefix k (:66-75); on entry s+L.A = A_k, s+L.BM = B_k,
+//                      s+L.Q = Q_k, s+L.RI = R^-1
+//   query_step       : query t = k + 1 (:77-86); on entry s+L.XT = QT_t (raw), s+L.Z0 = z0; J(t) in *J_out
+// Both return the error code of the first failing chol_inv (the reference raises there).
 template <typename R>
-HOP_DEVICE int sweep_step(int lane, int d, int m, int k, const Layout& L, R* s, R jitter, int max_tries, int& flags, R* J_out) {
+HOP_DEVICE int stage_prefix_step(int lane, int d, int m, int k, const Layout& L, R* s, R jitter, int max_tries, int& flags) {
     const int dd = d * d;
     R *A = s + L.A, *Q = s + L.Q, *E = s + L.E, *F = s + L.F, *G = s + L.G, *EB = s + L.EB, *FB = s + L.FB, *GB = s + L.GB;
-    R *W = s + L.W, *T1 = s + L.T1, *T2 = s + L.T2, *T3 = s + L.T3, *XT = s + L.XT, *MB = s + L.MB, *LB = s + L.LB;
-    R *BM = s + L.BM, *T4 = s + L.T4, *RI = s + L.RI, *Z0 = s + L.Z0, *V0 = s + L.V0;
+    R *W = s + L.W, *T1 = s + L.T1, *T2 = s + L.T2, *T3 = s + L.T3, *MB = s + L.MB, *LB = s + L.LB;
+    R *BM = s + L.BM, *T4 = s + L.T4, *RI = s + L.RI;
     // stage: E_k = chol_inv(Q_k); F_k = E_k A_k^T; G_k = sym((A_k E_k) A_k^T + (B_k R^-1) B_k^T)
     if (int rc = chol_inv(lane, d, Q, E, MB, LB, jitter, max_tries, flags)) return rc;
     mmt(lane, d, d, d, E, A, F);
@@ -244,7 +252,7 @@ HOP_DEVICE int sweep_step(int lane, int d, int m, int k, const Layout& L, R* s, 
     mm(lane, d, m, m, BM, RI, T4);
     simt::sync();
     mmt(lane, d, d, d, T1, A, T2);
-    mmt(lane, d, m, d, T4, BM, T3);
+    mmt(lane, d, m, d, T4, BM, T3);                   // (T3 = Q's buffer: Q_k is dead)
     simt::sync();
     axpy(lane, dd, T2, T3, false, T2);
     simt::sync();
@@ -253,28 +261,36 @@ HOP_DEVICE int sweep_step(int lane, int d, int m, int k, const Layout& L, R* s, 
     if (k == 0) {
         copy(lane, dd, E, EB); copy(lane, dd, F, FB); copy(lane, dd, G, GB);
         simt::sync();
-    } else {
-        // prefix: W = chol_inv(E_k + Gbar); Ebar <- sym(Ebar - (Fbar W) Fbar^T); Fbar <- (Fbar W) F_k;
-        //         Gbar <- sym(G_k - (F_k^T W) F_k); every right-hand side uses the OLD Ebar, Fbar, Gbar
-        axpy(lane, dd, E, GB, false, T1);
-        simt::sync();
-        if (int rc = chol_inv(lane, d, T1, W, MB, LB, jitter, max_tries, flags)) return rc;
-        mm(lane, d, d, d, FB, W, T1);
-        mtm(lane, d, d, d, F, W, T3);
-        simt::sync();
-        mmt(lane, d, d, d, T1, FB, T2);
-        simt::sync();
-        axpy(lane, dd, EB, T2, true, T2);
-        mm(lane, d, d, d, T1, F, FB);                 // old Fbar is no longer read
-        simt::sync();
-        sym(lane, d, T2, EB);
-        mm(lane, d, d, d, T3, F, T1);
-        simt::sync();
-        axpy(lane, dd, G, T1, true, T1);
-        simt::sync();
-        sym(lane, d, T1, GB);
-        simt::sync();
+        return ST_OK;
     }
+    // prefix: W = chol_inv(E_k + Gbar); Ebar <- sym(Ebar - (Fbar W) Fbar^T); Fbar <- (Fbar W) F_k;
+    //         Gbar <- sym(G_k - (F_k^T W) F_k); every right-hand side uses the OLD Ebar, Fbar, Gbar
+    axpy(lane, dd, E, GB, false, T1);
+    simt::sync();
+    if (int rc = chol_inv(lane, d, T1, W, MB, LB, jitter, max_tries, flags)) return rc;
+    mm(lane, d, d, d, FB, W, T1);
+    mtm(lane, d, d, d, F, W, T3);
+    simt::sync();
+    mmt(lane, d, d, d, T1, FB, T2);
+    simt::sync();
+    axpy(lane, dd, EB, T2, true, T2);
+    mm(lane, d, d, d, T1, F, FB);                     // old Fbar is no longer read
+    simt::sync();
+    sym(lane, d, T2, EB);
+    mm(lane, d, d, d, T3, F, T1);
+    simt::sync();
+    axpy(lane, dd, G, T1, true, T1);
+    simt::sync();
+    sym(lane, d, T1, GB);
+    simt::sync();
+    return ST_OK;
+}
+
+template <typename R>
+HOP_DEVICE int query_step(int lane, int d, const Layout& L, R* s, R jitter, int max_tries, int& flags, R* J_out) {
+    const int dd = d * d;
+    R *EB = s + L.EB, *FB = s + L.FB, *GB = s + L.GB, *W = s + L.W, *T1 = s + L.T1, *T2 = s + L.T2, *T3 = s + L.T3;
+    R *XT = s + L.XT, *MB = s + L.MB, *LB = s + L.LB, *Z0 = s + L.Z0, *V0 = s + L.V0;
     // query: X_t = chol_inv(QT_t); W_t = chol_inv(X_t + Gbar); X0 = sym(Ebar - (Fbar W_t) Fbar^T); P0 = chol_inv(X0)
     if (int rc = chol_inv(lane, d, XT, T1, MB, LB, jitter, max_tries, flags)) return rc;
     axpy(lane, dd, T1, GB, false, T1);
@@ -323,13 +339,18 @@ HOP_DEVICE void select_generic_body(const SelectArgs& p, int d, int m, int b, R*
         const double* Tk = p.QT + (base + k) * dd;
         const double* Bk = p.B_aug + (base + k) * dm;
         simt::sync();
-        for (int i = lane; i < dd; i += 32) { s[L.A + i] = (R)Ak[i]; s[L.Q + i] = (R)Qk[i]; s[L.XT + i] = (R)Tk[i]; }
+        for (int i = lane; i < dd; i += 32) { s[L.A + i] = (R)Ak[i]; s[L.Q + i] = (R)Qk[i]; }
         for (int i = lane; i < dm; i += 32) s[L.BM + i] = (R)Bk[i];
         if (p.rinv_step_stride)
             for (int i = lane; i < mm_; i += 32) s[L.RI + i] = (R)p.R_inv[(size_t)b * rinv_inst + (size_t)k * p.rinv_step_stride + i];
         simt::sync();
         R J = 0;
-        err = sweep_step<R>(lane, d, m, k, L, s, (R)p.jitter, p.max_tries, flags, &J);
+        err = stage_prefix_step<R>(lane, d, m, k, L, s, (R)p.jitter, p.max_tries, flags);
+        if (!err) {
+            for (int i = lane; i < dd; i += 32) s[L.XT + i] = (R)Tk[i];
+            simt::sync();
+            err = query_step<R>(lane, d, L, s, (R)p.jitter, p.max_tries, flags, &J);
+        }
         if (err) {                                    // the reference raises: the rest of the curve is undefined
             if (lane == 0)
                 for (int q = k; q < p.T_max; ++q) p.J_out[(size_t)b * p.T_max + q] = nan("");
@@ -433,7 +454,6 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int n, int m, int b, doubl
         for (int i = lane; i < n * n; i += 32) {
             const int a = i / n, c = i % n;
             Q[a * d + c] = add(cst[C.QS + i], a == c ? p.q_reg : 0.0);           // augmented.py:32
-            XT[a * d + c] = cst[C.PF + i];
         }
         simt::sync();
         if (lane == 0) {
@@ -441,7 +461,12 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int n, int m, int b, doubl
             for (int j = 0; j < n; ++j) eQe = add(eQe, V2[j]);
             Q[n * d + n] = add(add(eQe, mul(2.0, w)), p.rho_reg);                // augmented.py:37
         }
-        // terminal block of horizon t = k + 1 from X[k + 1] (augmented.py:78-86)
+        simt::sync();
+        double J = 0.0;
+        err = stage_prefix_step<R>(lane, d, m, k, L, s, p.jitter, p.max_tries, flags);
+        if (err) break;
+        // terminal block of horizon t = k + 1 from X[k + 1] (augmented.py:78-86), staged in F_k's buffer (dead by now)
+        for (int i = lane; i < n * n; i += 32) XT[(i / n) * d + (i % n)] = cst[C.PF + i];
         if (isx) {
             double px = 0.0;
             for (int j = 0; j < n; ++j) px = add(px, mul(cst[C.PF + lane * n + j], V3[j]));
@@ -456,8 +481,7 @@ HOP_DEVICE void select_fused_body(const FusedArgs& p, int n, int m, int b, doubl
             XT[n * d + n] = add(mul(2.0, mul(0.5, ePe)), p.rho_reg);
         }
         simt::sync();
-        double J = 0.0;
-        err = sweep_step<R>(lane, d, m, k, L, s, p.jitter, p.max_tries, flags, &J);
+        err = query_step<R>(lane, d, L, s, p.jitter, p.max_tries, flags, &J);
         if (err) break;
         if (lane == 0) p.J_out[(size_t)b * p.T_max + k] = J;
         if (k + 1 >= p.T_min) am.push(J, k + 1);
