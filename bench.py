@@ -296,69 +296,72 @@ def run_hop(args):
                         "algorithmic_bytes_per_solve": b_alg_fused(N_HORIZON, n, m),
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}}
 
-    # ---- CPU baseline + parity census (outside every timed region)
-    #  * the C port on ALL B instances of rank 0 (all host cores): throughput + the three-number census of oracle/census.py
-    #    (|gpu-oracle|, |oracle-fp80|, |gpu-fp80|, argmin gaps, ill-posed instances; a T* mismatch must be explained by it)
-    #  * HOP_MODE_EXACT on the same batch on the device: the measured mode against the parity mode
-    #  * the REAL reference (oracle/_ref, unmodified Python) on the first instances: T* equality and solves/s per core
-    #  * the committed reference-generated golden (first 4096 instances of this very batch, tests/golden)
-    import oracle as O
-    from oracle import census, ref_py
-    O.build()
-    cores = os.cpu_count() or 1
-    t0c = time.perf_counter()
-    rep = census.census_from_x0(case, x0_np, J_h, T_h, nthreads=cores, fp80_stride=8)
-    t_census = time.perf_counter() - t0c
-    dtc, Jc, Tc, stc = cpu_from_x0(case, x0_np[:min(B, 16384)], cores)          # timed alone (the census also runs fp80 sweeps)
-    sample = min(B, 16384)
-    ex = api.select_horizon_batched(case, x0_dev, mode=api.MODE_EXACT)
-    T_ex = ex.T_star.cpu().numpy().astype(np.int64); J_ex = ex.J.cpu().numpy()
-    Tg = T_h.astype(np.int64)
-    dmode = np.abs(J_h[:, T_min - 1:] - J_ex[:, T_min - 1:]) / np.abs(J_ex[:, T_min - 1:])
-    mm = np.nonzero(T_ex != Tg)[0]
-    unexpl = 0
-    for i in mm:
-        gap = abs(J_ex[i, T_ex[i] - 1] - J_ex[i, Tg[i] - 1]) / abs(J_ex[i, T_ex[i] - 1])
-        noise = max(abs(J_h[i, t - 1] - J_ex[i, t - 1]) / abs(J_ex[i, t - 1]) for t in (T_ex[i], Tg[i]))
-        unexpl += int(not gap < 10.0 * noise)
-    rep_ex = census.census_from_x0(case, x0_np[:sample], J_ex[:sample], T_ex[:sample], nthreads=cores, fp80_stride=8)
-    vs_exact = {"checked": int(B), "T_star_mismatches": int(mm.size), "T_star_mismatches_unexplained": unexpl,
-                "rule": "gap between the two candidates (EXACT curve) < 10 x distance between the two curves at those horizons",
-                "max_rel_J_window": float(dmode.max()), "p99_rel_J_window": float(np.percentile(dmode.max(axis=1), 99)),
-                "exact_mode_vs_oracle": {k: rep_ex[k] for k in ("checked", "T_star_mismatches", "T_star_mismatches_unexplained",
-                                                                 "rel_J_window", "rel_J_at_Tstar")}}
-    golden_chk = None
-    try:
-        g = np.load(os.path.join(ROOT, "tests", "golden", "s1_quadrotor_ref4096.npz"))
-        if rank == 0 and int(g["seed"]) == 0 and B >= g["T"].shape[0]:
-            ng = g["T"].shape[0]
-            Tr = g["T"].astype(np.int64)
-            cols = np.clip(Tr[:, None] + np.arange(-2, 3)[None, :], 1, T_max)
-            J5 = J_h[np.arange(ng)[:, None], cols - 1]
-            golden_chk = {"instances": int(ng), "T_star_mismatches": int((Tg[:ng] != Tr).sum()),
-                          "max_rel_J_at_Tstar_pm2": float(np.nanmax(np.abs(J5 - g["J_pm2"]) / np.abs(g["J_pm2"]))),
-                          "what": "first 4096 instances of this batch computed by the REAL reference in the build container "
-                                  "(tests/golden/make_golden.py s1_ref4096)"}
-    except OSError:
-        pass
-    ref_leg = {"available": False, "why": "oracle/_ref not staged"}
-    if ref_py.available():
-        nref = 8 * cores
-        pool = ref_py.Pool(cores)
-        Tpy, Jpy, dpy = pool.s1_select(x0_np[:nref])
-        pool.close()
-        ref_leg = {"available": True, "kind": "reference", "instances": int(nref), "value": nref / dpy, "unit": UNIT,
-                   "cores": cores, "per_core": nref / dpy / cores,
-                   "T_star_equal_gpu": int((Tpy == T_h[:nref]).sum()), "T_star_equal_port": int((Tpy == Tc[:nref]).sum()),
-                   "max_rel_J_window_gpu_vs_reference": float(np.max(np.abs(J_h[:nref, T_min - 1:] - Jpy[:, T_min - 1:]) / np.abs(Jpy[:, T_min - 1:]))),
-                   "max_rel_J_window_port_vs_reference": float(np.max(np.abs(Jc[:nref, T_min - 1:] - Jpy[:, T_min - 1:]) / np.abs(Jpy[:, T_min - 1:]))),
-                   "what": "the unmodified reference modules (oracle/_ref) on the first instances of this batch, one process per core"}
-    cpu_baseline = {"value": sample / dtc, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"first {sample} instances of rank 0's batch, x0 -> T* pipeline, oracle/hop_oracle.c on {cores} "
-                              "pthreads",
-                    "reference_python": ref_leg,
-                    "parity_on_sample": dict(rep, census_seconds=t_census, mode_checked=args.mode),
-                    "fast_vs_exact_mode_on_device": vs_exact, "reference_golden": golden_chk}
+    cpu_baseline = None
+    if not args.no_cpu_legs:
+        # ---- CPU baseline + parity census (outside every timed region)
+        #  * the C port on ALL B instances of rank 0 (all host cores): throughput + the three-number census of oracle/census.py
+        #    (|gpu-oracle|, |oracle-fp80|, |gpu-fp80|, argmin gaps, ill-posed instances; a T* mismatch must be explained by it)
+        #  * HOP_MODE_EXACT on the same batch on the device: the measured mode against the parity mode
+        #  * the REAL reference (oracle/_ref, unmodified Python) on the first instances: T* equality and solves/s per core
+        #  * the committed reference-generated golden (first 4096 instances of this very batch, tests/golden)
+        import oracle as O
+        from oracle import census, ref_py
+        O.build()
+        cores = os.cpu_count() or 1
+        t0c = time.perf_counter()
+        rep = census.census_from_x0(case, x0_np, J_h, T_h, nthreads=cores, fp80_stride=8)
+        t_census = time.perf_counter() - t0c
+        dtc, Jc, Tc, stc = cpu_from_x0(case, x0_np[:min(B, 16384)], cores)          # timed alone (the census also runs fp80 sweeps)
+        sample = min(B, 16384)
+        ex = api.select_horizon_batched(case, x0_dev, mode=api.MODE_EXACT)
+        T_ex = ex.T_star.cpu().numpy().astype(np.int64); J_ex = ex.J.cpu().numpy()
+        Tg = T_h.astype(np.int64)
+        dmode = np.abs(J_h[:, T_min - 1:] - J_ex[:, T_min - 1:]) / np.abs(J_ex[:, T_min - 1:])
+        mm = np.nonzero(T_ex != Tg)[0]
+        unexpl = 0
+        for i in mm:
+            gap = abs(J_ex[i, T_ex[i] - 1] - J_ex[i, Tg[i] - 1]) / abs(J_ex[i, T_ex[i] - 1])
+            noise = max(abs(J_h[i, t - 1] - J_ex[i, t - 1]) / abs(J_ex[i, t - 1]) for t in (T_ex[i], Tg[i]))
+            unexpl += int(not gap < 10.0 * noise)
+        rep_ex = census.census_from_x0(case, x0_np[:sample], J_ex[:sample], T_ex[:sample], nthreads=cores, fp80_stride=8)
+        vs_exact = {"checked": int(B), "T_star_mismatches": int(mm.size), "T_star_mismatches_unexplained": unexpl,
+                    "rule": "gap between the two candidates (EXACT curve) < 10 x distance between the two curves at those horizons",
+                    "max_rel_J_window": float(dmode.max()), "p99_rel_J_window": float(np.percentile(dmode.max(axis=1), 99)),
+                    "exact_mode_vs_oracle": {k: rep_ex[k] for k in ("checked", "T_star_mismatches", "T_star_mismatches_unexplained",
+                                                                     "rel_J_window", "rel_J_at_Tstar")}}
+        golden_chk = None
+        try:
+            g = np.load(os.path.join(ROOT, "tests", "golden", "s1_quadrotor_ref4096.npz"))
+            if rank == 0 and int(g["seed"]) == 0 and B >= g["T"].shape[0]:
+                ng = g["T"].shape[0]
+                Tr = g["T"].astype(np.int64)
+                cols = np.clip(Tr[:, None] + np.arange(-2, 3)[None, :], 1, T_max)
+                J5 = J_h[np.arange(ng)[:, None], cols - 1]
+                golden_chk = {"instances": int(ng), "T_star_mismatches": int((Tg[:ng] != Tr).sum()),
+                              "max_rel_J_at_Tstar_pm2": float(np.nanmax(np.abs(J5 - g["J_pm2"]) / np.abs(g["J_pm2"]))),
+                              "what": "first 4096 instances of this batch computed by the REAL reference in the build container "
+                                      "(tests/golden/make_golden.py s1_ref4096)"}
+        except OSError:
+            pass
+        ref_leg = {"available": False, "why": "oracle/_ref not staged"}
+        if ref_py.available():
+            nref = 8 * cores
+            pool = ref_py.Pool(cores)
+            Tpy, Jpy, dpy = pool.s1_select(x0_np[:nref])
+            pool.close()
+            ref_leg = {"available": True, "kind": "reference", "instances": int(nref), "value": nref / dpy, "unit": UNIT,
+                       "cores": cores, "per_core": nref / dpy / cores,
+                       "T_star_equal_gpu": int((Tpy == T_h[:nref]).sum()), "T_star_equal_port": int((Tpy == Tc[:nref]).sum()),
+                       "max_rel_J_window_gpu_vs_reference": float(np.max(np.abs(J_h[:nref, T_min - 1:] - Jpy[:, T_min - 1:]) / np.abs(Jpy[:, T_min - 1:]))),
+                       "max_rel_J_window_port_vs_reference": float(np.max(np.abs(Jc[:nref, T_min - 1:] - Jpy[:, T_min - 1:]) / np.abs(Jpy[:, T_min - 1:]))),
+                       "what": "the unmodified reference modules (oracle/_ref) on the first instances of this batch, one process per core"}
+        cpu_baseline = {"value": sample / dtc, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"first {sample} instances of rank 0's batch, x0 -> T* pipeline, oracle/hop_oracle.c on {cores} "
+                                  "pthreads",
+                        "reference_python": ref_leg,
+                        "parity_on_sample": dict(rep, census_seconds=t_census, mode_checked=args.mode),
+                        "fast_vs_exact_mode_on_device": vs_exact, "reference_golden": golden_chk}
+
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_launch, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -392,6 +395,8 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU (weak scaling)")
     ap.add_argument("--mode", choices=["exact", "fast", "gj"], default="fast",
                     help="selection variant (include/hop_b200.h HOP_MODE_*); all compute the same function")
+    ap.add_argument("--no-cpu-legs", action="store_true",
+                    help="skip the CPU baseline / parity census (they fork worker processes); only for the ncu launch list")
     ap.add_argument("--ref-kind", choices=["auto", "port"], default="auto",
                     help="--impl reference: auto = the Python reference from oracle/_ref when staged, else the C port")
     args = ap.parse_args()
