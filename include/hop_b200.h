@@ -219,6 +219,10 @@ long hop_test_set_tpp_min_batch(long min_batch);
  * in a parallel pre-pass (k_preinvert), 0 = inside the sequential kernel, -1 = pre-pass for B <= 1024 only [default]; identical
  * bits.  Returns the previous value. */
 int hop_test_set_generic_pre(int on);
+/* Test hook: hop_select_f64 for d in {12, 13}: 1 [default] = DIAGONAL input blocks Q_k / QT_t are inverted element-wise (what the
+ * Gauss-Jordan sweep of a diagonal matrix computes anyway), 0 = by the sweep like any other block; identical bits.  Returns the
+ * previous value. */
+int hop_test_set_generic_diag(int on);
 /* Test hook: fused selection kernel of the small systems (n <= 4), 0 = one matrix element per lane, a warp per problem
  * [default], 1 = lane group per problem; identical bits.  Returns the previous value. */
 int hop_test_set_fused_small_variant(int variant);

@@ -16,7 +16,7 @@ class SelectArgs(C.Structure):
     _fields_ = [("B", C.c_int), ("N", C.c_int), ("T_min", C.c_int), ("T_max", C.c_int), ("jitter", C.c_double),
                 ("max_tries", C.c_int), ("A_aug", _dp), ("B_aug", _dp), ("Q_aug", _dp), ("R_inv", _dp), ("z0", _dp),
                 ("QT", _dp), ("rinv_step_stride", C.c_long), ("w_explicit", _dp), ("J_out", _dp), ("T_out", _ip), ("Jstar_out", _dp), ("status", _ip),
-                ("E_pre", _dp), ("X_pre", _dp), ("pre_bad", _ip)]
+                ("E_pre", _dp), ("X_pre", _dp), ("pre_bad", _ip), ("no_diag_fastpath", C.c_int)]
 
 
 class FusedArgs(C.Structure):
@@ -57,14 +57,15 @@ def _p(a):
 
 
 def select_generic(A_aug, B_aug, Q_aug, R_inv, z0, QT, T_min, T_max, w_explicit=None, jitter=1e-9, max_tries=8,
-                   mma=False, scan=False, pipe=False, tpp=False, ref=False, fp32=False):
+                   mma=False, scan=False, pipe=False, tpp=False, ref=False, fp32=False, no_diag=False):
     A_aug, B_aug, Q_aug, R_inv, z0, QT = map(_d, (A_aug, B_aug, Q_aug, R_inv, z0, QT))
     Bsz, N, d = A_aug.shape[:3]
     m = B_aug.shape[3]
     wexp = None if w_explicit is None else _d(w_explicit)
     J = np.full((Bsz, T_max), np.nan); T = np.zeros(Bsz, np.int32); Js = np.zeros(Bsz); st = np.zeros(Bsz, np.int32)
     a = SelectArgs(Bsz, N, T_min, T_max, jitter, max_tries, _p(A_aug), _p(B_aug), _p(Q_aug), _p(R_inv), _p(z0), _p(QT),
-                   (m * m if R_inv.ndim == 4 else 0), _p(wexp), _p(J), T.ctypes.data_as(_ip), _p(Js), st.ctypes.data_as(_ip))
+                   (m * m if R_inv.ndim == 4 else 0), _p(wexp), _p(J), T.ctypes.data_as(_ip), _p(Js), st.ctypes.data_as(_ip),
+                   None, None, None, int(bool(no_diag)))
     if ref or fp32:
         rc = lib().emul_select_generic_ref(d, m, C.byref(a), int(bool(fp32)))
         assert rc == 0, f"emulated kernel failed rc={rc}"

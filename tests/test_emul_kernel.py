@@ -274,3 +274,24 @@ def test_emulated_fp32_mode_stays_within_its_stated_tolerance(d, m, N):
     Jo, _ = O.propagator_batch(A, B, Q, Rinv, z0, QT)
     assert not st.any() and rel(J, Jo) <= 1e-4
     assert np.array_equal(T, np.argmin(Jo + w[:, None] * np.arange(1, N + 1), axis=1) + 1)
+
+
+@pytest.mark.parametrize("d,m,N", [(12, 4, 12), (13, 4, 16)])
+def test_emulated_diagonal_block_fast_path_is_bit_identical_to_the_sweep(d, m, N):
+    """hop_select_gpipe_body.cuh inverts DIAGONAL input blocks (Q_k, QT_t: the whole synthetic family S2) element-wise instead
+    of by two Gauss-Jordan sweeps.  The sweep of a diagonal matrix computes exactly those reciprocals, so J, T*, J*, status
+    must not change by a bit -- also when only some blocks are diagonal (instance 1: a dense Q_3, a dense QT_5) and when a
+    diagonal entry is not positive (instance 2: ladder -> sequential cold path)."""
+    A, B, Q, R, z0, w, QT = s2_batch(range(3), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    rng = np.random.default_rng(8)
+    Mx = rng.standard_normal((d, d)); Q[1, 3] = Mx @ Mx.T / d + np.eye(d)          # dense SPD blocks
+    Mx = rng.standard_normal((d, d)); QT[1, 5] = Mx @ Mx.T + 50.0 * np.eye(d)
+    Q[2, 4] = np.diag(np.r_[np.ones(d - 1), -1e-4])                                 # diagonal, not PD: jitter ladder
+    a = emul.select_generic(A, B, Q, Rinv, z0, QT, 1, N, w_explicit=w, pipe=True)
+    b = emul.select_generic(A, B, Q, Rinv, z0, QT, 1, N, w_explicit=w, pipe=True, no_diag=True)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y, equal_nan=True)
+    Jo, sto = O.propagator_batch(A, B, Q, Rinv, z0, QT)
+    assert a[3][0] == 0 and a[3][1] == 0 and a[3][2] & 0x100 and not sto.any()
+    assert rel(a[0], Jo) <= 1e-9

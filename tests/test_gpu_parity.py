@@ -565,6 +565,37 @@ def test_pre_inverted_and_in_kernel_sweep_b_agree_bit_for_bit(d, m, N, T_max):
         assert st[2] == 0x300 and (st[B - 1] & 0xFF) == 1 and st[0] == 0
 
 
+@pytest.mark.parametrize("d,m,N", [(12, 4, 40), (13, 4, 64)])
+def test_diagonal_block_fast_path_and_sweep_agree_bit_for_bit(d, m, N):
+    """hop_select_f64, d in {12, 13}: DIAGONAL input blocks Q_k / QT_t (the whole S2 family) are inverted element-wise instead
+    of by two Gauss-Jordan sweeps; the sweep of a diagonal matrix computes exactly those reciprocals, so nothing may change by a
+    bit -- with dense blocks mixed in (instance 1) and a non-PD diagonal block (instance 2: ladder, sequential cold path)."""
+    from hop import _cabi
+    lib = _cabi.require_device()
+    B = 19
+    A, Bm, Q, R, z0, w, QT = s2_batch(range(B), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    rng = np.random.default_rng(8)
+    Mx = rng.standard_normal((d, d)); Q[1, 3] = Mx @ Mx.T / d + np.eye(d)
+    Mx = rng.standard_normal((d, d)); QT[1, 5] = Mx @ Mx.T + 50.0 * np.eye(d)
+    Q[2, 4] = np.diag(np.r_[np.ones(d - 1), -1e-4])
+    args = (_t(A), _t(Bm), _t(Q), _t(Rinv), _t(z0), _t(QT), 1, N)
+    out = {}
+    old = lib.hop_test_set_generic_diag(1)
+    try:
+        for on in (1, 0):
+            lib.hop_test_set_generic_diag(on)
+            sel = api.propagator_all_Jt_aug_batched(*args, w_explicit=_t(w), mode=api.MODE_FAST)
+            out[on] = tuple(x.cpu().numpy() for x in (sel.J, sel.T_star, sel.J_star, sel.status))
+    finally:
+        lib.hop_test_set_generic_diag(old)
+    for a, b in zip(out[1], out[0]):
+        assert np.array_equal(a, b, equal_nan=True)
+    Jo, sto = O.propagator_batch(A, Bm, Q, Rinv, z0, QT, nthreads=4)
+    assert not sto.any() and out[1][3][0] == 0 and out[1][3][2] & 0x100
+    assert rel(out[1][0], Jo) <= 1e-9
+
+
 @pytest.mark.parametrize("name", ["DoubleIntegrator", "Segway_Balance", "Cartpole_SwingUp"])
 def test_element_per_lane_and_lane_group_fused_kernels_agree_bit_for_bit(name):
     """The fused selection of the small systems has two device mappings (a warp per problem with one matrix element per

@@ -23,6 +23,7 @@ extern int g_backward_variant;
 extern int g_linesearch_variant;
 extern int g_fused_small_variant;
 extern int g_generic_pre;
+extern int g_generic_nodiag;
 struct DdpConst {
     const double *xg, *w, *u_ref, *Q, *R, *Qf;
     unsigned wrap_mask;
@@ -121,7 +122,7 @@ int hop_select_f64(int B, int N, int d, int m, int T_min, int T_max, const doubl
     if (int rc = need_device()) return rc;
     if (B == 0) return 0;
     SelectArgs p{B, N, T_min, T_max, kJitter, kMaxTries, A_aug, B_aug, Q_aug, R_inv, z0, QT, rinv_step_stride, w_explicit,
-                 J_out, Tstar_out, Jstar_out, status};
+                 J_out, Tstar_out, Jstar_out, status, nullptr, nullptr, nullptr, g_generic_nodiag};
     return dispatch_select_generic(d, m, mode, p, (cudaStream_t)stream);
 }
 
@@ -160,7 +161,7 @@ int hop_select_fused_f64(int B, int N, int n, int m, int T_min, int T_max, const
         if (!rc) rc = launch_scan_consts(B, d, m, R1, R_inv, z0, st);                                 // augmented.py:59
         if (!rc) {
             SelectArgs q{B, N, T_min, T_max, kJitter, kMaxTries, A_aug, B_aug, Q_aug, R_inv, z0, QT, 0, nullptr,
-                         J_out, Tstar_out, Jstar_out, status};
+                         J_out, Tstar_out, Jstar_out, status, nullptr, nullptr, nullptr, g_generic_nodiag};
             rc = dispatch_select_generic(d, m, HOP_MODE_SCAN, q, st);
         }
         stream_free(ws, st);
@@ -503,6 +504,12 @@ int hop_test_set_linesearch_variant(int variant) {
 int hop_test_set_fused_small_variant(int variant) {
     const int old = g_fused_small_variant;
     if (variant == 0 || variant == 1) g_fused_small_variant = variant;
+    return old;
+}
+
+int hop_test_set_generic_diag(int on) {
+    const int old = g_generic_nodiag ? 0 : 1;
+    if (on == 0 || on == 1) g_generic_nodiag = on ? 0 : 1;
     return old;
 }
 

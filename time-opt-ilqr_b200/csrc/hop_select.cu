@@ -206,6 +206,8 @@ void stream_free(void* ptr, cudaStream_t st) {
 // (S2, d = 13, N = 128): B = 8: 0.95 -> 0.76 ms (one sweep latency per step instead of two); B = 65 536: 63.3 -> 68.2 ms
 // (sequential kernel 63.3 -> 46.5 ms, but the pre-pass moves 45 GB and costs 19.8 ms): it pays where latency matters.
 int g_generic_pre = getenv("HOP_GENERIC_PRE") ? atoi(getenv("HOP_GENERIC_PRE")) : -1;
+// 1: diagonal input blocks go through the Gauss-Jordan sweep like any other block (A/B switch + test hook); 0 [default]: element-wise
+int g_generic_nodiag = getenv("HOP_GENERIC_NODIAG") ? atoi(getenv("HOP_GENERIC_NODIAG")) : 0;
 constexpr int kGenericPreMaxBatch = 1024;
 
 template <int D, int M>

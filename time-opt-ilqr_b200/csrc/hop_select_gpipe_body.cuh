@@ -185,6 +185,33 @@ HOP_DEVICE void pre_invert_cols(const double* src, double jitter, double* dst, i
     if (live && (signs < 0 || !fin)) *bad_out = 1;
 }
 
+// ---- diagonal input blocks -------------------------------------------------------------------------------------------
+// Sweep B inverts blocks that only depend on the inputs (Q_k, QT_t).  When such a block is DIAGONAL -- every problem of
+// the synthetic HOP-LQR family of SURVEY.md s.8d (Q_k = diag, QT_t = 50 I), and any LQR problem with diagonal weights --
+// the Gauss-Jordan sweep of sym(block) + eps I degenerates: pivot j is the j-th diagonal entry, every multiplier is an exact
+// zero, and the result is the matrix with pivot_rcp3(p_j) on the diagonal.  The same values are produced here element-wise
+// (13 reciprocals instead of two 13-round sweeps: one sweep latency per step instead of two), decided per block pair by a
+// warp vote on the staged block, so mixed inputs still take the sweep.  Identical bits either way (asserted).
+template <int D>
+HOP_DEVICE bool is_diagonal(const Mat& S, const LaneGeo& L) {
+    bool z = true;
+    HOP_FOR_ELEMS(I, J, s) {
+        if (L.row(I) != L.col(J, s)) z = z && (S.v[I][J][s] == 0.0);
+    }
+    return simt::all(z);
+}
+template <int D>
+HOP_DEVICE void diagonal_inverse(Mat& S, const LaneGeo& L, int& signs) {
+    HOP_FOR_ELEMS(I, J, s) {
+        const int R = L.row(I);
+        if (R == L.col(J, s) && R < D) {
+            const double p = S.v[I][J][s];
+            signs |= hi_word(p);
+            S.v[I][J][s] = pivot_rcp3(p);
+        }
+    }
+}
+
 // Returns true when the problem was solved by the pipelined sweep; false => caller must run the sequential body.
 template <int D, int M, bool PRE = false>
 HOP_DEVICE bool select_generic_pipe_body(const SelectArgs& p, int b, double* slab) {
@@ -226,13 +253,24 @@ HOP_DEVICE bool select_generic_pipe_body(const SelectArgs& p, int b, double* sla
         }
     };
     auto ident = [&](Mat& S) { HOP_FOR_ELEMS(I, J, s) S.v[I][J][s] = (L.row(I) == L.col(J, s)) ? 1.0 : 0.0; };
+    int signs = 0;
+    const bool diag_ok = (p.no_diag_fastpath == 0);
+    // sweep B on a pair of input blocks (each already sym(.) + eps I): element-wise when both are diagonal
+    auto sweep_b = [&](Mat& S1, Mat& S2) {
+        if (diag_ok && is_diagonal<D>(S1, L) && is_diagonal<D>(S2, L)) {
+            diagonal_inverse<D>(S1, L, signs);
+            diagonal_inverse<D>(S2, L, signs);
+        } else {
+            gj2_group<D, 0, 0>(S1, S2, L, signs); gj2_group<D, 0, 1>(S1, S2, L, signs);
+            gj2_group<D, 1, 0>(S1, S2, L, signs); gj2_group<D, 1, 1>(S1, S2, L, signs);
+        }
+    };
     Mat RinvT;
     mat_load_t(RinvT, p.R_inv + (size_t)b * rinv_inst, M, M, M, L);
     double zr[2];
 #pragma unroll
     for (int I = 0; I < 2; ++I) zr[I] = (L.row(I) < D) ? p.z0[(size_t)b * D + L.row(I)] : 0.0;
     const double wexp = p.w_explicit ? p.w_explicit[b] : 0.0;
-    int signs = 0;
     bool bad = false;
 
     issue(0); issue(1); issue(2);
@@ -245,17 +283,11 @@ HOP_DEVICE bool select_generic_pipe_body(const SelectArgs& p, int b, double* sla
         Mat E0;
         load_spd(E0, slab + 0 * GS_::STAGE + GS_::oQ);
         load_spd(Xt, slab + 0 * GS_::STAGE + GS_::oT);
-        if (!PRE) {
-            gj2_group<D, 0, 0>(E0, Xt, L, signs); gj2_group<D, 0, 1>(E0, Xt, L, signs);
-            gj2_group<D, 1, 0>(E0, Xt, L, signs); gj2_group<D, 1, 1>(E0, Xt, L, signs);
-        }
+        if (!PRE) sweep_b(E0, Xt);
         Mat dummy;
         ident(dummy);
         if (p.T_max > 1) load_spd(En, slab + 1 * GS_::STAGE + GS_::oQ); else ident(En);
-        if (!PRE) {
-            gj2_group<D, 0, 0>(En, dummy, L, signs); gj2_group<D, 0, 1>(En, dummy, L, signs);
-            gj2_group<D, 1, 0>(En, dummy, L, signs); gj2_group<D, 1, 1>(En, dummy, L, signs);
-        }
+        if (!PRE) sweep_b(En, dummy);
         Mat A, Bm, Ft, G, BR;
         mat_load(A, slab + GS_::oA, D, D, D, L);
         mat_load(Bm, slab + GS_::oB, D, M, M, L);
@@ -367,10 +399,7 @@ HOP_DEVICE bool select_generic_pipe_body(const SelectArgs& p, int b, double* sla
             simt::sync();
             load_spd(Xt, stg + GS_::oT);
             if (k + 2 < p.T_max) load_spd(En, slab + ((k + 2) % 3) * GS_::STAGE + GS_::oQ); else ident(En);
-            if (!PRE) {
-                gj2_group<D, 0, 0>(En, Xt, L, signs); gj2_group<D, 0, 1>(En, Xt, L, signs);
-                gj2_group<D, 1, 0>(En, Xt, L, signs); gj2_group<D, 1, 1>(En, Xt, L, signs);
-            }
+            if (!PRE) sweep_b(En, Xt);
         }
     }
     // ---------------- epilogue: cost of the last horizon

@@ -48,6 +48,7 @@ SIGNATURES = {
     "hop_test_set_linesearch_variant": (_i, [_i]),
     "hop_test_set_fused_small_variant": (_i, [_i]),
     "hop_test_set_generic_pre": (_i, [_i]),
+    "hop_test_set_generic_diag": (_i, [_i]),
     "hop_test_set_tpp_min_batch": (_l, [_l]),
     "hop_probe_fp64_tflops": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }

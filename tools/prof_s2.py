@@ -33,7 +33,7 @@ Rd = 0.05 + 0.45 * torch.rand((B, m), dtype=torch.float64, device=dev, generator
 Rinv = torch.diag_embed(1.0 / (Rd + 1e-9))
 z0 = torch.randn((B, d), dtype=torch.float64, device=dev, generator=gen)
 w = 0.01 + 0.09 * torch.rand((B,), dtype=torch.float64, device=dev, generator=gen)
-run = lambda: api.propagator_all_Jt_aug_batched(A, Bm, Q, Rinv, z0, QT, 1, N, w_explicit=w)  # noqa: E731
+run = lambda: api.propagator_all_Jt_aug_batched(A, Bm, Q, Rinv, z0, QT, 1, N, w_explicit=w, mode=api.MODE_FAST)  # noqa: E731
 sel = run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
