@@ -226,9 +226,8 @@ int hop_test_set_generic_diag(int on);
 /* Test hook: fused selection kernel of the small systems (n <= 4), 0 = one matrix element per lane, a warp per problem
  * [default], 1 = lane group per problem; identical bits.  Returns the previous value. */
 int hop_test_set_fused_small_variant(int variant);
-/* Test hook: line-search kernel, 0 = the five step sizes side by side as single-warp CTAs spread over the SMs, two launches
- * [default], 1 = one thread per problem trying them in turn, 2 = the six roles of 32 problems in one CTA; identical bits.
- * Returns the previous value. */
+/* Test hook: line-search kernel, 0 = the five step sizes side by side, six threads per problem [default], 1 = one thread
+ * per problem trying them in turn; identical bits.  Returns the previous value. */
 int hop_test_set_linesearch_variant(int variant);
 /* Test hook: backward-pass kernel, 0 = one warp per problem [default], 1 = one thread per problem; identical bits. */
 int hop_test_set_backward_variant(int variant);

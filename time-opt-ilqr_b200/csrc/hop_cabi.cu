@@ -497,7 +497,7 @@ int hop_test_set_backward_variant(int variant) {
 
 int hop_test_set_linesearch_variant(int variant) {
     const int old = g_linesearch_variant;
-    if (variant >= 0 && variant <= 2) g_linesearch_variant = variant;
+    if (variant == 0 || variant == 1) g_linesearch_variant = variant;
     return old;
 }
 

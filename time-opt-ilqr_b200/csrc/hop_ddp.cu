@@ -199,89 +199,9 @@ __global__ void __launch_bounds__(kLsRoles * 32) k_linesearch_par(int B, DynPara
     for (size_t i = role; i < (size_t)N * m; i += kLsRoles) Unb[i] = Ub[i];
     if (role == 0) { Jn[b] = J_old; acc[b] = 0; }
 }
-// The same side-by-side line search as TWO launches of single-warp CTAs.  k_linesearch_par puts the six roles of 32
-// instances into one CTA, i.e. onto one SM, where they queue for the same FP64 pipes: a HOP-DDP batch of a few thousand
-// instances occupies a fraction of the SMs with six warps each while the rest idle (2 048 quadrotor instances: 64 of 148
-// SMs, 0.73 ms per line search).  Here every (role, 32 instances) pair is its own CTA, so the block scheduler spreads the
-// 6 B / 32 warps over all SMs; the candidates' costs go through a small global scratch ([6][B] doubles + flags) to the
-// second launch, which takes the reference's decision (first alpha with J_new < J_old, solver.py:262-284), lets another
-// winner than alpha = 1 roll once more with stores, and copies the old trajectory of rejected instances warp-cooperatively.
-// Same candidate function, same decision: X_new, U_new, J and `accepted` are bit-identical to the other two kernels.
-template <int SYS>
-__global__ void __launch_bounds__(32) k_linesearch_cand(int B, DynParams2 prm, int N, const double* X, const double* U, DdpConst c,
-                                                        const int* T, const double* k_list, const double* K_list, const int* ok,
-                                                        const int* done, double* Xn, double* Un, double* cJ, int* cOk) {
-    constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
-    const int lane = threadIdx.x, role = blockIdx.y;
-    const int b = blockIdx.x * 32 + lane;
-    if (b >= B) return;
-    double J = HUGE_VAL;
-    bool cand_ok = false;
-    if (!((done && done[b]) || (ok && !ok[b]))) {
-        const ddp::CostConst cc = cost_const<n>(c, b);
-        const double* Xb = X + (size_t)b * (N + 1) * n;
-        const double* Ub = U + (size_t)b * N * m;
-        const double* kb = k_list + (size_t)b * N * m;
-        const double* Kb = K_list + (size_t)b * N * m * n;
-        const int Tb = horizon_of(T, b, N);
-        const double alpha = role == 0 ? 1.0 : role == 1 ? 0.5 : role == 2 ? 0.25 : role == 3 ? 0.1 : 0.05;
-        if (role == 0) cand_ok = ddp::linesearch_candidate<SYS, true>(prm.p, N, Xb, Ub, cc, Tb, kb, Kb, alpha, Xn + (size_t)b * (N + 1) * n,
-                                                                      Un + (size_t)b * N * m, &J);
-        else if (role < 5) cand_ok = ddp::linesearch_candidate<SYS, false>(prm.p, N, Xb, Ub, cc, Tb, kb, Kb, alpha, nullptr, nullptr, &J);
-        else J = ddp::cost_timeopt_true<n, m>(Xb, Ub, cc, Tb);
-    }
-    cJ[(size_t)role * B + b] = J;
-    cOk[(size_t)role * B + b] = cand_ok ? 1 : 0;
-}
-template <int SYS>
-__global__ void __launch_bounds__(32) k_linesearch_pick(int B, DynParams2 prm, int N, const double* X, const double* U, DdpConst c,
-                                                        const int* T, const double* k_list, const double* K_list, const int* ok,
-                                                        const int* done, const double* cJ, const int* cOk, double* Xn, double* Un,
-                                                        double* Jn, int* acc) {
-    constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
-    const int lane = threadIdx.x;
-    const int b_raw = blockIdx.x * 32 + lane;
-    const bool valid = b_raw < B;
-    const int b = valid ? b_raw : B - 1;
-    const bool active = valid && !((done && done[b]) || (ok && !ok[b]));
-    if (valid) acc[b] = 0;
-    bool copy_old = false;
-    if (active) {
-        const double J_old = cJ[(size_t)5 * B + b];
-        int winner = -1;
-#pragma unroll
-        for (int r = 4; r >= 0; --r)
-            if (cOk[(size_t)r * B + b] && cJ[(size_t)r * B + b] < J_old) winner = r;
-        if (winner > 0) {                                                        // roll the winner once more, with stores
-            const ddp::CostConst cc = cost_const<n>(c, b);
-            const double alpha = winner == 1 ? 0.5 : winner == 2 ? 0.25 : winner == 3 ? 0.1 : 0.05;
-            double J = HUGE_VAL;
-            ddp::linesearch_candidate<SYS, true>(prm.p, N, X + (size_t)b * (N + 1) * n, U + (size_t)b * N * m, cc, horizon_of(T, b, N),
-                                                 k_list + (size_t)b * N * m, K_list + (size_t)b * N * m * n, alpha,
-                                                 Xn + (size_t)b * (N + 1) * n, Un + (size_t)b * N * m, &J);
-            Jn[b] = J; acc[b] = 1;
-        } else if (winner == 0) {
-            Jn[b] = cJ[b]; acc[b] = 1;                                           // alpha = 1 stored its candidate while rolling
-        } else {
-            Jn[b] = J_old;
-            copy_old = true;                                                     // no improving step: X_new, U_new <- X, U
-        }
-    }
-    unsigned todo = __ballot_sync(0xffffffffu, copy_old);
-    while (todo) {
-        const int l = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const size_t bb = (size_t)blockIdx.x * 32 + l;
-        for (size_t i = lane; i < (size_t)(N + 1) * n; i += 32) Xn[bb * (N + 1) * n + i] = X[bb * (N + 1) * n + i];
-        for (size_t i = lane; i < (size_t)N * m; i += 32) Un[bb * N * m + i] = U[bb * N * m + i];
-    }
-}
-
-int stream_alloc(void** ptr, size_t bytes, cudaStream_t st, const char* what);
-void stream_free(void* ptr, cudaStream_t st);
-// line-search kernel: 0 the five step sizes side by side as single-warp CTAs spread over the SMs (default), 1 one thread per
-// problem trying them in turn, 2 the six roles of 32 instances in one CTA (test / A-B hook; identical bits)
-int g_linesearch_variant = getenv("HOP_LS_VARIANT") ? atoi(getenv("HOP_LS_VARIANT")) : (getenv("HOP_LS_SERIAL") && atoi(getenv("HOP_LS_SERIAL")) ? 1 : 0);
+// line-search kernel: 0 step sizes side by side (default), 1 one thread per problem trying them in turn (test / A-B hook;
+// identical bits)
+int g_linesearch_variant = getenv("HOP_LS_SERIAL") ? atoi(getenv("HOP_LS_SERIAL")) : 0;
 template <int SYS>
 static int launch_linesearch(int B, const DynParams2& prm, int N, const double* X, const double* U, const DdpConst& c, const int* T,
                              const double* kl, const double* Kl, const int* ok, const int* done, double* Xn, double* Un,
@@ -291,27 +211,12 @@ static int launch_linesearch(int B, const DynParams2& prm, int N, const double* 
     // solve: Segway B = 25 7.6 -> 2.5 ms, Cartpole B = 4096 67.5 -> 16.1 ms, Quadrotor B = 16384 22.1 -> 28.3 ms (130
     // registers: the machine holds ~75k such threads, 16384 x 6 no longer fit in one wave).  $HOP_LS_PAR_MAX_BATCH overrides.
     static const long par_max = getenv("HOP_LS_PAR_MAX_BATCH") ? atol(getenv("HOP_LS_PAR_MAX_BATCH")) : 8192;
-    if (g_linesearch_variant == 1 || B > par_max) {
+    if (g_linesearch_variant != 0 || B > par_max) {
         k_linesearch<SYS><<<(B + threads - 1) / threads, threads, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, done, Xn, Un, Jn, acc);
         return check_launch("k_linesearch");
     }
-    if (g_linesearch_variant == 2) {
-        k_linesearch_par<SYS><<<(B + 31) / 32, kLsRoles * 32, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, done, Xn, Un, Jn, acc);
-        return check_launch("k_linesearch_par");
-    }
-    void* scratch = nullptr;
-    const size_t nJ = sizeof(double) * (size_t)kLsRoles * B;
-    if (int rc = stream_alloc(&scratch, nJ + sizeof(int) * (size_t)kLsRoles * B, st, "cudaMallocAsync(line-search candidates)")) return rc;
-    double* cJ = (double*)scratch;
-    int* cOk = (int*)((char*)scratch + nJ);
-    k_linesearch_cand<SYS><<<dim3((B + 31) / 32, kLsRoles), 32, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, done, Xn, Un, cJ, cOk);
-    int rc = check_launch("k_linesearch_cand");
-    if (!rc) {
-        k_linesearch_pick<SYS><<<(B + 31) / 32, 32, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, done, cJ, cOk, Xn, Un, Jn, acc);
-        rc = check_launch("k_linesearch_pick");
-    }
-    stream_free(scratch, st);
-    return rc;
+    k_linesearch_par<SYS><<<(B + 31) / 32, kLsRoles * 32, 0, st>>>(B, prm, N, X, U, c, T, kl, Kl, ok, done, Xn, Un, Jn, acc);
+    return check_launch("k_linesearch_par");
 }
 
 // After a selection: an instance whose selection raised in the reference (status low byte != 0) stops
