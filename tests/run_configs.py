@@ -203,7 +203,7 @@ def cfg3(args, dev):
 
 def cfg4(args, dev):
     from _common import s1_x0
-    B = 1024 if args.small else 16384
+    B = int(os.environ.get("HOP_CFG4_B", "0")) or (1024 if args.small else 16384)    # HOP_CFG4_B: per-rank load of a strong-scaled run on one GPU
     _ddp("Quadrotor", s1_x0(B, seed=4), dev, 12, 1024, f"Quadrotor 12-DOF HOP-DDP, N=128, {B} initial states, max-iter 12, "
          "batch sharded over the ranks", 4, N=128)
 
