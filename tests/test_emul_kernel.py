@@ -295,3 +295,24 @@ def test_emulated_diagonal_block_fast_path_is_bit_identical_to_the_sweep(d, m, N
     Jo, sto = O.propagator_batch(A, B, Q, Rinv, z0, QT)
     assert a[3][0] == 0 and a[3][1] == 0 and a[3][2] & 0x100 and not sto.any()
     assert rel(a[0], Jo) <= 1e-9
+
+
+def test_emulated_pipelined_fast_kernel_with_a_dense_running_weight():
+    """The pipelined FAST body forms F_k^T = A_k E_k in closed form (column scaling + rank-1 term) when K = (sym(Q) + q_reg I +
+    eps I)^-1 is diagonal -- every reference case -- and through the tensor pipe otherwise.  Both branches against the oracle on
+    the quadrotor nominal trajectory: the case's diagonal Q, and a dense SPD Q (same problem otherwise)."""
+    g = golden("case_Quadrotor")
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case("Quadrotor", N=128)
+    T_max = 56
+    rng = np.random.default_rng(12)
+    Mx = rng.standard_normal((12, 12))
+    Qd = Q + 0.05 * (Mx @ Mx.T) / 12.0
+    for Qc in (Q, Qd):
+        J, T, Js, st = emul.select_fused(g["A_fwd"][None], g["B_fwd"][None], g["a_resid"][None], g["X"][None], g["U"][None],
+                                         xg[None], np.array([w]), u_ref, Qc, R, O.as_terminal_weight(alpha, 12),
+                                         O.wrap_mask(wrap_idx), T_min, T_max, mma=True, mode=5)
+        Jo, To = O.select_fused(g["A_fwd"], g["B_fwd"], g["X"], g["U"], xg, u_ref, Qc, R, alpha, w, T_min, T_max, wrap_idx)
+        assert (st[0] & 0xFF) == 0
+        assert rel(J[0, T_min - 1:T_max], Jo[T_min - 1:T_max]) <= 1e-6
+        assert abs(J[0, To - 1] - Jo[To - 1]) <= 5e-8 * abs(Jo[To - 1])
+        assert int(T[0]) == To or abs(Jo[int(T[0]) - 1] - Jo[To - 1]) <= 1e-7 * abs(Jo[To - 1])

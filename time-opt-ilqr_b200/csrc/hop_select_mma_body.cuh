@@ -193,6 +193,14 @@ HOP_DEVICE void fast_const_fill_warp(const FusedArgs& p, double* cst, double* sc
         }
     }
     if (L.lane == 0) cst[XC::FLAG] = (st != 0) ? 1.0 : 0.0;   // ladder needed: the closed forms do not apply
+    // FLAG + 1: K = (Qs + eps I)^-1 is DIAGONAL (a diagonal running weight Q, as in every reference case): the stage product
+    // A_k E_k then splits into a column scaling and a rank-1 term (hop_select_pipe_body.cuh)
+    simt::sync();
+    bool dg = true;
+    for (int i = L.lane; i < n * n; i += 32)
+        if (i / n != i % n) dg = dg && (cst[XC::KQ + i] == 0.0);
+    dg = simt::all(dg);
+    if (L.lane == 0) cst[XC::FLAG + 1] = dg ? 1.0 : 0.0;
 }
 
 // Last LDL^T pivot of (S + eps I) by forward elimination (no back-substitution).  ok &= all pivots > 0.

@@ -555,6 +555,33 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
             for (int s = 0; s < 2; ++s) yc[J][s] = Y[L.col(J, s)];
         HOP_FOR_ELEMS(I, J, s) E.v[I][J][s] = fma(yr[I] * yc[J][s], rs, KF[((I * 2 + J) * 2 + s) * 32]);
     };
+    // F_k^T = A_k E_k without the tensor pipe when K is diagonal:  E = diag(K, 0) + rs yx yx^T  (yx = [y ; -1 ; 0])  gives
+    //   A E = A diag(K, 0) + rs (A yx) yx^T :  a column scaling and a rank-1 term -- 30 FP64 instructions (60 pipe clocks)
+    // instead of 12 DMMAs + the rank-1 last column (208 clocks), and E_k itself is never formed.
+    const bool kdiag = (cst[XC::FLAG + 1] != 0.0);
+    auto ft_closed = [&](Mat& Ft, const Mat& A, const double* Y, double rs) {
+        double yc[2][2], kd[2][2], u[2];
+#pragma unroll
+        for (int J = 0; J < 2; ++J)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int c = L.col(J, s);
+                yc[J][s] = Y[c];
+                kd[J][s] = (c < n) ? cst[XC::KQ + c * n + c] : 0.0;
+            }
+#pragma unroll
+        for (int I = 0; I < 2; ++I) {
+            double a = 0.0;
+#pragma unroll
+            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                for (int s = 0; s < 2; ++s) a = fma(A.v[I][J][s], yc[J][s], a);
+            a += simt::shfl_xor(a, 1, 32);
+            a += simt::shfl_xor(a, 2, 32);                                      // (A yx)_row: the four lanes of a row hold 4 columns each
+            u[I] = a * rs;
+        }
+        HOP_FOR_ELEMS(I, J, s) Ft.v[I][J][s] = fma(u[I], yc[J][s], A.v[I][J][s] * kd[J][s]);
+    };
     auto load_AB = [&](const double* stg, const double* DU, Mat& A, Mat& Bm) {
         const double* Ak = stg + oA;
         const double* Bk = stg + oB;
@@ -675,15 +702,20 @@ HOP_DEVICE bool select_fused_pipe_body(const FusedArgs& p, int b, double* scratc
         // ---------------- prefix step k+1 (:57-75)
         simt::mbar_wait(bars + q1, (unsigned)(((k + 1) >> 1) & 1));
         {
-            Mat E, A, Bm, Ft, G;
-            closed_inverse(E, KF1, scratch + PS::YQ + q1 * 16, rsq);
+            Mat A, Bm, Ft, G;
             load_AB(stage0 + q1 * kStage, scratch + PS::DU + q1 * 8, A, Bm);
             double ft_r[2], ft_c[2][2], w_c[2][2];
-            mma_nt<NT, NT, KD, false>(Ft, A, E);                               // F_k^T = A_k E_k
-            if (R1) {
-                double r[2], c[2][2];
-                last_col_rows<D>(r, A, L); last_col_cols<D>(c, E, L);
-                rank1_add<false>(Ft, r, c);
+            if (kdiag) {
+                ft_closed(Ft, A, scratch + PS::YQ + q1 * 16, rsq);             // F_k^T = A_k E_k, closed form
+            } else {
+                Mat E;
+                closed_inverse(E, KF1, scratch + PS::YQ + q1 * 16, rsq);
+                mma_nt<NT, NT, KD, false>(Ft, A, E);                           // F_k^T = A_k E_k
+                if (R1) {
+                    double r[2], c[2][2];
+                    last_col_rows<D>(r, A, L); last_col_cols<D>(c, E, L);
+                    rank1_add<false>(Ft, r, c);
+                }
             }
             mma_nt<NT, NT, KD, false>(G, Ft, A);                               // (A_k E_k) A_k^T              (:61)
             if (R1) {
