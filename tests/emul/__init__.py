@@ -28,13 +28,13 @@ class FusedArgs(C.Structure):
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("simt_emul.cpp", "simt_emul.h", "emul_select.cpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("simt_emul.cpp", "simt_emul.h", "emul_select.cpp", "emul_ddp.cpp")]
     srcs += [os.path.join(_CSRC, f) for f in ("hop_select_core.cuh", "hop_select_body.cuh", "hop_simt.cuh", "hop_mma.cuh",
-                                              "hop_select_mma_body.cuh", "hop_select_pipe_body.cuh", "hop_select_scan_body.cuh", "hop_select_gpipe_body.cuh", "hop_select_tpp_body.cuh", "hop_select_epl_body.cuh", "hop_select_ref_body.cuh")]
+                                              "hop_select_mma_body.cuh", "hop_select_pipe_body.cuh", "hop_select_scan_body.cuh", "hop_select_gpipe_body.cuh", "hop_select_tpp_body.cuh", "hop_select_epl_body.cuh", "hop_select_ref_body.cuh", "hop_ddp_core.cuh", "hop_ddp_mma.cuh", "hop_dynamics.cuh")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-DHOP_HOST_EMUL", "-Wno-unknown-pragmas", "-I" + _HERE, "-I" + _CSRC, "-fPIC",
                                "-shared", "-o", _SO, os.path.join(_HERE, "simt_emul.cpp"),
-                               os.path.join(_HERE, "emul_select.cpp")])
+                               os.path.join(_HERE, "emul_select.cpp"), os.path.join(_HERE, "emul_ddp.cpp")])
     return _SO
 
 
@@ -100,3 +100,16 @@ def chol_inv_mma(A):
     rc = lib().emul_chol_inv_mma(d, _p(A), _p(X), C.byref(st))
     assert rc == 0, rc
     return X, st.value
+
+
+def backward_pass(A, Bm, X, U, xg, u_ref, Q, R, Qf, w, wrap_mask, T, lm, variant):
+    """solver.backward_pass_truncated of ONE (n, m) = (12, 4) instance through the emulated kernels (variant 2: one warp, the
+    reference's summation order; 3: matrix products as DMMA fragments).  Returns (k [T, m], K [T, m, n], ok, code)."""
+    A, Bm, X, U, xg, u_ref, Q, R, Qf = map(_d, (A, Bm, X, U, xg, u_ref, Q, R, Qf))
+    N, n = A.shape[0], A.shape[1]
+    m = Bm.shape[2]
+    k = np.zeros((N, m)); K = np.zeros((N, m, n)); ok = C.c_int(0)
+    rc = lib().emul_backward(n, m, int(variant), int(T), C.c_double(lm), _p(A), _p(Bm), _p(X), _p(U), _p(xg), _p(u_ref), _p(Q), _p(R),
+                             _p(Qf), C.c_double(w), C.c_uint(wrap_mask), _p(k), _p(K), C.byref(ok))
+    assert rc >= 0, f"emulated backward pass failed rc={rc}"
+    return k[:T], K[:T], bool(ok.value), rc

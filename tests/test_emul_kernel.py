@@ -316,3 +316,44 @@ def test_emulated_pipelined_fast_kernel_with_a_dense_running_weight():
         assert rel(J[0, T_min - 1:T_max], Jo[T_min - 1:T_max]) <= 1e-6
         assert abs(J[0, To - 1] - Jo[To - 1]) <= 5e-8 * abs(Jo[To - 1])
         assert int(T[0]) == To or abs(Jo[int(T[0]) - 1] - Jo[To - 1]) <= 1e-7 * abs(Jo[To - 1])
+
+
+@pytest.mark.parametrize("variant", ["lanes", "tpp", "mma", "pipe"])
+def test_emulated_gauss_jordan_kernels_treat_an_infinite_diagonal_as_non_finite_input(variant):
+    """utils.py:75 raises FloatingPointError on a non-finite chol_inv input before any attempt.  A +Inf diagonal entry used to
+    pass the pivot test of the Gauss-Jordan kernels (p = +Inf > 0, 1/p = 0) and come back as an 'inverse' with a zeroed
+    row; the pivot test now rejects +Inf, the finiteness check runs, and the status is the reference's (1)."""
+    d, m, N = (4, 2, 8) if variant in ("lanes", "tpp") else (13, 4, 8)
+    A, B, Q, R, z0, w, QT = s2_batch(range(2), d, m, N)
+    Rinv = np.stack([O.chol_inv(r) for r in R])
+    Q[1, 2] = np.diag(np.r_[np.inf, np.ones(d - 1)])
+    kw = {"lanes": {}, "tpp": {"tpp": True}, "mma": {"mma": True}, "pipe": {"pipe": True}}[variant]
+    J, T, Js, st = emul.select_generic(A, B, Q, Rinv, z0, QT, 1, N, **kw)
+    _, sto = O.propagator_batch(A, B, Q, Rinv, z0, QT)
+    assert sto[1] == 1 and (st[1] & 0xFF) == 1 and st[0] == 0
+
+
+@pytest.mark.parametrize("traj", ["nominal", "converged"])
+def test_emulated_tensor_pipe_backward_pass(traj):
+    """hop_ddp_mma.cuh (12 x 12 products of solver.backward_pass_truncated as DMMA fragments) on the host emulator: the ordered
+    warp kernel reproduces the oracle bit for bit, the tensor-pipe kernel stays within 1e-12 relative of it (FMA accumulation
+    in k-blocks instead of unfused left-to-right sums) and takes the same ok decision, also for a short horizon."""
+    g = golden("case_Quadrotor")
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = cases.make_case("Quadrotor", N=128)
+    Qf = O.as_terminal_weight(alpha, 12)
+    if traj == "nominal":
+        X, U, A, Bm, T = g["X"], g["U"], g["A_fwd"], g["B_fwd"], int(g["T0"])
+    else:
+        X, U = g["sol_X"], g["sol_U"]
+        A, Bm = O.linearize(F.hop_sys, F.hop_params, X, U)
+        T = int(g["sol_T_star"])
+    for Tq in (T, 3):
+        ko, Ko, oko = O.backward_pass(A, Bm, X, U, xg, u_ref, Q, R, alpha, Tq, 1e-3, wrap_idx)
+        k2, K2, ok2, rc2 = emul.backward_pass(A, Bm, X, U, xg, u_ref, Q, R, Qf, w, O.wrap_mask(wrap_idx), Tq, 1e-3, 2)
+        k3, K3, ok3, rc3 = emul.backward_pass(A, Bm, X, U, xg, u_ref, Q, R, Qf, w, O.wrap_mask(wrap_idx), Tq, 1e-3, 3)
+        assert oko and ok2 and ok3 and rc2 == 0 and rc3 == 0
+        assert np.array_equal(K2, Ko) and np.array_equal(k2, ko)
+        assert np.abs(K3 - K2).max() <= 1e-12 * np.abs(K2).max() and np.abs(k3 - k2).max() <= 1e-12 * np.abs(k2).max()
+    Xn = X.copy(); Xn[5, 3] = np.nan                                        # non-finite trajectory: ok = False in both
+    assert not emul.backward_pass(A, Bm, Xn, U, xg, u_ref, Q, R, Qf, w, O.wrap_mask(wrap_idx), T, 1e-3, 3)[2]
+    assert not emul.backward_pass(A, Bm, Xn, U, xg, u_ref, Q, R, Qf, w, O.wrap_mask(wrap_idx), T, 1e-3, 2)[2]

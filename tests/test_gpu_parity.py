@@ -515,8 +515,9 @@ def test_batched_hop_ddp_solve_matches_reference_golden(name, mode):
 
 @pytest.mark.parametrize("name", ["Quadrotor", "Segway_Balance", "DoubleIntegrator"])
 def test_warp_and_thread_backward_kernels_agree_bit_for_bit(name):
-    """backward_pass_truncated has two device mappings (one warp per problem, elements of every product spread over the
-    lanes; one thread per problem).  Same operation order per element => identical gains, flags and solves."""
+    """backward_pass_truncated has two device mappings in the reference's summation order (one warp per problem, elements of
+    every product spread over the lanes; one thread per problem).  Same operation order per element => identical gains, flags
+    and solves."""
     from hop import _cabi
     lib = _cabi.require_device()
     case = cases.make_case(name, N=128) if name == "Quadrotor" else cases.make_case(name)
@@ -525,13 +526,56 @@ def test_warp_and_thread_backward_kernels_agree_bit_for_bit(name):
     x0s = case[1][None] + 0.05 * rng.standard_normal((37, n))
     out = {}
     try:
-        for variant in (0, 1):
+        for variant in (2, 1):
             lib.hop_test_set_backward_variant(variant)
             out[variant] = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=4, use_central_diff=False, mode=api.MODE_FAST)
     finally:
         lib.hop_test_set_backward_variant(0)
     for key in ("X", "U", "J_hist", "T_hist", "n_hist", "T_star", "status"):
-        assert torch.equal(torch.nan_to_num(out[0][key].double(), nan=-1.0), torch.nan_to_num(out[1][key].double(), nan=-1.0)), key
+        assert torch.equal(torch.nan_to_num(out[2][key].double(), nan=-1.0), torch.nan_to_num(out[1][key].double(), nan=-1.0)), key
+
+
+def test_tensor_pipe_backward_kernel_against_the_ordered_kernel_and_the_reference():
+    """The quadrotor backward pass of FAST / GJ solves runs its 12 x 12 products on the FP64 tensor pipe (hop_ddp_mma.cuh): FMA
+    accumulation in k-blocks instead of the reference's unfused left-to-right sums.  Gains against the ordered kernel on the
+    same inputs (<= 1e-12 relative) and against the reference golden (<= 1e-9); whole solves: same T_hist, J_hist <= 1e-9.
+    HOP_MODE_EXACT solves and the stand-alone entry point keep the ordered kernel."""
+    from hop import _cabi
+    lib = _cabi.require_device()
+    g = golden("case_Quadrotor")
+    case = cases.make_case("Quadrotor", N=128)
+    T0 = int(g["T0"])
+    Bsz = 5
+    A = _t(np.stack([g["A_fwd"]] * Bsz)); Bm = _t(np.stack([g["B_fwd"]] * Bsz))
+    X = _t(np.stack([g["X"]] * Bsz)); U = _t(np.stack([g["U"]] * Bsz))
+    T = torch.tensor([T0, T0 - 7, T0 + 9, 1, T0], dtype=torch.int32)
+    res = {}
+    try:
+        for variant in (2, 3):
+            lib.hop_test_set_backward_variant(variant)
+            res[variant] = api.backward_linesearch_batched(case, A, Bm, X, U, T, 1e-3)
+    finally:
+        lib.hop_test_set_backward_variant(0)
+    assert res[3]["ok"].cpu().numpy().all() and torch.equal(res[3]["ok"], res[2]["ok"]) and torch.equal(res[3]["accepted"], res[2]["accepted"])
+    for key in ("k", "K"):
+        a, b = res[3][key].cpu().numpy(), res[2][key].cpu().numpy()
+        assert np.abs(a - b).max() <= 1e-12 * np.abs(b).max(), key
+    K = res[3]["K"].cpu().numpy()[0, :T0]
+    assert np.abs(K - g["K_list"]).max() <= 1e-9 * np.abs(g["K_list"]).max()                   # the reference itself
+    assert abs(float(res[3]["J_new"][0]) - float(g["J1"])) <= 1e-9 * abs(float(g["J1"]))
+    x0s = _t(s1_x0(48, seed=13))
+    sol = {}
+    try:
+        for variant in (2, 0):                                                             # 0: the default routing (tensor pipe here)
+            lib.hop_test_set_backward_variant(variant)
+            sol[variant] = api.ilqr_timeopt_batched(case, x0s, max_iter=8, use_central_diff=False, mode=api.MODE_FAST)
+    finally:
+        lib.hop_test_set_backward_variant(0)
+    assert torch.equal(sol[0]["n_hist"], sol[2]["n_hist"]) and torch.equal(sol[0]["T_hist"], sol[2]["T_hist"])
+    Ja, Jb = sol[0]["J_hist"].cpu().numpy(), sol[2]["J_hist"].cpu().numpy()
+    m_ = np.isfinite(Jb)
+    assert np.abs(Ja[m_] - Jb[m_]).max() <= 1e-9 * np.abs(Jb[m_]).max()
+    assert not torch.equal(sol[0]["J_hist"], sol[2]["J_hist"])                              # (it IS a different kernel)
 
 
 @pytest.mark.parametrize("d,m,N,T_max", [(12, 4, 48, 48), (13, 4, 64, 61), (13, 4, 8, 1)])

@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.environ.get("HOP_BUILD_OUT") or os.path.join(os.path.dirname(HERE), "hop", "libhop_b200.so")   # experiments: other name
 SRCS = ["hop_select.cu", "hop_select_ref.cu", "hop_select_tpp.cu", "hop_select_epl.cu", "hop_traj.cu", "hop_ddp.cu", "hop_util.cu", "hop_cabi.cu"]
-HDRS = ["hop_simt.cuh", "hop_select_ref_body.cuh", "hop_select_core.cuh", "hop_select_body.cuh", "hop_mma.cuh", "hop_select_mma_body.cuh", "hop_select_pipe_body.cuh", "hop_select_scan_body.cuh", "hop_select_gpipe_body.cuh", "hop_select_tpp_body.cuh", "hop_select_epl_body.cuh", "hop_dynamics.cuh", "hop_ddp_core.cuh", "hop_common.cuh",
+HDRS = ["hop_simt.cuh", "hop_select_ref_body.cuh", "hop_select_core.cuh", "hop_select_body.cuh", "hop_mma.cuh", "hop_select_mma_body.cuh", "hop_select_pipe_body.cuh", "hop_select_scan_body.cuh", "hop_select_gpipe_body.cuh", "hop_select_tpp_body.cuh", "hop_select_epl_body.cuh", "hop_dynamics.cuh", "hop_ddp_core.cuh", "hop_ddp_mma.cuh", "hop_common.cuh",
         os.path.join("..", "..", "include", "hop_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

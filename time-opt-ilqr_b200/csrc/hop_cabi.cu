@@ -31,7 +31,7 @@ struct DdpConst {
 int dispatch_backward_linesearch(int sys, int B, const double* params_host, int N, const double* A, const double* Bm,
                                  const double* X, const double* U, const DdpConst& c, const int* T, const double* lm,
                                  const int* done, double* kl, double* Kl, int* ok, int* bw_err, double* Xn, double* Un,
-                                 double* Jn, int* acc, cudaEvent_t mid, cudaStream_t st);
+                                 double* Jn, int* acc, bool ordered, cudaEvent_t mid, cudaStream_t st);
 int dispatch_bruteforce(int n, int m, int B, int N, int T_max, const double* A, const double* Bm, const double* X, const double* U,
                         long ustride, const DdpConst& c, double lm, double* J_out, int* status, cudaStream_t st);
 int dispatch_cost(int n, int m, int B, int N, const double* X, const double* U, const DdpConst& c, const int* T, double* J,
@@ -302,8 +302,9 @@ int hop_backward_linesearch_f64(int B, int sys, const double* params_host, int N
         return HOP_E_BADARG;
     }
     DdpConst c{xg, w, u_ref, Q, R, Qf, wrap_mask};
+    // the stand-alone entry point is the API-parity path: the reference's summation order
     return dispatch_backward_linesearch(sys, B, params_host, N, A, Bm, X, U, c, T_star, lm, nullptr, k_out, K_out, ok_out,
-                                        err_out, X_new, U_new, J_new, accepted, nullptr, (cudaStream_t)stream);
+                                        err_out, X_new, U_new, J_new, accepted, true, nullptr, (cudaStream_t)stream);
 }
 
 int hop_linesearch_f64(int B, int sys, const double* params_host, int N, const double* X, const double* U, const double* xg,
@@ -424,7 +425,7 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T
     HOP_TRY(launch_after_select(B, ws.sel_status, ws.done, status, st));
     mark(2);
     HOP_TRY(dispatch_backward_linesearch(sys, B, params_host, N, ws.A, ws.Bm, X, U, c, ws.T_sel, ws.lm, ws.done, ws.kl, ws.Kl,
-                                         ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, timers_host ? ev(3) : nullptr, st));   // :541-551
+                                         ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, mode == HOP_MODE_EXACT, timers_host ? ev(3) : nullptr, st));   // :541-551
     HOP_TRY(launch_warm_update(B, cap, ws.T_sel, ws.ok, ws.acc, ws.Jn, ws.bw_err, ws.done, ws.T_bar, J_hist, T_hist, n_hist,
                                ws.copy, status, st));
     HOP_TRY(launch_copy_accepted(B, (size_t)(N + 1) * n, (size_t)N * m, ws.copy, ws.Xn, ws.Un, X, U, st));
@@ -444,7 +445,7 @@ int hop_ilqr_timeopt_f64(int B, int sys, const double* params_host, int N, int T
         HOP_TRY(launch_after_select(B, ws.sel_status, ws.done, status, st));
         mark(2);
         HOP_TRY(dispatch_backward_linesearch(sys, B, params_host, N, ws.A, ws.Bm, X, U, c, ws.T_sel, ws.lm, ws.done, ws.kl,
-                                             ws.Kl, ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, timers_host ? ev(3) : nullptr, st)); // :594-604
+                                             ws.Kl, ws.ok, ws.bw_err, ws.Xn, ws.Un, ws.Jn, ws.acc, mode == HOP_MODE_EXACT, timers_host ? ev(3) : nullptr, st)); // :594-604
         HOP_TRY(report_cuda(cudaMemsetAsync(ws.n_active + slot, 0, sizeof(int), st), "memset n_active"));
         HOP_TRY(launch_ddp_update(B, cap, ws.T_sel, ws.ok, ws.acc, ws.Jn, ws.bw_err, ws.done, ws.T_bar, ws.lm, J_hist, T_hist,
                                   n_hist, ws.copy, status, ws.n_active + slot, st));                      // :735-748
@@ -491,7 +492,7 @@ __global__ void k_probe_dfma(int iters, double seed, double* sink) {
 
 int hop_test_set_backward_variant(int variant) {
     const int old = g_backward_variant;
-    if (variant == 0 || variant == 1) g_backward_variant = variant;
+    if (variant >= 0 && variant <= 3) g_backward_variant = variant;
     return old;
 }
 

@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "hop_ddp_core.cuh"
+#include "hop_ddp_mma.cuh"
 #include "../../include/hop_b200.h"
 
 namespace hop {
@@ -64,8 +65,11 @@ __global__ void k_backward(int B, int N, const double* A, const double* Bm, cons
     if (err) err[b] = rc;
 }
 
-// backward-pass kernel: 0 warp per problem (default), 1 thread per problem (test / A-B hook; identical bits)
-int g_backward_variant = getenv("HOP_BW_THREAD") ? atoi(getenv("HOP_BW_THREAD")) : 0;
+// backward-pass kernel: 0 [default] = the tensor-pipe kernel (backward_pass_mma) for n > 8 unless the caller asks for the
+// reference's summation order (HOP_MODE_EXACT solves, the stand-alone entry point), else the warp kernel; 1 = one thread per
+// problem; 2 = one warp per problem, ordered sums (1 and 2: identical bits); 3 = tensor-pipe kernel wherever it is instantiated.
+// $HOP_BW_VARIANT / hop_test_set_backward_variant ($HOP_BW_THREAD=1 is the old spelling of variant 1)
+int g_backward_variant = getenv("HOP_BW_VARIANT") ? atoi(getenv("HOP_BW_VARIANT")) : (getenv("HOP_BW_THREAD") && atoi(getenv("HOP_BW_THREAD")) ? 1 : 0);
 
 // one warp per problem (backward_pass_warp), kBwWarps problems per CTA
 constexpr int kBwWarps = 4;
@@ -83,6 +87,27 @@ __global__ void __launch_bounds__(kBwWarps * 32) k_backward_warp(int B, int N, c
     const int rc = ddp::backward_pass_warp<n, m>(A + (size_t)b * N * n * n, Bm + (size_t)b * N * n * m, X + (size_t)b * (N + 1) * n,
                                                  U + (size_t)b * N * m, cc, horizon_of(T, b, N), lm[b], k_out + (size_t)b * N * m,
                                                  K_out + (size_t)b * N * m * n, &okb, smem + (size_t)warp * ddp::BwSmem<n, m>::SIZE, lane);
+    if (lane == 0) {
+        ok[b] = (rc == 0) ? okb : 0;
+        if (err) err[b] = rc;
+    }
+}
+
+// same grid, matrix products on the FP64 tensor pipe (hop_ddp_mma.cuh)
+template <int n, int m>
+__global__ void __launch_bounds__(kBwWarps * 32) k_backward_mma(int B, int N, const double* A, const double* Bm, const double* X,
+                                                                const double* U, DdpConst c, const int* T, const double* lm,
+                                                                const int* done, double* k_out, double* K_out, int* ok, int* err) {
+    __shared__ __align__(16) double smem[kBwWarps * ddp::BwSmem<n, m>::SIZE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kBwWarps + warp;
+    if (b >= B) return;
+    if (done && done[b]) { if (lane == 0) ok[b] = 0; return; }
+    const ddp::CostConst cc = cost_const<n>(c, b);
+    int okb = 0;
+    const int rc = ddp::backward_pass_mma<n, m>(A + (size_t)b * N * n * n, Bm + (size_t)b * N * n * m, X + (size_t)b * (N + 1) * n,
+                                                U + (size_t)b * N * m, cc, horizon_of(T, b, N), lm[b], k_out + (size_t)b * N * m,
+                                                K_out + (size_t)b * N * m * n, &okb, smem + (size_t)warp * ddp::BwSmem<n, m>::SIZE, lane);
     if (lane == 0) {
         ok[b] = (rc == 0) ? okb : 0;
         if (err) err[b] = rc;
@@ -317,13 +342,16 @@ template <int SYS>
 static int ddp_backward_linesearch(int B, const DynParams2& prm, int N, const double* A, const double* Bm, const double* X,
                                    const double* U, const DdpConst& c, const int* T, const double* lm, const int* done,
                                    double* kl, double* Kl, int* ok, int* bw_err, double* Xn, double* Un, double* Jn, int* acc,
-                                   cudaEvent_t mid, cudaStream_t st) {
+                                   bool ordered, cudaEvent_t mid, cudaStream_t st) {
     constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
     const int threads = 64;
-    // A/B + test switch: HOP_BW_THREAD=1 selects the thread-per-problem kernel (bit-identical results)
-    const bool per_thread = g_backward_variant != 0;
-    if (per_thread) k_backward<n, m><<<grid1(B, threads), threads, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
-    else k_backward_warp<n, m><<<grid1(B, kBwWarps), kBwWarps * 32, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
+    const int v = g_backward_variant;
+    bool use_mma = false;
+    if constexpr (n > 8) use_mma = (v == 3) || (v == 0 && !ordered);
+    if (v == 1) k_backward<n, m><<<grid1(B, threads), threads, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
+    else if (use_mma) {
+        if constexpr (n > 8) k_backward_mma<n, m><<<grid1(B, kBwWarps), kBwWarps * 32, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
+    } else k_backward_warp<n, m><<<grid1(B, kBwWarps), kBwWarps * 32, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
     if (int rc = check_launch("k_backward")) return rc;
     if (mid) cudaEventRecord(mid, st);
     return launch_linesearch<SYS>(B, prm, N, X, U, c, T, kl, Kl, ok, done, Xn, Un, Jn, acc, st);
@@ -332,14 +360,14 @@ static int ddp_backward_linesearch(int B, const DynParams2& prm, int N, const do
 int dispatch_backward_linesearch(int sys, int B, const double* params_host, int N, const double* A, const double* Bm,
                                  const double* X, const double* U, const DdpConst& c, const int* T, const double* lm,
                                  const int* done, double* kl, double* Kl, int* ok, int* bw_err, double* Xn, double* Un,
-                                 double* Jn, int* acc, cudaEvent_t mid, cudaStream_t st) {
+                                 double* Jn, int* acc, bool ordered, cudaEvent_t mid, cudaStream_t st) {
     DynParams2 prm;
     for (int i = 0; i < HOP_NPARAMS; ++i) prm.p[i] = params_host[i];
     switch (sys) {
-        case 0: return ddp_backward_linesearch<0>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, mid, st);
-        case 1: return ddp_backward_linesearch<1>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, mid, st);
-        case 2: return ddp_backward_linesearch<2>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, mid, st);
-        case 3: return ddp_backward_linesearch<3>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, mid, st);
+        case 0: return ddp_backward_linesearch<0>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, ordered, mid, st);
+        case 1: return ddp_backward_linesearch<1>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, ordered, mid, st);
+        case 2: return ddp_backward_linesearch<2>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, ordered, mid, st);
+        case 3: return ddp_backward_linesearch<3>(B, prm, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err, Xn, Un, Jn, acc, ordered, mid, st);
     }
     set_last_error("unknown system id");
     return HOP_E_BADARG;

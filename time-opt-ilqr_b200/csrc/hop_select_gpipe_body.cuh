@@ -206,7 +206,7 @@ HOP_DEVICE void diagonal_inverse(Mat& S, const LaneGeo& L, int& signs) {
         const int R = L.row(I);
         if (R == L.col(J, s) && R < D) {
             const double p = S.v[I][J][s];
-            signs |= hi_word(p);
+            signs |= pivot_bad(p) ? (int)0x80000000 : 0;                         // <= 0, NaN, +inf: the sequential body decides
             S.v[I][J][s] = pivot_rcp3(p);
         }
     }

@@ -99,7 +99,7 @@ HOP_DEVICE double pivot_rcp3(double p) {
     const double t = fma(e, e, e);
     return fma(r, t, r);
 #else
-    return 1.0 / p;
+    return (p - p == 0.0) ? 1.0 / p : (p - p);   // the device sequence turns +-inf and NaN into NaN (fma(-inf, 0, 1))
 #endif
 }
 
