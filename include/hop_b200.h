@@ -230,7 +230,7 @@ int hop_test_set_fused_small_variant(int variant);
  * per problem trying them in turn; identical bits.  Returns the previous value. */
 int hop_test_set_linesearch_variant(int variant);
 /* Test hook: backward-pass kernel.  0 [default] = matrix products on the FP64 tensor pipe for n > 8 (quadrotor) in FAST / GJ
- * solves, one warp per problem with the reference's summation order otherwise (small systems, HOP_MODE_EXACT solves, the
+ * solves of at least 4 096 instances, one warp per problem with the reference's summation order otherwise (small systems, HOP_MODE_EXACT solves, the
  * stand-alone entry point); 1 = one thread per problem; 2 = one warp per problem, ordered sums (1 and 2: identical bits);
  * 3 = tensor-pipe kernel wherever it is instantiated (gains within 1e-12 relative of 2).  Returns the previous value. */
 int hop_test_set_backward_variant(int variant);

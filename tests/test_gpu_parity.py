@@ -566,16 +566,16 @@ def test_tensor_pipe_backward_kernel_against_the_ordered_kernel_and_the_referenc
     x0s = _t(s1_x0(48, seed=13))
     sol = {}
     try:
-        for variant in (2, 0):                                                             # 0: the default routing (tensor pipe here)
+        for variant in (2, 3):
             lib.hop_test_set_backward_variant(variant)
             sol[variant] = api.ilqr_timeopt_batched(case, x0s, max_iter=8, use_central_diff=False, mode=api.MODE_FAST)
     finally:
         lib.hop_test_set_backward_variant(0)
-    assert torch.equal(sol[0]["n_hist"], sol[2]["n_hist"]) and torch.equal(sol[0]["T_hist"], sol[2]["T_hist"])
-    Ja, Jb = sol[0]["J_hist"].cpu().numpy(), sol[2]["J_hist"].cpu().numpy()
+    assert torch.equal(sol[3]["n_hist"], sol[2]["n_hist"]) and torch.equal(sol[3]["T_hist"], sol[2]["T_hist"])
+    Ja, Jb = sol[3]["J_hist"].cpu().numpy(), sol[2]["J_hist"].cpu().numpy()
     m_ = np.isfinite(Jb)
     assert np.abs(Ja[m_] - Jb[m_]).max() <= 1e-9 * np.abs(Jb[m_]).max()
-    assert not torch.equal(sol[0]["J_hist"], sol[2]["J_hist"])                              # (it IS a different kernel)
+    assert not torch.equal(sol[3]["J_hist"], sol[2]["J_hist"])                              # (it IS a different kernel)
 
 
 @pytest.mark.parametrize("d,m,N,T_max", [(12, 4, 48, 48), (13, 4, 64, 61), (13, 4, 8, 1)])

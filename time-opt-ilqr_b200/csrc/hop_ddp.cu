@@ -347,7 +347,10 @@ static int ddp_backward_linesearch(int B, const DynParams2& prm, int N, const do
     const int threads = 64;
     const int v = g_backward_variant;
     bool use_mma = false;
-    if constexpr (n > 8) use_mma = (v == 3) || (v == 0 && !ordered);
+    // measured on B200 (quadrotor, 12 iterations): backward phase 42.9 -> 37.6 ms at 16 384 instances, 7.06 -> 7.60 ms at 2 048
+    // (few instances: the step is bound by the latency of the m x m Cholesky ladder and the vector recursions, which both
+    // kernels share, and the fragment loads lengthen that chain) => the tensor-pipe kernel from 4 096 instances on
+    if constexpr (n > 8) use_mma = (v == 3) || (v == 0 && !ordered && B >= 4096);
     if (v == 1) k_backward<n, m><<<grid1(B, threads), threads, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
     else if (use_mma) {
         if constexpr (n > 8) k_backward_mma<n, m><<<grid1(B, kBwWarps), kBwWarps * 32, 0, st>>>(B, N, A, Bm, X, U, c, T, lm, done, kl, Kl, ok, bw_err);
