@@ -336,17 +336,11 @@ int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st) {
     if (n == 4 && m == 1) return launch_fused<5, 1, 8>(p, st);
     if (n == 12 && m == 4) {
         if (p.mode != HOP_MODE_FAST) return launch_fused_mma<13, 4, 0>(p, st);
-        // A/B switches (all variants compute the same function): HOP_FAST_SEQ=1 sequential sweep, HOP_PIPE_UNROLL=1 unrolled
-        // pipelined sweep, HOP_PIPE_SHFL=1 looped sweep with the shuffle exchange, HOP_PIPE_U2=0 one pivot per loop trip;
-        // default: shared-memory exchange, two pivots per trip, high-word zeroing
+        // A/B switch: HOP_FAST_SEQ=1 runs the sequential FAST sweep (the pipelined kernel's cold path) for the whole batch.  The
+        // earlier schedules of the pipelined sweep (unrolled / looped with the shuffle exchange / one pivot per loop trip, template
+        // arguments 2..4) are no longer instantiated in the library; tests/emul still runs them as cross-checks of the same math.
         static const bool seq = getenv("HOP_FAST_SEQ") && atoi(getenv("HOP_FAST_SEQ")) != 0;
-        static const bool unrolled = getenv("HOP_PIPE_UNROLL") && atoi(getenv("HOP_PIPE_UNROLL")) != 0;
-        static const bool shfl = getenv("HOP_PIPE_SHFL") && atoi(getenv("HOP_PIPE_SHFL")) != 0;
         if (seq) return launch_fused_mma<13, 4, 1>(p, st);
-        if (unrolled) return launch_fused_mma<13, 4, 2>(p, st);
-        if (shfl) return launch_fused_mma<13, 4, 3>(p, st);
-        static const bool u1 = getenv("HOP_PIPE_U2") && atoi(getenv("HOP_PIPE_U2")) == 0;   // HOP_PIPE_U2=0: one pivot per loop trip
-        if (u1) return launch_fused_mma<13, 4, 4>(p, st);
         return launch_fused_mma<13, 4, 5>(p, st);
     }
     set_last_error("hop_select_fused_f64: (n, m) not instantiated; supported: (2,1) (4,1) (12,4)");
