@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import select_from_x0_batch
+from . import ilqr_timeopt_batch, select_from_x0_batch
 
 
 def _rel(a, b):
@@ -116,3 +116,38 @@ def census_from_x0(case, x0, J_gpu, T_gpu, nthreads=1, fp80_stride=8, max_listed
                       "instances": [int(b) for b in idx[ill][:max_listed]]},
         "mismatch_detail": (unexplained + listed)[:max_listed],
     }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# iterated solves (HOP-DDP): which instances have a T_hist that the reference computation itself reproduces?
+# ---------------------------------------------------------------------------------------------------------------------
+PERTURBATIONS = ("fp80_selection", "x0+1e-15", "x0-1e-15", "x0*(1+4e-16)", "x0*(1-4e-16)", "x0+3e-15")
+
+
+def same_history(p, q, b):
+    """T_hist of instance b identical in two result dicts (n_hist, T_hist)."""
+    return p["n_hist"][b] == q["n_hist"][b] and np.array_equal(p["T_hist"][b, :p["n_hist"][b]], q["T_hist"][b, :q["n_hist"][b]])
+
+
+def ddp_oracle_census(case, N, x0s, max_iter=12, nthreads=1):
+    """The fp64 oracle and six rounding-level perturbations of it on the same initial states (the selection sweep in x87
+    extended precision; x0 +- 1e-15; x0 (1 +- 4e-16); x0 + 3e-15).  Returns (oracle result, well [B] bool = T_hist identical
+    in all seven runs, {perturbation: fraction of instances whose T_hist it flips}, seconds of the unperturbed run)."""
+    import time
+    F, _x0, xg, u_ref, Q, R, alpha, w, _N, T_min, T_max, wrap_idx, _ = case
+    T_max = min(T_max, N)
+    x0s = np.ascontiguousarray(x0s, dtype=float)
+    kw = dict(max_iter=max_iter, use_central_diff=False, nthreads=nthreads)
+    a = lambda x: (F.hop_sys, F.hop_params, N, T_min, T_max, x, np.tile(u_ref, (N, 1)), xg, u_ref, Q, R, alpha, w, wrap_idx)  # noqa: E731
+    t0 = time.perf_counter()
+    o = ilqr_timeopt_batch(*a(x0s), **kw)
+    dt = time.perf_counter() - t0
+    variants = {"fp80_selection": ilqr_timeopt_batch(*a(x0s), f80_select=True, **kw),
+                "x0+1e-15": ilqr_timeopt_batch(*a(x0s + 1e-15), **kw), "x0-1e-15": ilqr_timeopt_batch(*a(x0s - 1e-15), **kw),
+                "x0*(1+4e-16)": ilqr_timeopt_batch(*a(x0s * (1.0 + 4e-16)), **kw),
+                "x0*(1-4e-16)": ilqr_timeopt_batch(*a(x0s * (1.0 - 4e-16)), **kw),
+                "x0+3e-15": ilqr_timeopt_batch(*a(x0s + 3e-15), **kw)}
+    B = len(x0s)
+    stable = {name: np.array([same_history(o, v, b) for b in range(B)]) for name, v in variants.items()}
+    well = np.logical_and.reduce(list(stable.values()))
+    return o, well, {name: float(1.0 - s_.mean()) for name, s_ in stable.items()}, dt

@@ -234,6 +234,47 @@ def gold_resid(B=4):
     save("resid_Quadrotor", **{k: (np.asarray(v, dtype=np.int64) if k == "T" else stack(v)) for k, v in out.items()})
 
 
+def _ddp_ref_one(arg):
+    name, x0 = arg
+    maker = quadrotor_128 if name == "Quadrotor" else CASES[name]
+    F, _x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = maker()
+    res = solver.ilqr_timeopt_ourmethod(F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, max_iter=12, S_window=20,
+                                        use_central_diff=False, wrap_idx=wrap_idx)
+    return np.asarray(res["T_hist"], dtype=np.int32), np.asarray(res["J_hist"], dtype=float), int(res["T_star"])
+
+
+def gold_ddp_batch():
+    """Full HOP-DDP solves of the REAL reference (solver.ilqr_timeopt_ourmethod, run_suite defaults: max_iter = 12, forward
+    differences) on sampled initial states: the configurations 2-4 of BASELINE.json at a size the reference finishes in
+    minutes -- Segway 25 trials (sigma .02, run_suite.py:73), Cartpole 48 instances (x0 ~ N(0, diag(.1,.1,.2,.2)^2), the
+    distribution tests/run_configs.py uses: the reference's own sigma is zero), Quadrotor N = 128 16 instances (sigma .4 on the
+    position).  Stored: x0, T_hist / J_hist (padded to 13), n_hist, T_star."""
+    import multiprocessing as mp
+    out = {}
+    jobs = []
+    rng = np.random.default_rng(2024)
+    x0s = {}
+    base = CASES["Segway_Balance"]()[1]
+    x0s["Segway_Balance"] = base[None] + 0.02 * rng.standard_normal((25, 4)); x0s["Segway_Balance"][0] = base
+    x0s["Cartpole_SwingUp"] = np.array([rng.normal(0, .1, 48), rng.normal(0, .1, 48), rng.normal(0, .2, 48), rng.normal(0, .2, 48)]).T
+    x0s["Cartpole_SwingUp"][0] = CASES["Cartpole_SwingUp"]()[1]
+    base = quadrotor_128()[1]
+    x0s["Quadrotor"] = base[None] + np.array([0.4, 0.4, 0.4] + [0.0] * 9)[None] * rng.standard_normal((16, 12))
+    for name, xs in x0s.items():
+        jobs += [(name, x) for x in xs]
+    with mp.Pool(os.cpu_count()) as pool:
+        res = pool.map(_ddp_ref_one, jobs, chunksize=1)
+    i = 0
+    for name, xs in x0s.items():
+        B = len(xs)
+        Th = np.zeros((B, 13), dtype=np.int32); Jh = np.full((B, 13), np.nan); nh = np.zeros(B, dtype=np.int32); Ts = np.zeros(B, dtype=np.int32)
+        for b in range(B):
+            T_hist, J_hist, T_star = res[i]; i += 1
+            nh[b] = len(T_hist); Th[b, :nh[b]] = T_hist; Jh[b, :nh[b]] = J_hist; Ts[b] = T_star
+        out.update({name + "_x0": xs, name + "_T_hist": Th, name + "_J_hist": Jh, name + "_n_hist": nh, name + "_T_star": Ts})
+    save("ddp_batch", **out)
+
+
 def s2_instance(seed, d, m, N):
     """Synthetic HOP-LQR generator S2 -- draw order: all A, all B, all Q, R, z0, w."""
     r = np.random.default_rng(seed)
@@ -292,6 +333,6 @@ def gold_signatures():
 
 if __name__ == "__main__":
     ALL = {"signatures": gold_signatures, "utils": gold_utils, "dynamics": gold_dynamics, "cases": gold_cases,
-           "s1_batch": gold_s1_batch, "s2": gold_s2, "s1_ref4096": gold_s1_ref4096, "resid": gold_resid}
+           "s1_batch": gold_s1_batch, "s2": gold_s2, "s1_ref4096": gold_s1_ref4096, "resid": gold_resid, "ddp_batch": gold_ddp_batch}
     for name in (sys.argv[1:] or list(ALL)):      # no arguments: everything (s1_ref4096 takes ~5 core-minutes)
         ALL[name]()

@@ -141,28 +141,12 @@ def ddp_census(case, Nn, x0s, max_iter, runs, dev):
     sin/cos differ from glibc's by <= 2 ulp; FAST also re-orders the selection arithmetic): its mismatch rate is reported
     next to the oracle's own flip rates, and its T_hist on the well-posed instances must be the oracle's.
     `runs` maps a label to a device result (n_hist, T_hist, J_hist, T_star); HOP_MODE_EXACT is always run here in addition."""
-    import oracle as O
+    from oracle import census
     from _common import rel
     from hop import api
-    F, x0, xg, u_ref, Q, R, alpha, w, _N, T_min, T_max, wrap_idx, _ = case
-    T_max = min(T_max, Nn)
     k = len(x0s)
     th = os.cpu_count() or 1
-    kw = dict(max_iter=max_iter, use_central_diff=False, nthreads=th)
-    a = lambda x: (F.hop_sys, F.hop_params, Nn, T_min, T_max, x, np.tile(u_ref, (Nn, 1)), xg, u_ref, Q, R, alpha, w, wrap_idx)  # noqa: E731
-    t0 = time.perf_counter()
-    o = O.ilqr_timeopt_batch(*a(x0s), **kw)
-    t_cpu = time.perf_counter() - t0
-    variants = {"fp80_selection": O.ilqr_timeopt_batch(*a(x0s), f80_select=True, **kw),
-                "x0+1e-15": O.ilqr_timeopt_batch(*a(x0s + 1e-15), **kw), "x0-1e-15": O.ilqr_timeopt_batch(*a(x0s - 1e-15), **kw),
-                "x0*(1+4e-16)": O.ilqr_timeopt_batch(*a(x0s * (1.0 + 4e-16)), **kw),
-                "x0*(1-4e-16)": O.ilqr_timeopt_batch(*a(x0s * (1.0 - 4e-16)), **kw),
-                "x0+3e-15": O.ilqr_timeopt_batch(*a(x0s + 3e-15), **kw)}
-
-    def same(p, q, b):
-        return p["n_hist"][b] == q["n_hist"][b] and np.array_equal(p["T_hist"][b, :p["n_hist"][b]], q["T_hist"][b, :q["n_hist"][b]])
-    stable = {name: np.array([same(o, v, b) for b in range(k)]) for name, v in variants.items()}
-    well = np.logical_and.reduce(list(stable.values()))
+    o, well, self_flip, t_cpu = census.ddp_oracle_census(case, Nn, x0s, max_iter, th)
     ex = api.ilqr_timeopt_batched(case, torch.as_tensor(x0s, device=dev), max_iter=max_iter, use_central_diff=False,
                                   mode=api.MODE_EXACT)
     runs = dict(runs, exact=(ex["n_hist"].cpu().numpy(), ex["T_hist"].cpu().numpy(), ex["J_hist"].cpu().numpy(),
@@ -170,7 +154,7 @@ def ddp_census(case, Nn, x0s, max_iter, runs, dev):
     out = {"checked": k, "well_posed": int(well.sum()),
            "well_posed_rule": "T_hist identical among the fp64 oracle and six rounding-level perturbations of it (fp80 selection "
                               "sweep; x0 +- 1e-15; x0 (1 +- 4e-16); x0 + 3e-15)",
-           "oracle_self_flip_rate": {name: float(1.0 - s_.mean()) for name, s_ in stable.items()},
+           "oracle_self_flip_rate": self_flip,
            "oracle_solves_per_s_all_host_threads": k / t_cpu, "host_threads": th}
     for label, (nh, Th, Jh, Ts) in runs.items():
         same_T = np.array([nh[b] == o["n_hist"][b] and np.array_equal(Th[b, :nh[b]], o["T_hist"][b, :o["n_hist"][b]]) for b in range(k)])

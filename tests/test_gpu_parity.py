@@ -797,3 +797,32 @@ def test_cartpole_batched_solve_against_the_oracle_on_identical_initial_states()
     # the reference's own run of the nominal instance (golden); the oracle itself is within |dT| <= 1 of it (tests/test_oracle.py)
     n0 = len(g["sol_T_hist"])
     assert int(r["n_hist"][0]) == n0 and np.abs(r["T_hist"].cpu().numpy()[0, :n0] - g["sol_T_hist"]).max() <= 1
+
+
+@pytest.mark.parametrize("name", ["Segway_Balance", "Cartpole_SwingUp", "Quadrotor"])
+@pytest.mark.parametrize("mode", [api.MODE_EXACT, api.MODE_FAST])
+def test_batched_hop_ddp_against_reference_solves_on_sampled_initial_states(name, mode):
+    """tests/golden/ddp_batch.npz (full solves of the REAL reference: Segway 25 trials, Cartpole 48, Quadrotor 16 instances) on
+    the device.  Same bar as tests/test_oracle.py applies to the oracle: on every instance that is well-posed by the oracle's
+    perturbation census T_hist is the reference's (Segway, Quadrotor; J_hist <= 1e-9); on the cartpole embedding the device's
+    distance to the reference stays within the oracle's own self-flip band and >= 85 % of the well-posed instances agree."""
+    from oracle import census
+    g = golden("ddp_batch")
+    case = cases.make_case(name, N=128) if name == "Quadrotor" else cases.make_case(name)
+    x0s = g[name + "_x0"]
+    B = len(x0s)
+    r = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=12, use_central_diff=False, mode=mode)
+    dev = {"n_hist": r["n_hist"].cpu().numpy(), "T_hist": r["T_hist"].cpu().numpy()}
+    Jh = r["J_hist"].cpu().numpy()
+    ref = {"n_hist": g[name + "_n_hist"], "T_hist": g[name + "_T_hist"]}
+    o, well, self_flip, _ = census.ddp_oracle_census(case, case[8], x0s, 12, nthreads=8)
+    same = np.array([census.same_history(dev, ref, b) for b in range(B)])
+    relJ = [rel(Jh[b, :dev["n_hist"][b]], g[name + "_J_hist"][b, :dev["n_hist"][b]]) for b in range(B) if same[b]]
+    assert not (r["status"].cpu().numpy() & 0xFF).any()
+    if name == "Cartpole_SwingUp":
+        assert 1.0 - same.mean() <= max(self_flip.values()) + 3.0 / B + 0.1, (same.sum(), self_flip)
+        assert (same & well).sum() >= 0.85 * well.sum()
+        assert max(relJ) <= 1e-6
+    else:
+        assert (same & well).sum() == well.sum(), (np.nonzero(well & ~same)[0], self_flip)
+        assert max(relJ) <= 1e-9
