@@ -91,19 +91,7 @@ HOP_DEVICE bool mat_all_finite(const Mat& M) {
 
 // 1/p for a pivot.  Device: MUFU.RCP64H seed + two Newton steps (<= 1 ulp; the IEEE-correct `1.0/p`
 // costs ~3x the instructions and sits on the critical path of every elimination step).
-HOP_DEVICE double pivot_rcp(double p) {
-#if defined(__CUDA_ARCH__)
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
-    double e = fma(-p, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-p, r, 1.0);
-    r = fma(r, e, r);
-    return r;
-#else
-    return 1.0 / p;
-#endif
-}
+HOP_DEVICE double pivot_rcp(double p) { return simt::rcp_newton(p); }
 
 // One in-place Gauss-Jordan inversion attempt of the leading D x D block (no pivoting, natural pivot
 // order).  The pivots met are those of LDL^T, so "some pivot <= 0" <=> np.linalg.cholesky fails; the

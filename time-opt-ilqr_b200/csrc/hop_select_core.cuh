@@ -135,7 +135,7 @@ HOP_DEVICE bool gj_attempt(double (&a)[D], int r, double* rowbuf) {
     for (int j = 0; j < D; ++j) {
         const double p = simt::shfl(a[j], j, G);
         ok = ok && (p > 0.0) && (p <= 1.7976931348623157e308);   // +Inf is non-finite input (utils.py:75), not a pivot
-        const double rinv = 1.0 / p;
+        const double rinv = simt::rcp_newton(p);
         double* rb = rowbuf + (j & 1) * DP;
         const bool piv = (r == j);
         if (piv) st_row<D, DP>(rb, 0, a);

@@ -72,7 +72,7 @@ HOP_DEVICE bool gj_attempt(double& a, int r, int c) {
     for (int j = 0; j < D; ++j) {
         const double p = at(a, j * D + j);
         ok = ok && (p > 0.0) && (p <= 1.7976931348623157e308);   // +Inf is non-finite input (utils.py:75), not a pivot
-        const double rinv = 1.0 / p;
+        const double rinv = simt::rcp_newton(p);
         const double rowv = at(a, j * D + c);      // pivot row, my column
         const double colv = at(a, r * D + j);      // my row, pivot column
         if (r == j) {

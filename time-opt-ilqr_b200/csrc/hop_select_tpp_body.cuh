@@ -89,7 +89,7 @@ HOP_DEVICE bool gj_attempt(double (&a)[D][D]) {
     for (int j = 0; j < D; ++j) {
         const double p = a[j][j];
         ok = ok && (p > 0.0) && (p <= 1.7976931348623157e308);   // +Inf is non-finite input (utils.py:75), not a pivot
-        const double rinv = 1.0 / p;
+        const double rinv = simt::rcp_newton(p);
         double rb[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) rb[c] = a[j][c];

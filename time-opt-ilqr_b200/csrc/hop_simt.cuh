@@ -13,6 +13,7 @@ namespace hop { namespace simt {
 // (g++ on x86-64 without -mfma never contracts a * b + c)
 inline double mul_rn(double a, double b) { return a * b; }
 inline double add_rn(double a, double b) { return a + b; }
+inline double rcp_newton(double p) { return 1.0 / p; }
 }}  // namespace hop::simt
 #else
 #include <cuda_runtime.h>
@@ -29,6 +30,18 @@ HOP_DEVICE bool all(bool p) { return __all_sync(0xffffffffu, p) != 0; }
 // a product / a sum that must NOT be contracted into an FMA with its neighbours (numpy evaluates them separately)
 HOP_DEVICE double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 HOP_DEVICE double add_rn(double a, double b) { return __dadd_rn(a, b); }
+// 1/p for a Gauss-Jordan pivot: MUFU.RCP64H seed (rel. error <= 2^-23) + two Newton steps (<= 1 ulp).  The IEEE-correct
+// `1.0 / p` is a ~25-instruction dependent sequence with a slow-path test and sits on the critical path of every
+// elimination step (25 of them per horizon step in the d <= 5 kernels); the host emulation uses the exact quotient.
+HOP_DEVICE double rcp_newton(double p) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
+    double e = fma(-p, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-p, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
 // D(8x8) += A(8x4) * B(4x8) in fp64 on the tensor pipe (SASS: DMMA.8x8x4).  Fragments (g = lane>>2,
 // t = lane&3): a = A[g][t], b = B[t][g], c0/c1 = C[g][2t], C[g][2t+1].
 HOP_DEVICE void dmma(double& c0, double& c1, double a, double b) {
