@@ -123,7 +123,7 @@ def _ddp(name, x0s, dev, max_iter, check, label, cfg, N=None, mode=None):
     rec = {"config": cfg, "what": label, "instances": len(x0s), "max_iter": max_iter, "device_s": dt,
            "solves_per_s": len(x0s) / dt, "outer_iterations_run": r["iters"], "crashed": int(((st & 0xFF) != 0).sum()),
            "phase_seconds_rank0": r["timers"]}
-    if rank == 0 and check > 0:
+    if rank == 0 and check > 0 and not os.environ.get("HOP_CFG_NO_PARITY"):           # (timing-only A/B runs skip the CPU census)
         k = min(check, hi - lo)
         rec["parity_vs_oracle"] = ddp_census(case, Nn, x0s[:k], max_iter, {"fast": (nh, Th, Jh, r["T_star"].cpu().numpy())}, dev)
     emit(rec)
