@@ -177,7 +177,7 @@ def cfg2(args, dev):
 
 
 def cfg3(args, dev):
-    B = 256 if args.small else 4096
+    B = int(os.environ.get("HOP_CFG3_B", "0")) or (256 if args.small else 4096)    # HOP_CFG3_B: batch-size A/B runs
     rng = np.random.default_rng(0)                                              # the reference's cartpole sigma is 0
     x0s = np.array([rng.normal(0, .1, B), rng.normal(0, .1, B), rng.normal(0, .2, B), rng.normal(0, .2, B)]).T
     _ddp("Cartpole_SwingUp", x0s, dev, 12, B, f"Cartpole swing-up HOP-DDP (augmented homogeneous state), {B} random initial "

@@ -642,9 +642,11 @@ def test_diagonal_block_fast_path_and_sweep_agree_bit_for_bit(d, m, N):
 
 @pytest.mark.parametrize("name", ["DoubleIntegrator", "Segway_Balance", "Cartpole_SwingUp"])
 def test_element_per_lane_and_lane_group_fused_kernels_agree_bit_for_bit(name):
-    """The fused selection of the small systems has two device mappings (a warp per problem with one matrix element per
-    lane -- the low-latency default -- and a lane group per problem).  Same IEEE operations per element => the whole
-    batched HOP-DDP solve (every selection of every iteration feeds the next one) is identical bit for bit."""
+    """The fused selection of the small systems has three device mappings: a lane group per problem (large batches), a warp
+    per problem with one matrix element per lane, and -- for batches that leave the machine idle -- one problem per CTA as a
+    warp-specialised pipeline (two stage warps, the prefix recursion on one warp, the queries J(t) on three, blocks handed
+    over through shared-memory rings).  Same IEEE operations per element => the whole batched HOP-DDP solve (every selection
+    of every iteration feeds the next one) is identical bit for bit, and so are T_max = 1, 2 and T_min = T_max."""
     from hop import _cabi
     lib = _cabi.require_device()
     case = cases.make_case(name)
@@ -653,14 +655,35 @@ def test_element_per_lane_and_lane_group_fused_kernels_agree_bit_for_bit(name):
     x0s = case[1][None] + 0.2 * rng.standard_normal((41, n))
     out = {}
     try:
-        for variant in (0, 1):
+        for variant in (1, 2, 3):
             lib.hop_test_set_fused_small_variant(variant)
             out[variant] = api.ilqr_timeopt_batched(case, _t(x0s), max_iter=5, use_central_diff=False, mode=api.MODE_GJ)
     finally:
         lib.hop_test_set_fused_small_variant(0)
-    for key in ("X", "U", "J_hist", "T_hist", "n_hist", "T_star", "J_curve", "status"):
-        assert torch.equal(torch.nan_to_num(out[0][key].double(), nan=-1.0), torch.nan_to_num(out[1][key].double(), nan=-1.0)), key
-    assert torch.isfinite(out[0]["J_curve"]).any()
+    for variant in (2, 3):
+        for key in ("X", "U", "J_hist", "T_hist", "n_hist", "T_star", "J_curve", "status"):
+            assert torch.equal(torch.nan_to_num(out[variant][key].double(), nan=-1.0),
+                               torch.nan_to_num(out[1][key].double(), nan=-1.0)), (variant, key)
+    assert torch.isfinite(out[1]["J_curve"]).any()
+    # short sweeps: fewer steps than ring slots / query warps, a one-point window, a NaN in the inputs
+    F, x0, xg, u_ref, Q, R, alpha, w, N, T_min, T_max, wrap_idx, _ = case
+    g = golden("case_" + name)
+    A = _t(np.repeat(g["A_fwd"][None], 3, 0)); Bm = _t(np.repeat(g["B_fwd"][None], 3, 0)); X = np.repeat(g["X"][None], 3, 0)
+    X[2, 3, 0] = np.nan
+    X = _t(X); U = _t(np.repeat(g["U"][None], 3, 0)); ar = _t(np.repeat(g["a_resid"][None], 3, 0))
+    for (tmin, tmax) in ((1, 1), (1, 2), (2, 2), (3, 7), (int(T_min), min(int(T_max), int(g["N"])))):
+        res = {}
+        try:
+            for variant in (1, 2, 3):
+                lib.hop_test_set_fused_small_variant(variant)
+                r = api.select_fused_batched(A, Bm, X, U, xg, w, u_ref, Q, R, alpha, tmin, tmax, wrap_idx=wrap_idx, a_resid=ar,
+                                             mode=api.MODE_GJ)
+                res[variant] = tuple(x.cpu().numpy() for x in (r.J, r.T_star, r.J_star, r.status))
+        finally:
+            lib.hop_test_set_fused_small_variant(0)
+        for variant in (2, 3):
+            for a, b in zip(res[variant], res[1]):
+                assert np.array_equal(a, b, equal_nan=True), (variant, tmin, tmax)
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)

@@ -504,7 +504,7 @@ int hop_test_set_linesearch_variant(int variant) {
 
 int hop_test_set_fused_small_variant(int variant) {
     const int old = g_fused_small_variant;
-    if (variant == 0 || variant == 1) g_fused_small_variant = variant;
+    if (variant >= 0 && variant <= 3) g_fused_small_variant = variant;
     return old;
 }
 

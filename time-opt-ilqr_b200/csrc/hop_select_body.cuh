@@ -49,10 +49,15 @@ struct FusedArgs {
     int* status;
 };
 
-// utils.py:127-128: (a + pi) % (2 pi) - pi with Python's floored modulo
+// utils.py:127-128: (a + pi) % (2 pi) - pi with Python's floored modulo.  For s = a + pi in (-2 pi, 4 pi) the floored modulo
+// is s, s + 2 pi or s - 2 pi -- exactly what fmod and the sign fix-up return (fmod is exact, the subtraction is exact by
+// Sterbenz) -- so those ranges skip the library call: same bits, a shorter dependent chain in every roll-out / sweep step.
 HOP_DEVICE double wrap_pi(double a) {
     const double pi = 3.141592653589793, two_pi = 6.283185307179586;
     const double s = a + pi;
+    if (s >= 0.0 && s < two_pi) return s - pi;                        // (fmod(s, 2 pi) = s; -0.0 and +0.0 both give 0.0 - pi below)
+    if (s >= two_pi && s < 2.0 * two_pi) return (s - two_pi) - pi;
+    if (s < 0.0 && s > -two_pi) return (s + two_pi) - pi;
     double r = fmod(s, two_pi);
     if (r != 0.0) {
         if (r < 0.0) r += two_pi;

@@ -64,7 +64,9 @@ template <int D>
 HOP_DEVICE double sym(double v, int r, int c) { return 0.5 * (v + at(v, c * D + r)); }
 
 // One Gauss-Jordan inversion attempt (hop::gj_attempt element for element).  The pivot is the same value on every
-// lane, so the returned flag is warp-uniform.
+// lane, so the returned flag is warp-uniform.  (Forming the next pivot on every lane from the pre-update entries -- same
+// bits, one shuffle latency less per elimination step -- was measured: one-warp kernel -3 %, pipeline unchanged, at three
+// more shuffles per pivot on a shuffle unit the pipeline already keeps ~40 % busy.  Not kept.)
 template <int D>
 HOP_DEVICE bool gj_attempt(double& a, int r, int c) {
     bool ok = true;
@@ -288,5 +290,256 @@ HOP_DEVICE void select_fused_epl_body(const FusedArgs& p, int b, double* scratch
         p.status[b] = status;
     }
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same sweep as a WARP-SPECIALISED PIPELINE: one problem per CTA of kWspWarps warps.
+//
+// A horizon step of select_fused_epl_body is three pieces with different dependencies:
+//   stage   (E_k, F_k, G_k)            depends on the inputs of step k only
+//   prefix  (Ebar, Fbar, Gbar)_k       the loop-carried recursion: needs the prefix of step k-1 and the stage of step k
+//   query   J(k+1)                     hangs off the prefix of step k, nothing depends on it
+// A single warp executes them back to back (~850 dependent instructions, 4.8 k clocks per step on an otherwise idle SM --
+// the 25-trial configurations).  Here three warps compute the stages of the steps k = s (mod 3) ahead of time, one warp runs
+// the recursion (one chol_inv and five products per step), three warps take the queries of the steps k = q (mod 3), and the
+// blocks travel between them through shared-memory rings (one element per lane, as in the registers) guarded by named
+// barriers (producer: fence + bar.arrive, consumer: bar.sync).  Every element goes through the same IEEE operations in the
+// same order as in the one-warp body -- the functions below are that body cut at the hand-over points -- so the two kernels
+// are bit-identical (asserted on the GPU; the host emulator runs one warp at a time and does not cover this body).
+// Role counts (measured on B200, select phase of the Segway 25-trial / cartpole 148-instance HOP-DDP solves, ms; one warp:
+// 7.56 / 11.8): 2 + 1 + 3 warps 2.68 / 5.94, 1 + 1 + 3: 2.98 / 6.10, 3 + 1 + 3: 2.34 / 4.98 [default], 4 + 1 + 3 and 3 + 1 + 4:
+// 2.70 / 6.03 -- with seven warps the recursion (warp 3) is alone on its SM sub-partition, an eighth warp shares it.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef HOP_WSP_STAGE_WARPS
+#define HOP_WSP_STAGE_WARPS 3
+#endif
+#ifndef HOP_WSP_QUERY_WARPS
+#define HOP_WSP_QUERY_WARPS 3
+#endif
+#ifndef HOP_WSP_RING_PER_STAGE
+#define HOP_WSP_RING_PER_STAGE 1
+#endif
+constexpr int kWspStageWarps = HOP_WSP_STAGE_WARPS, kWspQueryWarps = HOP_WSP_QUERY_WARPS, kWspWarps = kWspStageWarps + 1 + kWspQueryWarps;
+constexpr int kWspStageRing = kWspStageWarps * HOP_WSP_RING_PER_STAGE;   // stage -> prefix ring slots
+// named barrier ids (0 is __syncthreads): full / empty per ring slot
+constexpr int kBarStageFull = 1, kBarStageEmpty = kBarStageFull + kWspStageRing;
+constexpr int kBarPrefixFull = kBarStageEmpty + kWspStageRing, kBarPrefixEmpty = kBarPrefixFull + kWspQueryWarps;
+static_assert(kBarPrefixEmpty + kWspQueryWarps <= 16, "sixteen named barriers per CTA");
+
+#ifndef HOP_HOST_EMUL
+HOP_DEVICE void bar_arrive(int id) {   // producer / releasing side: this warp's shared-memory accesses first
+    __threadfence_block();
+    asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
+}
+HOP_DEVICE void bar_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int D>
+struct WspSmem {   // doubles; per CTA, after the constants
+    static constexpr int DP = (D + 1) & ~1;
+    static constexpr int LU = 0;                                           // kWspWarps x (2 D DP): LU fallback scratch per warp
+    static constexpr int STAGE = LU + kWspWarps * 2 * D * DP;              // [kWspStageRing][3][32]: e, f, g
+    static constexpr int PREFIX = STAGE + kWspStageRing * 3 * 32;          // [kWspQueryWarps][3][32]: eb, fb, gb
+    static constexpr int RESULT = PREFIX + kWspQueryWarps * 3 * 32;        // [kWspQueryWarps][4]: best, idx, nan_hit, -; then status words
+    static constexpr int SIZE = RESULT + kWspQueryWarps * 4 + kWspWarps + (kWspWarps & 1);
+};
+
+// role 0 .. kWspStageWarps-1: stages of the steps k = role (mod kWspStageWarps)
+template <int D, int M>
+HOP_DEVICE void wsp_stage_role(const FusedArgs& p, int b, int role, double* lu, double* ring, const double* cst, int& status) {
+    using FC = FusedConst<D, M>;
+    constexpr int n = D - 1;
+    constexpr int G = (D <= 4) ? 4 : 8;
+    Geo<D> L;
+    L.init();
+    const int lane = L.lane, r = L.r, c = L.c;
+    const bool isx = lane < n;
+    const int li = isx ? lane : 0;
+    const bool isb = lane < D * M;
+    const int rB = isb ? lane / M : 0, cB = isb ? lane % M : 0;
+    const bool ism = lane < M * M;
+    const int rM = ism ? lane / M : 0, cM = ism ? lane % M : 0;
+    const double rinv_e = chol_inv<M>(cst[FC::RS + rM * M + cM], rM, cM, ism, lu, p.jitter, p.max_tries, status);
+    const double xg_l = isx ? p.xg[(size_t)b * n + li] : 0.0;
+    const bool wrap_l = isx && ((p.wrap_mask >> li) & 1u);
+    const double uref_l = (lane < M) ? cst[FC::UREF + lane] : 0.0;
+    const double w = p.w[b];
+    const double qs_e = (r < n && c < n) ? cst[FC::QS + r * n + c] : 0.0;
+    const size_t baseN = (size_t)b * p.N;
+    const double* Xb = p.X + (size_t)b * (p.N + 1) * n;
+    const double* Ub = p.U + (size_t)b * p.u_stride;
+    struct Step { double a, bm, brow[M], ar, u, x0; };
+    auto load_step = [&](int k) {
+        Step s;
+        const bool in = k < p.T_max;
+        const double* Ak = p.A + (baseN + k) * n * n;
+        const double* Bk = p.Bm + (baseN + k) * n * M;
+        s.a = (in && L.act && r < n && c < n) ? Ak[r * n + c] : 0.0;
+        s.bm = (in && isb && rB < n) ? Bk[rB * M + cB] : 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) s.brow[j] = (in && isx) ? Bk[li * M + j] : 0.0;
+        s.ar = (in && isx && p.a_resid) ? p.a_resid[(baseN + k) * n + li] : 0.0;
+        s.u = (in && lane < M) ? Ub[(size_t)k * M + lane] : 0.0;
+        s.x0 = (in && isx) ? Xb[(size_t)k * n + li] : 0.0;
+        return s;
+    };
+    Step cur = load_step(role);
+    for (int k = role; k < p.T_max; k += kWspStageWarps) {
+        const Step nxt = load_step(k + kWspStageWarps);
+        double ev = 0.0;                              // e_k = wrap(X_k - xg)  (augmented.py:28)
+        if (isx) {
+            ev = cur.x0 - xg_l;
+            if (wrap_l) ev = wrap_pi(ev);
+        }
+        const double du = (lane < M) ? cur.u - uref_l : 0.0;
+        double colA = 0.0;
+        {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < M; ++j) s = fma(cur.brow[j], at(du, j), s);
+            colA = cur.ar - s;
+        }
+        const double colA_r = at(colA, r);
+        const double a_e = (r < n) ? ((c < n) ? cur.a : colA_r) : ((c == n) ? 1.0 : 0.0);
+        const double b_e = cur.bm;
+        double qe = 0.0, qc = 0.0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            const double ej = at(ev, j);
+            qe = fma(cst[FC::QRAW + li * n + j], ej, qe);
+            qc = fma(ej, cst[FC::QRAW + j * n + li], qc);
+        }
+        const double eQe = tree_sum<n, G>(isx ? simt::mul_rn(qc, ev) : 0.0, 1);
+        const double qe_x = at(qe, (r == n) ? c : r);
+        const double q_e = (r < n) ? ((c < n) ? qs_e : qe_x) : ((c < n) ? qe_x : (eQe + 2.0 * w + p.rho_reg));
+        const double e = chol_inv<D>(q_e, r, c, L.act, lu, p.jitter, p.max_tries, status);
+        const double f = mul_nt<D>(e, a_e, r, c);                                          // F_k = E_k A_k^T
+        double g;
+        {
+            const double t = mul_nn<D>(a_e, e, r, c);
+            g = mul_nt<D>(t, a_e, r, c);
+            double br = 0.0;
+#pragma unroll
+            for (int l = 0; l < M; ++l) br = fma(at(b_e, rB * M + l), at(rinv_e, l * M + cB), br);
+#pragma unroll
+            for (int l = 0; l < M; ++l) g = fma(at(br, r * M + l), at(b_e, c * M + l), g);
+            g = sym<D>(g, r, c);
+        }
+        const int slot = k % kWspStageRing;
+        if (k >= kWspStageRing) bar_wait(kBarStageEmpty + slot);    // the prefix warp has read step k - kWspStageRing
+        double* dst = ring + slot * 96;
+        dst[lane] = e; dst[32 + lane] = f; dst[64 + lane] = g;
+        bar_arrive(kBarStageFull + slot);
+        cur = nxt;
+    }
+}
+
+// the recursion: one warp, every step
+template <int D, int M>
+HOP_DEVICE void wsp_prefix_role(const FusedArgs& p, double* lu, const double* stage_ring, double* prefix_ring, int& status) {
+    Geo<D> L;
+    L.init();
+    const int lane = L.lane, r = L.r, c = L.c;
+    double eb = 0.0, fb = 0.0, gb = 0.0;
+    for (int k = 0; k < p.T_max; ++k) {
+        const int slot = k % kWspStageRing;
+        bar_wait(kBarStageFull + slot);
+        const double* src = stage_ring + slot * 96;
+        const double e = src[lane], f = src[32 + lane], g = src[64 + lane];
+        if (k + kWspStageRing < p.T_max) bar_arrive(kBarStageEmpty + slot);
+        if (k == 0) {
+            eb = e; fb = f; gb = g;
+        } else {
+            const double s = sym<D>(e + gb, r, c);
+            const double wv = chol_inv<D>(s, r, c, L.act, lu, p.jitter, p.max_tries, status);      // W = chol_inv(E_k + Gbar)  (:72)
+            const double t1 = mul_nn<D>(fb, wv, r, c);
+            const double acc = mul_nt<D>(t1, fb, r, c);
+            const double eb_new = eb - acc;
+            const double fb_new = mul_nn<D>(t1, f, r, c);
+            const double t2 = mul_tn<D>(f, wv, r, c);
+            const double acc2 = mul_nn<D>(t2, f, r, c);
+            const double gb_new = g - acc2;
+            fb = fb_new;
+            eb = sym<D>(eb_new, r, c);
+            gb = sym<D>(gb_new, r, c);
+        }
+        const int q = k % kWspQueryWarps;
+        if (k >= kWspQueryWarps) bar_wait(kBarPrefixEmpty + q);     // query warp q has read step k - kWspQueryWarps
+        double* dst = prefix_ring + q * 96;
+        dst[lane] = eb; dst[32 + lane] = fb; dst[64 + lane] = gb;
+        bar_arrive(kBarPrefixFull + q);
+    }
+}
+
+// queries of the steps k = q (mod kWspQueryWarps); leaves its running argmin in res[0..2]
+template <int D, int M>
+HOP_DEVICE void wsp_query_role(const FusedArgs& p, int b, int q, double* lu, const double* prefix_ring, const double* cst, double* res,
+                               int& status) {
+    using FC = FusedConst<D, M>;
+    constexpr int n = D - 1;
+    constexpr int G = (D <= 4) ? 4 : 8;
+    Geo<D> L;
+    L.init();
+    const int lane = L.lane, r = L.r, c = L.c;
+    const bool isx = lane < n;
+    const int li = isx ? lane : 0;
+    const double xg_l = isx ? p.xg[(size_t)b * n + li] : 0.0;
+    const bool wrap_l = isx && ((p.wrap_mask >> li) & 1u);
+    const double pf_e = (r < n && c < n) ? cst[FC::PF + r * n + c] : 0.0;
+    const double* Xb = p.X + (size_t)b * (p.N + 1) * n;
+    ArgMin am;
+    am.init();
+    double x1 = (q < p.T_max && isx) ? Xb[(size_t)(q + 1) * n + li] : 0.0;
+    for (int k = q; k < p.T_max; k += kWspQueryWarps) {
+        const int kn = k + kWspQueryWarps;
+        const double x1n = (kn < p.T_max && isx) ? Xb[(size_t)(kn + 1) * n + li] : 0.0;
+        // ---- terminal block QT_{k+1} from X[k+1] (augmented.py:78-86): does not need the prefix
+        double et = 0.0;
+        if (isx) {
+            et = x1 - xg_l;
+            if (wrap_l) et = wrap_pi(et);
+        }
+        double px = 0.0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) px = fma(cst[FC::PF + li * n + j], at(et, j), px);
+        const double ePe = tree_sum<n, G>(isx ? simt::mul_rn(et, px) : 0.0, 1);
+        const double px_x = at(px, (r == n) ? c : r);
+        const double qt_e = (r < n) ? ((c < n) ? pf_e : px_x) : ((c < n) ? px_x : (2.0 * (0.5 * ePe) + p.rho_reg));
+        const double xt = chol_inv<D>(qt_e, r, c, L.act, lu, p.jitter, p.max_tries, status);
+        bar_wait(kBarPrefixFull + q);
+        const double* src = prefix_ring + q * 96;
+        const double eb = src[lane], fb = src[32 + lane], gb = src[64 + lane];
+        if (kn < p.T_max) bar_arrive(kBarPrefixEmpty + q);
+        // ---- query of horizon t = k+1 (:77-86)
+        const double wt = chol_inv<D>(sym<D>(xt + gb, r, c), r, c, L.act, lu, p.jitter, p.max_tries, status);
+        const double t3 = mul_nn<D>(fb, wt, r, c);
+        const double acc3 = mul_nt<D>(t3, fb, r, c);
+        const double x0 = sym<D>(eb - acc3, r, c);
+        const double p0 = chol_inv<D>(x0, r, c, L.act, lu, p.jitter, p.max_tries, status);
+        double dot = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) dot = fma(at(p0, r * D + j), (j == n) ? 1.0 : 0.0, dot);
+        const double part = simt::mul_rn((r == n) ? 1.0 : 0.0, dot);
+        const double J = 0.5 * tree_sum<D, G>(part, D);
+        if (lane == 0) {
+            p.J_out[(size_t)b * p.T_max + k] = J;
+            const int t = k + 1;
+            if (t >= p.T_min) am.push(J, t);
+        }
+        x1 = x1n;
+    }
+    if (lane == 0) { res[0] = am.best; res[1] = (double)am.idx; res[2] = am.nan_hit ? 1.0 : 0.0; }
+}
+
+// np.argmin over the union of the query warps' horizons: the first NaN wins, else the first minimum
+HOP_DEVICE void wsp_merge(ArgMin& a, double best, int idx, bool nan_hit) {
+    if (idx == 0) return;
+    if (a.idx == 0) { a.best = best; a.idx = idx; a.nan_hit = nan_hit; return; }
+    if (a.nan_hit || nan_hit) {
+        if (nan_hit && (!a.nan_hit || idx < a.idx)) { a.best = best; a.idx = idx; a.nan_hit = true; }
+        return;
+    }
+    if (best < a.best || (best == a.best && idx < a.idx)) { a.best = best; a.idx = idx; }
+}
+#endif  // !HOP_HOST_EMUL
 
 }}  // namespace hop::epl
