@@ -32,7 +32,8 @@ extern "C" int emul_backward(int n, int m, int variant, int T, double lm, const 
                              const double* Qf, double w, unsigned wrap_mask, double* k_out, double* K_out, int* ok) {
     if (!(n == 12 && m == 4)) return -2;
     std::vector<double> smem(hop::ddp::BwSmem<12, 4>::SIZE, -7.0);
-    BwJob j{A, Bm, X, U, {xg, u_ref, Q, R, Qf, w, wrap_mask}, T, lm, k_out, K_out, 0, 0, variant, smem.data()};
+    const unsigned diag = (hop::ddp::is_diagonal<12>(Q) ? 1u : 0u) | (hop::ddp::is_diagonal<4>(R) ? 2u : 0u) | (hop::ddp::is_diagonal<12>(Qf) ? 4u : 0u);
+    BwJob j{A, Bm, X, U, {xg, u_ref, Q, R, Qf, w, wrap_mask, diag}, T, lm, k_out, K_out, 0, 0, variant, smem.data()};
     if (hop::simt::run_warp(bw_lane<12, 4>, &j)) return -1;
     *ok = j.ok;
     return j.rc;

@@ -24,9 +24,23 @@ struct DdpConst {   // device pointers to the shared case constants + per-instan
     unsigned wrap_mask;
 };
 
-template <int n>
-__device__ __forceinline__ ddp::CostConst cost_const(const DdpConst& c, int b) {
+// CostConst::diag for the whole CTA: the threads share the off-diagonal entries of Q, R, Qf (at most two loads each) and vote.
+// EVERY thread of the CTA calls this before any early return.
+template <int d>
+__device__ __forceinline__ bool cta_is_diagonal(const double* M) {
+    bool dg = true;
+    for (int i = threadIdx.x; i < d * d; i += blockDim.x)
+        if (i / d != i % d) dg = dg && (M[i] == 0.0);
+    return __syncthreads_and(dg) != 0;
+}
+template <int n, int m>
+__device__ __forceinline__ unsigned cta_diag_flags(const DdpConst& c) {
+    return (cta_is_diagonal<n>(c.Q) ? 1u : 0u) | (cta_is_diagonal<m>(c.R) ? 2u : 0u) | (cta_is_diagonal<n>(c.Qf) ? 4u : 0u);
+}
+template <int n, int m>
+__device__ __forceinline__ ddp::CostConst cost_const(const DdpConst& c, int b, unsigned diag) {
     ddp::CostConst cc;
+    cc.diag = diag;
     cc.xg = c.xg + (size_t)b * n;
     cc.u_ref = c.u_ref; cc.Q = c.Q; cc.R = c.R; cc.Qf = c.Qf;
     cc.w = c.w[b];
@@ -43,9 +57,10 @@ __device__ __forceinline__ int horizon_of(const int* T, int b, int N) {
 
 template <int n, int m>
 __global__ void k_cost(int B, int N, const double* X, const double* U, DdpConst c, const int* T, double* J) {
+    const unsigned diag = cta_diag_flags<n, m>(c);                              // (all threads, before any return)
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    const ddp::CostConst cc = cost_const<n>(c, b);
+    const ddp::CostConst cc = cost_const<n, m>(c, b, diag);
     J[b] = ddp::cost_timeopt_true<n, m>(X + (size_t)b * (N + 1) * n, U + (size_t)b * N * m, cc, horizon_of(T, b, N));
 }
 
@@ -53,10 +68,11 @@ template <int n, int m>
 __global__ void k_backward(int B, int N, const double* A, const double* Bm, const double* X, const double* U, DdpConst c,
                            const int* T, const double* lm, const int* done, double* k_out, double* K_out, int* ok,
                            int* err) {
+    const unsigned diag = cta_diag_flags<n, m>(c);                              // (all threads, before any return)
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     if (done && done[b]) { ok[b] = 0; return; }
-    const ddp::CostConst cc = cost_const<n>(c, b);
+    const ddp::CostConst cc = cost_const<n, m>(c, b, diag);
     int okb = 0;
     const int rc = ddp::backward_pass<n, m>(A + (size_t)b * N * n * n, Bm + (size_t)b * N * n * m, X + (size_t)b * (N + 1) * n,
                                             U + (size_t)b * N * m, cc, horizon_of(T, b, N), lm[b], k_out + (size_t)b * N * m,
@@ -73,16 +89,19 @@ int g_backward_variant = getenv("HOP_BW_VARIANT") ? atoi(getenv("HOP_BW_VARIANT"
 
 // one warp per problem (backward_pass_warp), kBwWarps problems per CTA
 constexpr int kBwWarps = 4;
+// small systems: 7 CTAs per SM (<= 72 registers), so that 4 096 instances -- 28 warps per SM -- are one wave; quadrotor: 4 CTAs
+// (<= 128 registers; 2 048 instances -- the per-GPU load of configuration 4 on eight GPUs -- are 14 warps per SM)
 template <int n, int m>
-__global__ void __launch_bounds__(kBwWarps * 32) k_backward_warp(int B, int N, const double* A, const double* Bm, const double* X,
+__global__ void __launch_bounds__(kBwWarps * 32, (n <= 4) ? 7 : 4) k_backward_warp(int B, int N, const double* A, const double* Bm, const double* X,
                                                                  const double* U, DdpConst c, const int* T, const double* lm,
                                                                  const int* done, double* k_out, double* K_out, int* ok, int* err) {
+    const unsigned diag = cta_diag_flags<n, m>(c);                              // (all threads, before any return)
     __shared__ __align__(16) double smem[kBwWarps * ddp::BwSmem<n, m>::SIZE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * kBwWarps + warp;
     if (b >= B) return;
     if (done && done[b]) { if (lane == 0) ok[b] = 0; return; }
-    const ddp::CostConst cc = cost_const<n>(c, b);
+    const ddp::CostConst cc = cost_const<n, m>(c, b, diag);
     int okb = 0;
     const int rc = ddp::backward_pass_warp<n, m>(A + (size_t)b * N * n * n, Bm + (size_t)b * N * n * m, X + (size_t)b * (N + 1) * n,
                                                  U + (size_t)b * N * m, cc, horizon_of(T, b, N), lm[b], k_out + (size_t)b * N * m,
@@ -98,12 +117,13 @@ template <int n, int m>
 __global__ void __launch_bounds__(kBwWarps * 32) k_backward_mma(int B, int N, const double* A, const double* Bm, const double* X,
                                                                 const double* U, DdpConst c, const int* T, const double* lm,
                                                                 const int* done, double* k_out, double* K_out, int* ok, int* err) {
+    const unsigned diag = cta_diag_flags<n, m>(c);                              // (all threads, before any return)
     __shared__ __align__(16) double smem[kBwWarps * ddp::BwSmem<n, m>::SIZE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * kBwWarps + warp;
     if (b >= B) return;
     if (done && done[b]) { if (lane == 0) ok[b] = 0; return; }
-    const ddp::CostConst cc = cost_const<n>(c, b);
+    const ddp::CostConst cc = cost_const<n, m>(c, b, diag);
     int okb = 0;
     const int rc = ddp::backward_pass_mma<n, m>(A + (size_t)b * N * n * n, Bm + (size_t)b * N * n * m, X + (size_t)b * (N + 1) * n,
                                                 U + (size_t)b * N * m, cc, horizon_of(T, b, N), lm[b], k_out + (size_t)b * N * m,
@@ -119,12 +139,13 @@ template <int n, int m>
 __global__ void __launch_bounds__(kBwWarps * 32) k_bruteforce(int B, int N, int T_max, const double* A, const double* Bm,
                                                               const double* X, const double* U, long ustride, DdpConst c,
                                                               double lm, double* J_out, int* status) {
+    const unsigned diag = cta_diag_flags<n, m>(c);                              // (all threads, before any return)
     __shared__ __align__(16) double smem[kBwWarps * ddp::BwSmem<n, m>::SIZE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t id = (size_t)blockIdx.x * kBwWarps + warp;
     if (id >= (size_t)B * T_max) return;
     const int b = (int)(id / T_max), T = T_max - (int)(id % T_max);          // long horizons first
-    const ddp::CostConst cc = cost_const<n>(c, b);
+    const ddp::CostConst cc = cost_const<n, m>(c, b, diag);
     double V0 = 0.0;
     const int rc = ddp::bruteforce_one_T_warp<n, m>(A + (size_t)b * N * n * n, Bm + (size_t)b * N * n * m,
                                                     X + (size_t)b * (N + 1) * n, U + (size_t)b * ustride, cc, T, lm, &V0,
@@ -152,11 +173,12 @@ __global__ void k_linesearch(int B, DynParams2 prm, int N, const double* X, cons
                              const double* k_list, const double* K_list, const int* ok, const int* done, double* Xn,
                              double* Un, double* Jn, int* acc) {
     constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
+    const unsigned diag = cta_diag_flags<n, m>(c);                              // (all threads, before any return)
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     acc[b] = 0;
     if ((done && done[b]) || (ok && !ok[b])) return;
-    const ddp::CostConst cc = cost_const<n>(c, b);
+    const ddp::CostConst cc = cost_const<n, m>(c, b, diag);
     double J = 0.0;
     int a = 0;
     ddp::forward_linesearch<SYS>(prm.p, N, X + (size_t)b * (N + 1) * n, U + (size_t)b * N * m, cc, horizon_of(T, b, N),
@@ -181,6 +203,7 @@ __global__ void __launch_bounds__(kLsRoles * 32) k_linesearch_par(int B, DynPara
                                                                     const double* K_list, const int* ok, const int* done,
                                                                     double* Xn, double* Un, double* Jn, int* acc) {
     constexpr int n = SysDims<SYS>::n, m = SysDims<SYS>::m;
+    const unsigned diag = cta_diag_flags<n, m>(c);                              // (all threads, before any return)
     __shared__ double sJ[kLsRoles][32];
     __shared__ int sOk[kLsRoles][32];
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
@@ -189,7 +212,7 @@ __global__ void __launch_bounds__(kLsRoles * 32) k_linesearch_par(int B, DynPara
     const int b = valid ? b_raw : B - 1;
     const bool active = valid && !((done && done[b]) || (ok && !ok[b]));
     if (valid && role == 0) acc[b] = 0;
-    const ddp::CostConst cc = cost_const<n>(c, b);
+    const ddp::CostConst cc = cost_const<n, m>(c, b, diag);
     const double* Xb = X + (size_t)b * (N + 1) * n;
     const double* Ub = U + (size_t)b * N * m;
     const double* kb = k_list + (size_t)b * N * m;

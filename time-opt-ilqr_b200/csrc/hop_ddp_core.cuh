@@ -36,16 +36,40 @@ HOP_DEVICE void wrapped_error(const double* x, const double* xg, unsigned wrap_m
     }
 }
 
+// (M v)_i as numpy's left-to-right sum.  When M is DIAGONAL (CostConst::diag; every reference case) only the term j = i is not
+// an exact zero: the skipped terms are +-0 products of finite v (the callers test finiteness first, or discard the value), the
+// running sum starts at +0.0 and +0 + (+-0) = +0 in round-to-nearest, so add(+0.0, mul(M_ii, v_i)) is the same bits as the full
+// sum -- n times fewer dependent operations on the chain of every roll-out and backward step.
+template <int n>
+HOP_DEVICE double row_dot(const double* M, const double* v, int i, bool diag) {
+    if (diag) return add(0.0, mul(M[i * n + i], v[i]));
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s = add(s, mul(M[i * n + j], v[j]));
+    return s;
+}
 // v^T (M v) as `v @ (M @ v)`
 template <int n>
-HOP_DEVICE double quad_form(const double* M, const double* v) {
+HOP_DEVICE double quad_form(const double* M, const double* v, bool diag) {
     double acc = 0.0;
+    if (diag) {
+        for (int i = 0; i < n; ++i) acc = add(acc, mul(v[i], add(0.0, mul(M[i * n + i], v[i]))));
+        return acc;
+    }
     for (int i = 0; i < n; ++i) {
         double s = 0.0;
         for (int j = 0; j < n; ++j) s = add(s, mul(M[i * n + j], v[j]));
         acc = add(acc, mul(v[i], s));
     }
     return acc;
+}
+// all off-diagonal entries of the row-major d x d block are +-0 (CostConst::diag; the kernels compute it per CTA, this serial form
+// serves the host emulation)
+template <int d>
+HOP_DEVICE bool is_diagonal(const double* M) {
+    bool dg = true;
+    for (int i = 0; i < d * d; ++i)
+        if (i / d != i % d) dg = dg && (M[i] == 0.0);
+    return dg;
 }
 
 // LAPACK dpotf2-style lower Cholesky of M (d x d); returns false on a non-positive pivot.
@@ -103,6 +127,10 @@ struct CostConst {   // shared case constants, row-major
     const double *xg, *u_ref, *Q, *R, *Qf;
     double w;
     unsigned wrap_mask;
+    unsigned diag;   // bit 0: Q, bit 1: R, bit 2: Qf is diagonal (is_diagonal): row_dot / quad_form take the one-term path
+    HOP_DEVICE bool q_diag() const { return diag & 1u; }
+    HOP_DEVICE bool r_diag() const { return (diag >> 1) & 1u; }
+    HOP_DEVICE bool qf_diag() const { return (diag >> 2) & 1u; }
 };
 
 // solver.py:65-105.  X [N+1][n], U [N][m] of ONE problem.
@@ -120,11 +148,11 @@ HOP_DEVICE double cost_timeopt_true(const double* X, const double* U, const Cost
 #pragma unroll
         for (int i = 0; i < m; ++i) du[i] = sub(U[(size_t)k * m + i], c.u_ref[i]);
         if (!all_finite<n>(e) || !all_finite<m>(du)) return inf;
-        acc = add(acc, add(add(mul(0.5, quad_form<n>(c.Q, e)), mul(0.5, quad_form<m>(c.R, du))), c.w));
+        acc = add(acc, add(add(mul(0.5, quad_form<n>(c.Q, e, c.q_diag())), mul(0.5, quad_form<m>(c.R, du, c.r_diag()))), c.w));
     }
     wrapped_error<n>(X + (size_t)T * n, c.xg, c.wrap_mask, e);
     if (!all_finite<n>(e)) return inf;
-    return add(acc, mul(0.5, quad_form<n>(c.Qf, e)));
+    return add(acc, mul(0.5, quad_form<n>(c.Qf, e, c.qf_diag())));
 }
 
 // small dense helpers on thread-local row-major arrays
@@ -158,9 +186,7 @@ HOP_DEVICE int backward_pass(const double* A, const double* Bm, const double* X,
     wrapped_error<n>(X + (size_t)T * n, c.xg, c.wrap_mask, e);
     if (!all_finite<n>(e)) return DDP_OK;
     for (int i = 0; i < n; ++i) {
-        double s = 0.0;
-        for (int j = 0; j < n; ++j) s = add(s, mul(c.Qf[i * n + j], e[j]));
-        Vx[i] = s;
+        Vx[i] = row_dot<n>(c.Qf, e, i, c.qf_diag());
     }
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) Vxx[i * n + j] = 0.5 * add(c.Qf[i * n + j], c.Qf[j * n + i]);
@@ -172,14 +198,14 @@ HOP_DEVICE int backward_pass(const double* A, const double* Bm, const double* X,
         if (!all_finite<n>(e) || !all_finite<m>(du)) return DDP_OK;
         double Qx[n], Qu[m], Qxx[n * n], Quu[m * m], Qux[m * n], AtV[n * n], BtV[m * n], t[n * n];
         for (int i = 0; i < n; ++i) {
-            double lx = 0.0, s = 0.0;
-            for (int j = 0; j < n; ++j) lx = add(lx, mul(c.Q[i * n + j], e[j]));
+            double s = 0.0;
+            const double lx = row_dot<n>(c.Q, e, i, c.q_diag());
             for (int l = 0; l < n; ++l) s = add(s, mul(Ak[l * n + i], Vx[l]));
             Qx[i] = add(lx, s);
         }
         for (int i = 0; i < m; ++i) {
-            double lu = 0.0, s = 0.0;
-            for (int j = 0; j < m; ++j) lu = add(lu, mul(c.R[i * m + j], du[j]));
+            double s = 0.0;
+            const double lu = row_dot<m>(c.R, du, i, c.r_diag());
             for (int l = 0; l < n; ++l) s = add(s, mul(Bk[l * m + i], Vx[l]));
             Qu[i] = add(lu, s);
         }
@@ -284,6 +310,77 @@ HOP_DEVICE int chol_solve_warp(const double* A, const double* Bm, double* X, dou
     return DDP_LINALG;
 }
 
+// The gains of one backward step in ONE pass (solver.py:213-221): the positive-definiteness test of Quu_reg and the two
+// chol_solve calls (k = -Quu_reg^-1 Qu, K = -Quu_reg^-1 Qux) as written above are three Cholesky factorisations one after the
+// other -- the test on Quu_reg, then twice the SAME jittered factor of sym(Quu_reg) + 1e-9 I -- and two substitution passes; fp64
+// sqrt and divide are ~250-clock dependent sequences, so they, not the matrix products, bound a backward step.  Here the two
+// DIFFERENT factorisations run column by column in lockstep (two independent chains, no early exit), the jittered factor is formed
+// once, and the n + 1 right-hand-side columns (Qux on lanes 0 .. n-1, Qu on lane n) are substituted together.  Every
+// value is produced by the operations of cholesky_lower / chol_solve_warp in their order, so the results are bit-identical; any
+// case the straight-line path does not cover (non-finite input, a failed first try, a non-finite solution: the jitter ladder)
+// returns -1 and the caller runs the reference sequence.  Returns 0: kap, Kk written (not yet negated); 1: Quu_reg is not PD.
+template <int m, int n>
+HOP_DEVICE int gains_one_pass(const double* Qreg, const double* Qu, const double* Qux, double* kap, double* Kk, int lane) {
+    static_assert(n + 1 <= 32, "one right-hand-side column per lane");
+    double S[m * m], M[m * m], L0[m * m], L1[m * m];
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) S[i * m + j] = 0.5 * add(Qreg[i * m + j], Qreg[j * m + i]);
+    for (int i = 0; i < m * m; ++i) M[i] = S[i];
+    for (int i = 0; i < m; ++i) M[i * m + i] = add(S[i * m + i], 1e-9);
+    for (int i = 0; i < m * m; ++i) { L0[i] = 0.0; L1[i] = 0.0; }
+    bool ok0 = true, ok1 = true;
+    for (int j = 0; j < m; ++j) {                                               // cholesky_lower<m> on Qreg and on M, interleaved
+        double a0 = Qreg[j * m + j], a1 = M[j * m + j];
+        for (int q = 0; q < j; ++q) {
+            a0 = sub(a0, mul(L0[j * m + q], L0[j * m + q]));
+            a1 = sub(a1, mul(L1[j * m + q], L1[j * m + q]));
+        }
+        ok0 = ok0 && (a0 > 0.0);
+        ok1 = ok1 && (a1 > 0.0);
+        a0 = sqrt(a0); a1 = sqrt(a1);                                           // (NaN after a failed pivot: the flag is already down)
+        L0[j * m + j] = a0; L1[j * m + j] = a1;
+        const double r0 = 1.0 / a0, r1 = 1.0 / a1;
+        for (int i = j + 1; i < m; ++i) {
+            double s0 = Qreg[i * m + j], s1 = M[i * m + j];
+            for (int q = 0; q < j; ++q) {
+                s0 = sub(s0, mul(L0[i * m + q], L0[j * m + q]));
+                s1 = sub(s1, mul(L1[i * m + q], L1[j * m + q]));
+            }
+            L0[i * m + j] = mul(s0, r0);
+            L1[i * m + j] = mul(s1, r1);
+        }
+    }
+    if (!ok0) return 1;                                                         // solver.py:213-216
+    bool fin = all_finite<m * m>(S);
+    for (int i = lane; i < m; i += 32) fin = fin && isfinite(Qu[i]);
+    for (int i = lane; i < m * n; i += 32) fin = fin && isfinite(Qux[i]);
+    if (!simt::all(fin) || !ok1) return -1;
+    bool okc = true;
+    double Y[m], Xc[m];
+    if (lane <= n) {
+        const double* rhs = (lane < n) ? Qux + lane : Qu;                       // column `lane` of Qux (stride n) | Qu (stride 1)
+        const int ld = (lane < n) ? n : 1;
+        for (int i = 0; i < m; ++i) {
+            double sacc = rhs[i * ld];
+            for (int q = 0; q < i; ++q) sacc = sub(sacc, mul(L1[i * m + q], Y[q]));
+            Y[i] = sacc / L1[i * m + i];
+        }
+        for (int i = m - 1; i >= 0; --i) {
+            double sacc = Y[i];
+            for (int q = i + 1; q < m; ++q) sacc = sub(sacc, mul(L1[q * m + i], Xc[q]));
+            Xc[i] = sacc / L1[i * m + i];
+        }
+        okc = all_finite<m>(Xc);
+    }
+    if (!simt::all(okc)) return -1;
+    if (lane < n) {
+        for (int i = 0; i < m; ++i) Kk[i * n + lane] = Xc[i];
+    } else if (lane == n) {
+        for (int i = 0; i < m; ++i) kap[i] = Xc[i];
+    }
+    return 0;
+}
+
 template <int n, int m>
 HOP_DEVICE int backward_pass_warp(const double* A, const double* Bm, const double* X, const double* U, const CostConst& c,
                                   int T, double lm, double* k_out, double* K_out, int* ok, double* sm, int lane) {
@@ -304,8 +401,7 @@ HOP_DEVICE int backward_pass_warp(const double* A, const double* Bm, const doubl
     if (!simt::all(fin)) return DDP_OK;
     simt::sync();
     if (lane < n) {
-        double s = 0.0;
-        for (int j = 0; j < n; ++j) s = add(s, mul(c.Qf[lane * n + j], e[j]));
+        const double s = row_dot<n>(c.Qf, e, lane, c.qf_diag());
         Vx[lane] = s;
     }
     for (int q = lane; q < n * n; q += 32) {
@@ -349,14 +445,14 @@ HOP_DEVICE int backward_pass_warp(const double* A, const double* Bm, const doubl
         // ---- Qx, Qu, A^T Vxx, B^T Vxx
         if (lane < n) {
             const int i = lane;
-            double lx = 0.0, s = 0.0;
-            for (int j = 0; j < n; ++j) lx = add(lx, mul(c.Q[i * n + j], e[j]));
+            double s = 0.0;
+            const double lx = row_dot<n>(c.Q, e, i, c.q_diag());
             for (int l = 0; l < n; ++l) s = add(s, mul(Ak[l * n + i], Vx[l]));
             Qx[i] = add(lx, s);
         } else if (lane < n + m) {
             const int i = lane - n;
-            double lu = 0.0, s = 0.0;
-            for (int j = 0; j < m; ++j) lu = add(lu, mul(c.R[i * m + j], du[j]));
+            double s = 0.0;
+            const double lu = row_dot<m>(c.R, du, i, c.r_diag());
             for (int l = 0; l < n; ++l) s = add(s, mul(Bk[l * m + i], Vx[l]));
             Qu[i] = add(lu, s);
         }
@@ -397,11 +493,15 @@ HOP_DEVICE int backward_pass_warp(const double* A, const double* Bm, const doubl
         double Qreg[m * m], Ltmp[m * m];
         for (int i = 0; i < m; ++i)
             for (int j = 0; j < m; ++j) Qreg[i * m + j] = add(0.5 * add(Quu[i * m + j], Quu[j * m + i]), (i == j) ? lm : 0.0);
-        if (!cholesky_lower<m>(Qreg, Ltmp)) return DDP_OK;                    // solver.py:213-216
-        int rc = chol_solve_warp<m, 1>(Qreg, Qu, kap, 1e-9, 8, lane);
-        if (rc) return rc;
-        rc = chol_solve_warp<m, n>(Qreg, Qux, Kk, 1e-9, 8, lane);
-        if (rc) return rc;
+        const int gp = gains_one_pass<m, n>(Qreg, Qu, Qux, kap, Kk, lane);
+        if (gp == 1) return DDP_OK;                                           // solver.py:213-216
+        if (gp < 0) {                                                         // the reference sequence (jitter ladder, error codes)
+            if (!cholesky_lower<m>(Qreg, Ltmp)) return DDP_OK;
+            int rc = chol_solve_warp<m, 1>(Qreg, Qu, kap, 1e-9, 8, lane);
+            if (rc) return rc;
+            rc = chol_solve_warp<m, n>(Qreg, Qux, Kk, 1e-9, 8, lane);
+            if (rc) return rc;
+        }
         simt::sync();
         if (lane < m) kap[lane] = -kap[lane];
         for (int q = lane; q < m * n; q += 32) Kk[q] = -Kk[q];
@@ -466,8 +566,7 @@ HOP_DEVICE int bruteforce_one_T_warp(const double* A, const double* Bm, const do
     }
     simt::sync();
     if (lane < n) {
-        double s = 0.0;
-        for (int j = 0; j < n; ++j) s = add(s, mul(c.Qf[lane * n + j], e[j]));
+        const double s = row_dot<n>(c.Qf, e, lane, c.qf_diag());
         Vx[lane] = s;                                                           // Vx[T] = Qf e_T
     }
     for (int q = lane; q < n * n; q += 32) {
@@ -495,15 +594,15 @@ HOP_DEVICE int bruteforce_one_T_warp(const double* A, const double* Bm, const do
         simt::sync();
         if (lane < n) {
             const int i = lane;
-            double a = 0.0, s = 0.0;
-            for (int j = 0; j < n; ++j) a = add(a, mul(c.Q[i * n + j], e[j]));  // lx = Q e
+            double s = 0.0;
+            const double a = row_dot<n>(c.Q, e, i, c.q_diag());                 // lx = Q e
             for (int l = 0; l < n; ++l) s = add(s, mul(Ak[l * n + i], Vx[l]));
             lx[i] = a;
             Qx[i] = add(a, s);
         } else if (lane < n + m) {
             const int i = lane - n;
-            double a = 0.0, s = 0.0;
-            for (int j = 0; j < m; ++j) a = add(a, mul(c.R[i * m + j], du[j])); // lu = R du
+            double s = 0.0;
+            const double a = row_dot<m>(c.R, du, i, c.r_diag());                // lu = R du
             for (int l = 0; l < n; ++l) s = add(s, mul(Bk[l * m + i], Vx[l]));
             lu[i] = a;
             Qu[i] = add(a, s);
@@ -682,11 +781,11 @@ HOP_DEVICE bool linesearch_candidate(const double* prm, int N, const double* X, 
 #pragma unroll
             for (int i = 0; i < m; ++i) du[i] = sub(u[i], c.u_ref[i]);
             if (!all_finite<n>(x) || !all_finite<m>(u) || !all_finite<n>(e) || !all_finite<m>(du)) inf = true;
-            acc = add(acc, add(add(mul(0.5, quad_form<n>(c.Q, e)), mul(0.5, quad_form<m>(c.R, du))), c.w));
+            acc = add(acc, add(add(mul(0.5, quad_form<n>(c.Q, e, c.q_diag())), mul(0.5, quad_form<m>(c.R, du, c.r_diag()))), c.w));
         } else if (k == T) {
             wrapped_error<n>(x, c.xg, c.wrap_mask, e);                          // terminal term at X_new[T] (solver.py:102-105)
             if (!all_finite<n>(x) || !all_finite<n>(e)) inf = true;
-            J = add(acc, mul(0.5, quad_form<n>(c.Qf, e)));
+            J = add(acc, mul(0.5, quad_form<n>(c.Qf, e, c.qf_diag())));
         }
         if (STORE)
             for (int i = 0; i < m; ++i) U_new[(size_t)k * m + i] = u[i];
@@ -697,7 +796,7 @@ HOP_DEVICE bool linesearch_candidate(const double* prm, int N, const double* X, 
     if (T >= N) {
         wrapped_error<n>(x, c.xg, c.wrap_mask, e);
         if (!all_finite<n>(e)) inf = true;
-        J = add(acc, mul(0.5, quad_form<n>(c.Qf, e)));
+        J = add(acc, mul(0.5, quad_form<n>(c.Qf, e, c.qf_diag())));
     }
     *J_out = inf ? HUGE_VAL : J;
     return true;

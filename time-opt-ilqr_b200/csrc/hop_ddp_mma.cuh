@@ -44,8 +44,7 @@ HOP_DEVICE int backward_pass_mma(const double* A, const double* Bm, const double
     if (!simt::all(fin)) return DDP_OK;
     simt::sync();
     if (lane < n) {
-        double s = 0.0;
-        for (int j = 0; j < n; ++j) s = add(s, mul(c.Qf[lane * n + j], e[j]));
+        const double s = row_dot<n>(c.Qf, e, lane, c.qf_diag());
         Vx[lane] = s;                                                           // Vx[T] = Qf e_T
     }
     Mat Vxx, Qm;
@@ -89,14 +88,14 @@ HOP_DEVICE int backward_pass_mma(const double* A, const double* Bm, const double
         // ---- Qx = lx + A^T Vx, Qu = lu + B^T Vx (lanes, as in backward_pass_warp)
         if (lane < n) {
             const int i = lane;
-            double lx = 0.0, s = 0.0;
-            for (int j = 0; j < n; ++j) lx = add(lx, mul(c.Q[i * n + j], e[j]));
+            double s = 0.0;
+            const double lx = row_dot<n>(c.Q, e, i, c.q_diag());
             for (int l = 0; l < n; ++l) s = add(s, mul(Ak[l * n + i], Vx[l]));
             Qx[i] = add(lx, s);
         } else if (lane < n + m) {
             const int i = lane - n;
-            double lu = 0.0, s = 0.0;
-            for (int j = 0; j < m; ++j) lu = add(lu, mul(c.R[i * m + j], du[j]));
+            double s = 0.0;
+            const double lu = row_dot<m>(c.R, du, i, c.r_diag());
             for (int l = 0; l < n; ++l) s = add(s, mul(Bk[l * m + i], Vx[l]));
             Qu[i] = add(lu, s);
         }
@@ -125,11 +124,15 @@ HOP_DEVICE int backward_pass_mma(const double* A, const double* Bm, const double
         double Qreg[m * m], Ltmp[m * m];
         for (int i = 0; i < m; ++i)
             for (int j = 0; j < m; ++j) Qreg[i * m + j] = add(0.5 * add(Quu[i * m + j], Quu[j * m + i]), (i == j) ? lm : 0.0);
-        if (!cholesky_lower<m>(Qreg, Ltmp)) return DDP_OK;                    // solver.py:213-216
-        int rc = chol_solve_warp<m, 1>(Qreg, Qu, kap, 1e-9, 8, lane);
-        if (rc) return rc;
-        rc = chol_solve_warp<m, n>(Qreg, Qux, Kk, 1e-9, 8, lane);
-        if (rc) return rc;
+        const int gp = gains_one_pass<m, n>(Qreg, Qu, Qux, kap, Kk, lane);
+        if (gp == 1) return DDP_OK;                                           // solver.py:213-216
+        if (gp < 0) {                                                         // the reference sequence (jitter ladder, error codes)
+            if (!cholesky_lower<m>(Qreg, Ltmp)) return DDP_OK;
+            int rc = chol_solve_warp<m, 1>(Qreg, Qu, kap, 1e-9, 8, lane);
+            if (rc) return rc;
+            rc = chol_solve_warp<m, n>(Qreg, Qux, Kk, 1e-9, 8, lane);
+            if (rc) return rc;
+        }
         simt::sync();
         if (lane < m) kap[lane] = -kap[lane];
         for (int q = lane; q < m * n; q += 32) Kk[q] = -Kk[q];
