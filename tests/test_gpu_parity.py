@@ -513,6 +513,38 @@ def test_batched_hop_ddp_solve_matches_reference_golden(name, mode):
     assert torch.equal(r["T_hist"][0], r["T_hist"][2]) and torch.equal(r["J_hist"][0, :nh], r["J_hist"][2, :nh])
 
 
+@pytest.mark.parametrize("name", ["Segway_Balance", "Quadrotor"])
+def test_one_pass_backward_gains_fall_back_to_the_reference_sequence(name):
+    """The warp backward kernel forms the gains of a step in one pass (PD test and jittered factor in lockstep, all right-hand
+    sides substituted together) and re-runs the reference sequence -- cholesky, chol_solve, chol_solve with their ladders and
+    error codes -- whenever the straight-line path does not apply.  Instances: clean; an infinite entry in A_k (non-finite
+    Qux: chol_solve's FloatingPointError); a negative regularisation (Quu_reg not PD: ok = False); an overflowing B_k.  The
+    thread-per-problem kernel runs the reference sequence only: gains, flags and error codes must be identical."""
+    from hop import _cabi
+    lib = _cabi.require_device()
+    g = golden("case_" + name)
+    case = cases.make_case(name, N=int(g["N"]))
+    Bsz = 4
+    A = np.repeat(g["A_fwd"][None], Bsz, 0); Bm = np.repeat(g["B_fwd"][None], Bsz, 0)
+    X = np.repeat(g["X"][None], Bsz, 0); U = np.repeat(g["U"][None], Bsz, 0)
+    T = np.full(Bsz, min(40, int(g["N"])), np.int32)
+    A[1, 17, 0, 1] = np.inf
+    lm = np.array([1e-3, 1e-3, -1e9, 1e-3])
+    Bm[3, 9] *= 1e200
+    out = {}
+    try:
+        for variant in (2, 1):
+            lib.hop_test_set_backward_variant(variant)
+            r = api.backward_linesearch_batched(case, _t(A), _t(Bm), _t(X), _t(U), torch.as_tensor(T), lm)
+            out[variant] = {k: v.cpu().numpy() for k, v in r.items()}
+    finally:
+        lib.hop_test_set_backward_variant(0)
+    assert out[2]["ok"][0] == 1 and out[2]["ok"][2] == 0 and out[2]["ok"][1] == 0
+    for key in ("k", "K", "ok", "err", "X_new", "U_new", "J_new", "accepted"):
+        assert np.array_equal(np.nan_to_num(out[2][key].astype(float), nan=-1.0, posinf=-2.0, neginf=-3.0),
+                              np.nan_to_num(out[1][key].astype(float), nan=-1.0, posinf=-2.0, neginf=-3.0)), key
+
+
 @pytest.mark.parametrize("name", ["Quadrotor", "Segway_Balance", "DoubleIntegrator"])
 def test_warp_and_thread_backward_kernels_agree_bit_for_bit(name):
     """backward_pass_truncated has two device mappings in the reference's summation order (one warp per problem, elements of
