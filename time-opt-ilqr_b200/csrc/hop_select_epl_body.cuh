@@ -65,8 +65,8 @@ HOP_DEVICE double sym(double v, int r, int c) { return 0.5 * (v + at(v, c * D + 
 
 // One Gauss-Jordan inversion attempt (hop::gj_attempt element for element).  The pivot is the same value on every
 // lane, so the returned flag is warp-uniform.  (Forming the next pivot on every lane from the pre-update entries -- same
-// bits, one shuffle latency less per elimination step -- was measured: one-warp kernel -3 %, pipeline unchanged, at three
-// more shuffles per pivot on a shuffle unit the pipeline already keeps ~40 % busy.  Not kept.)
+// bits, one shuffle latency less per elimination step -- was measured three times: one-warp kernel -3 %, pipeline unchanged or slower,
+// also when applied to the prefix warp's inversion only: three more shuffles per pivot cost more than the latency saved.  Not kept.)
 template <int D>
 HOP_DEVICE bool gj_attempt(double& a, int r, int c) {
     bool ok = true;
@@ -433,13 +433,25 @@ HOP_DEVICE void wsp_stage_role(const FusedArgs& p, int b, int role, double* lu, 
     }
 }
 
-// the recursion: one warp, every step
+// the recursion: one warp, every step.  Only Gbar is loop-carried through the inversion (gb -> W -> gb); the (Ebar, Fbar) update of
+// step k needs W_k but nothing of step k+1 needs it before ITS products, so it is deferred by one step and placed in the same
+// basic block as the first Gauss-Jordan attempt of step k+1 -- the compiler interleaves the three products with the pivot chain
+// (a reciprocal and two shuffle latencies per pivot, otherwise idle issue slots).  The prefix of step k is published one
+// inversion later; the queries are off the critical path.  Same operations on the same operands: identical bits.
 template <int D, int M>
 HOP_DEVICE void wsp_prefix_role(const FusedArgs& p, double* lu, const double* stage_ring, double* prefix_ring, int& status) {
     Geo<D> L;
     L.init();
     const int lane = L.lane, r = L.r, c = L.c;
     double eb = 0.0, fb = 0.0, gb = 0.0;
+    double gb_pub = 0.0, wv_prev = 0.0, f_prev = 0.0;       // state of the step whose (Ebar, Fbar) update / publication is pending
+    auto publish = [&](int k, double ebv, double fbv, double gbv) {
+        const int q = k % kWspQueryWarps;
+        if (k >= kWspQueryWarps) bar_wait(kBarPrefixEmpty + q);     // query warp q has read step k - kWspQueryWarps
+        double* dst = prefix_ring + q * 96;
+        dst[lane] = ebv; dst[32 + lane] = fbv; dst[64 + lane] = gbv;
+        bar_arrive(kBarPrefixFull + q);
+    };
     for (int k = 0; k < p.T_max; ++k) {
         const int slot = k % kWspStageRing;
         bar_wait(kBarStageFull + slot);
@@ -448,25 +460,40 @@ HOP_DEVICE void wsp_prefix_role(const FusedArgs& p, double* lu, const double* st
         if (k + kWspStageRing < p.T_max) bar_arrive(kBarStageEmpty + slot);
         if (k == 0) {
             eb = e; fb = f; gb = g;
-        } else {
-            const double s = sym<D>(e + gb, r, c);
-            const double wv = chol_inv<D>(s, r, c, L.act, lu, p.jitter, p.max_tries, status);      // W = chol_inv(E_k + Gbar)  (:72)
-            const double t1 = mul_nn<D>(fb, wv, r, c);
-            const double acc = mul_nt<D>(t1, fb, r, c);
-            const double eb_new = eb - acc;
-            const double fb_new = mul_nn<D>(t1, f, r, c);
-            const double t2 = mul_tn<D>(f, wv, r, c);
-            const double acc2 = mul_nn<D>(t2, f, r, c);
-            const double gb_new = g - acc2;
-            fb = fb_new;
-            eb = sym<D>(eb_new, r, c);
-            gb = sym<D>(gb_new, r, c);
+            gb_pub = g;
+            continue;                                                // published at the top of step 1 (or after the loop)
         }
-        const int q = k % kWspQueryWarps;
-        if (k >= kWspQueryWarps) bar_wait(kBarPrefixEmpty + q);     // query warp q has read step k - kWspQueryWarps
-        double* dst = prefix_ring + q * 96;
-        dst[lane] = eb; dst[32 + lane] = fb; dst[64 + lane] = gb;
-        bar_arrive(kBarPrefixFull + q);
+        // ---- one basic block: first attempt of W = chol_inv(E_k + Gbar) (:72)  ||  (Ebar, Fbar) update of step k-1 (:73-74)
+        const double s = sym<D>(e + gb, r, c);
+        double wv = s + ((r == c) ? p.jitter : 0.0);
+        const bool first_ok = gj_attempt<D>(wv, r, c);
+        if (k >= 2) {
+            const double t1 = mul_nn<D>(fb, wv_prev, r, c);          // Fbar W
+            const double acc = mul_nt<D>(t1, fb, r, c);              // (Fbar W) Fbar^T
+            const double fb_new = mul_nn<D>(t1, f_prev, r, c);       // (Fbar W) F_k
+            eb = sym<D>(eb - acc, r, c);
+            fb = fb_new;
+        }
+        if (!first_ok) wv = chol_inv<D>(s, r, c, L.act, lu, p.jitter, p.max_tries, status);   // the ladder, from its first rung
+        publish(k - 1, eb, fb, gb_pub);
+        // ---- Gbar of step k (:75)
+        const double t2 = mul_tn<D>(f, wv, r, c);                    // F_k^T W
+        const double acc2 = mul_nn<D>(t2, f, r, c);                  // (F_k^T W) F_k
+        gb = sym<D>(g - acc2, r, c);
+        gb_pub = gb;
+        wv_prev = wv;
+        f_prev = f;
+    }
+    if (p.T_max >= 1) {
+        const int k = p.T_max - 1;
+        if (k >= 1) {                                                // pending (Ebar, Fbar) update of the last step
+            const double t1 = mul_nn<D>(fb, wv_prev, r, c);
+            const double acc = mul_nt<D>(t1, fb, r, c);
+            const double fb_new = mul_nn<D>(t1, f_prev, r, c);
+            eb = sym<D>(eb - acc, r, c);
+            fb = fb_new;
+        }
+        publish(k, eb, fb, gb_pub);
     }
 }
 
