@@ -223,7 +223,7 @@ int hop_test_set_generic_pre(int on);
  * Gauss-Jordan sweep of a diagonal matrix computes anyway), 0 = by the sweep like any other block; identical bits.  Returns the
  * previous value. */
 int hop_test_set_generic_diag(int on);
-/* Test hook: fused selection kernel of the small systems (n <= 4).  0 [default] = by batch size: up to $HOP_WSP_MAX_BATCH = 296
+/* Test hook: fused selection kernel of the small systems (n <= 4).  0 [default] = by batch size: up to $HOP_WSP_MAX_BATCH = 592
  * instances one problem per CTA as a warp-specialised pipeline (stage / prefix / query warps, one matrix element per lane), up to
  * $HOP_EPL_MAX_BATCH = 1024 one warp per problem (one element per lane), a lane group per problem above; 1 = lane group,
  * 2 = pipeline, 3 = one warp per problem.  All three perform the same IEEE operations per element: identical bits.  Returns the
