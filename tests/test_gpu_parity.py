@@ -540,9 +540,13 @@ def test_one_pass_backward_gains_fall_back_to_the_reference_sequence(name):
     finally:
         lib.hop_test_set_backward_variant(0)
     assert out[2]["ok"][0] == 1 and out[2]["ok"][2] == 0 and out[2]["ok"][1] == 0
-    for key in ("k", "K", "ok", "err", "X_new", "U_new", "J_new", "accepted"):
-        assert np.array_equal(np.nan_to_num(out[2][key].astype(float), nan=-1.0, posinf=-2.0, neginf=-3.0),
-                              np.nan_to_num(out[1][key].astype(float), nan=-1.0, posinf=-2.0, neginf=-3.0)), key
+    flat = lambda a: np.nan_to_num(a.astype(float), nan=-1.0, posinf=-2.0, neginf=-3.0)   # noqa: E731
+    for key in ("ok", "err", "accepted"):
+        assert np.array_equal(out[2][key], out[1][key]), key
+    good = out[2]["ok"] == 1                         # the line search leaves X_new / U_new / J_new of a failed backward pass untouched
+    assert np.array_equal(flat(out[2]["k"]), flat(out[1]["k"])) and np.array_equal(flat(out[2]["K"]), flat(out[1]["K"]))
+    for key in ("X_new", "U_new", "J_new"):
+        assert np.array_equal(flat(out[2][key][good]), flat(out[1][key][good])), key
 
 
 @pytest.mark.parametrize("name", ["Quadrotor", "Segway_Balance", "DoubleIntegrator"])
