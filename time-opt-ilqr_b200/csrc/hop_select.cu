@@ -69,13 +69,6 @@ static int launch_fused(const FusedArgs& p, cudaStream_t st) {
 // ---- one problem per warp, DMMA register fragments (d in 9..16) -----------------------------------
 constexpr int kMmaWarps = 4;   // warps (= problems) per CTA
 
-template <int D, int M>
-__global__ void __launch_bounds__(kMmaWarps * 32) k_select_generic_mma(const SelectArgs p) {
-    extern __shared__ __align__(16) double smem[];
-    const int warp = threadIdx.x >> 5;
-    mma::select_generic_body<D, M>(p, blockIdx.x * kMmaWarps + warp, smem + (size_t)warp * mma::kWarpScratch);
-}
-
 // sequential FAST body out of line: the cold path of the pipelined kernel (jitter ladder, LU, status word)
 template <int D, int M>
 __device__ __noinline__ void select_fused_seq_cold(const FusedArgs& p, int b, double* scratch, const double* cst) {
@@ -257,13 +250,6 @@ static int launch_generic_pipe(const SelectArgs& p, cudaStream_t st) {
     return rc_all;
 }
 
-template <int D, int M>
-static int launch_generic_mma(const SelectArgs& p, cudaStream_t st) {
-    const size_t smem = sizeof(double) * (size_t)kMmaWarps * mma::kWarpScratch;
-    const int grid = (p.B + kMmaWarps - 1) / kMmaWarps;
-    k_select_generic_mma<D, M><<<grid, kMmaWarps * 32, smem, st>>>(p);
-    return check_launch("k_select_generic_mma");
-}
 // MINB = CTAs per SM the register allocation is bounded for (2 -> 255 regs, 3 -> 168, 4 -> 128).
 static int mma_min_blocks() {
     static int v = -1;
@@ -319,9 +305,8 @@ int dispatch_select_generic(int d, int m, int mode, const SelectArgs& p, cudaStr
     if (d == 3 && m == 1) return launch_generic<3, 1, 4>(p, st);
     if (d == 4 && m == 2) return launch_generic<4, 2, 4>(p, st);
     if (d == 5 && m == 1) return launch_generic<5, 1, 8>(p, st);
-    static const bool gseq = getenv("HOP_GENERIC_SEQ") && atoi(getenv("HOP_GENERIC_SEQ")) != 0;   // A/B switch: sequential sweep
-    if (d == 12 && m == 4) return gseq ? launch_generic_mma<12, 4>(p, st) : launch_generic_pipe<12, 4>(p, st);
-    if (d == 13 && m == 4) return gseq ? launch_generic_mma<13, 4>(p, st) : launch_generic_pipe<13, 4>(p, st);
+    if (d == 12 && m == 4) return launch_generic_pipe<12, 4>(p, st);
+    if (d == 13 && m == 4) return launch_generic_pipe<13, 4>(p, st);
     set_last_error("hop_select_f64: (d, m) not instantiated; supported: (3,1) (4,2) (5,1) (12,4) (13,4)");
     return HOP_E_UNSUPPORTED_DIMS;
 }
@@ -336,11 +321,8 @@ int dispatch_select_fused(int n, int m, const FusedArgs& p, cudaStream_t st) {
     if (n == 4 && m == 1) return launch_fused<5, 1, 8>(p, st);
     if (n == 12 && m == 4) {
         if (p.mode != HOP_MODE_FAST) return launch_fused_mma<13, 4, 0>(p, st);
-        // A/B switch: HOP_FAST_SEQ=1 runs the sequential FAST sweep (the pipelined kernel's cold path) for the whole batch.  The
-        // earlier schedules of the pipelined sweep (unrolled / looped with the shuffle exchange / one pivot per loop trip, template
-        // arguments 2..4) are no longer instantiated in the library; tests/emul still runs them as cross-checks of the same math.
-        static const bool seq = getenv("HOP_FAST_SEQ") && atoi(getenv("HOP_FAST_SEQ")) != 0;
-        if (seq) return launch_fused_mma<13, 4, 1>(p, st);
+        // (The sequential FAST sweep -- the pipelined kernel's out-of-line cold path -- and the earlier schedules of the pipelined
+        // sweep are no longer instantiated as kernels of their own; tests/emul still runs them as cross-checks of the same math.)
         return launch_fused_mma<13, 4, 5>(p, st);
     }
     set_last_error("hop_select_fused_f64: (n, m) not instantiated; supported: (2,1) (4,1) (12,4)");
